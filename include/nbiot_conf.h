@@ -1,0 +1,33 @@
+/*
+ * nbiot_conf.h -- construction-time configuration of one batch of simulated cells.
+ * Fields mirror the `conf` dict read by the reference's create_system
+ * (system/system_creator.py:24-44) plus the carrier count that the reference keeps in
+ * a module global (system/parameters.py:16,96-100) and the fixed capacities that
+ * replace the reference's unbounded Python containers.
+ */
+#ifndef NBIOT_CONF_H
+#define NBIOT_CONF_H
+
+#include <stdint.h>
+
+typedef struct nbiot_conf {
+    double ratio;             /* conf['ratio']: share of uniform (vs beta-burst) devices       */
+    double max_d;             /* conf['max_d'] cell range in km; <= 0 means default (10 km)    */
+    int32_t M;                /* conf['M']: devices per cell                                    */
+    int32_t buffer_lo;        /* conf['buffer_range'][0]                                        */
+    int32_t buffer_hi;        /* conf['buffer_range'][1]                                        */
+    int32_t reward_criteria;  /* NB_RW_* (conf['reward_criteria'])                             */
+    int32_t sort_by_loss;     /* conf['sort_criterium'] == 'loss' (default 't_connection')      */
+    int32_t sc_adjustment;    /* default 1 */
+    int32_t mcs_automatic;    /* default 1 */
+    int32_t ce_mcs_automatic; /* default 1 */
+    int32_t tx_all_buffer;    /* default 1 */
+    int32_t random_traffic;   /* conf['random'] */
+    int32_t n_carriers;       /* 1 or 2 (parameters.N_carriers) */
+    /* capacities (CUDA path only; the oracle grows its containers) */
+    int32_t ue_cap;           /* live-UE slots per instance (<= M suffices: closed population)  */
+    int32_t grid_w;           /* carrier look-ahead ring, columns, power of two                 */
+    int32_t hist_cap;         /* entries of incoming/delays/service_times kept per period       */
+} nbiot_conf_t;
+
+#endif /* NBIOT_CONF_H */

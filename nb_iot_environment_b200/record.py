@@ -1,0 +1,152 @@
+"""Host-side mirrors of the C structs in include/nbiot_record.h and include/nbiot_conf.h.
+
+`RECORD_DTYPE` is the per-instance decision record: the reward plus the `info` dict the
+reference assembles in NodeB.get_node_info (reference system/node_b.py:278-418; schema in
+SURVEY.md App. D).  `make_conf` turns the reference's `conf` dict
+(system/system_creator.py:24-44) into the C struct.
+"""
+import ctypes
+
+import numpy as np
+
+MAX_OCC = 48
+STEP_LIST = 16
+N_ACTIONS = 23
+
+STATE_NAMES = ['Scheduling', 'NPRACH_update', 'RAR_window', 'RAR_window_end', 'Idle']   # NB_ST_* order
+STATE_IDS = {n: i for i, n in enumerate(STATE_NAMES)}
+
+FAULT_UE_SLOTS, FAULT_LOOKAHEAD, FAULT_ACTION, FAULT_MCS_KEY, FAULT_EVENT_SLOTS, FAULT_LIST_TRUNC = 1, 2, 4, 8, 16, 32
+FAULT_FATAL_MASK = 0x1F
+
+# reward_criteria names of perf_monitor.py:29-38 -> NB_RW_*
+REWARD_IDS = {'throughput': 0, 'average_delay': 1, 'accumulated_delay': 2, 'users': 3,
+              'invd_users': 4, 'log_invd_users': 5}
+
+# NPRACH_items order (parameters.py:136-153)
+NPRACH_ITEMS = ['backoff', 'rar_window', 'mac_timer', 'transmax', 'panchor', 'th_C1', 'th_C0',
+                'period_C0', 'rep_C0', 'sc_C0', 'period_C1', 'rep_C1', 'sc_C1', 'period_C2', 'rep_C2', 'sc_C2']
+
+RECORD_DTYPE = np.dtype([
+    ('reward', '<f8'), ('loss', '<f8', 4), ('sinr', '<f8', 4),
+    ('detection_ratios', '<f8', 3), ('colision_ratios', '<f8', 3), ('msg3_detection', '<f8', 3),
+    ('msg3_sent', '<f8', 3), ('msg3_received', '<f8', 3), ('distribution', '<f8', 15),
+    ('RA_occupation', '<f8'), ('NPUSCH_occupation', '<f8'), ('NPRACH_occupation', '<f8'), ('av_delay', '<f8'),
+    ('time', '<i4'), ('state', '<i4'), ('total_ues', '<i4'), ('fault', '<i4'), ('n_sel', '<i4'),
+    ('ues', '<i4', 4), ('connection_time', '<i4', 4), ('buffer', '<i4', 4),
+    ('n_rx', '<i4'), ('n_err', '<i4'), ('n_unfit', '<i4'), ('n_acc', '<i4'),
+    ('rx_id', '<i4', STEP_LIST), ('rx_delay', '<i4', STEP_LIST), ('err_id', '<i4', STEP_LIST),
+    ('unfit_id', '<i4', STEP_LIST), ('acc_id', '<i4', STEP_LIST), ('acc_delay', '<i4', STEP_LIST),
+    ('ues_per_CE', '<i4', 3), ('RAR_in', '<i4', 3), ('RAR_sent', '<i4', 3), ('RAR_ids', '<i4', 3),
+    ('RAR_detected', '<i4', 3), ('RAR_failed', '<i4', 3),
+    ('valid_CE_control', '<i4'), ('NPDCCH_sf_left', '<i4'), ('total_departures', '<i4'),
+    ('action', '<i4', 3), ('nprach_conf', '<i4', 16), ('preambles', '<i4', 3),
+    ('departures', '<i4'), ('n_incoming', '<i4'), ('n_occ', '<i4', 3),
+    ('draws_lo', '<i4'), ('draws_hi', '<i4'), ('events', '<i4'),
+    ('det_hist', '<i2', (3, MAX_OCC)), ('col_hist', '<i2', (3, MAX_OCC)),
+    ('carrier_busy', 'u1', 40),
+])
+assert RECORD_DTYPE.itemsize == 1632
+
+FLOAT_FIELDS = [n for n in RECORD_DTYPE.names if RECORD_DTYPE[n].base == np.dtype('<f8')]
+INT_FIELDS = [n for n in RECORD_DTYPE.names if n not in FLOAT_FIELDS]
+# diagnostics that the Python reference cannot report the same way
+NON_PARITY_FIELDS = ('events', 'fault')
+
+
+class NbiotConf(ctypes.Structure):
+    _fields_ = [('ratio', ctypes.c_double), ('max_d', ctypes.c_double),
+                ('M', ctypes.c_int32), ('buffer_lo', ctypes.c_int32), ('buffer_hi', ctypes.c_int32),
+                ('reward_criteria', ctypes.c_int32), ('sort_by_loss', ctypes.c_int32),
+                ('sc_adjustment', ctypes.c_int32), ('mcs_automatic', ctypes.c_int32),
+                ('ce_mcs_automatic', ctypes.c_int32), ('tx_all_buffer', ctypes.c_int32),
+                ('random_traffic', ctypes.c_int32), ('n_carriers', ctypes.c_int32),
+                ('ue_cap', ctypes.c_int32), ('grid_w', ctypes.c_int32), ('hist_cap', ctypes.c_int32)]
+
+
+_UNSUPPORTED_TRUE = ('animate_carrier', 'animate_stats', 'traces', 'resource_monitor', 'clustered')
+_KNOWN = {'ratio', 'M', 'buffer_range', 'reward_criteria', 'sort_criterium', 'levels', 'max_d', 'sc_adjustment',
+          'mcs_automatic', 'ce_mcs_automatic', 'tx_all_buffer', 'animate_carrier', 'statistics', 'animate_stats',
+          'traces', 'resource_monitor', 'random', 'clustered', 'cluster_ues', 'cluster_prob', 'cluster_range'}
+
+
+def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256):
+    """conf dict with the reference's keys and defaults (system_creator.py:24-44) -> NbiotConf."""
+    unknown = set(conf) - _KNOWN
+    if unknown:
+        raise KeyError(f'unknown conf keys {sorted(unknown)}')
+    for k in _UNSUPPORTED_TRUE:
+        if conf.get(k, False):
+            raise NotImplementedError(f"conf['{k}']=True is outside the batched hot path (SURVEY.md section 8)")
+    crit = conf['reward_criteria']
+    if crit not in REWARD_IDS:
+        raise NotImplementedError(f"reward_criteria '{crit}' is not supported")
+    sort = conf.get('sort_criterium', 't_connection')
+    if sort not in ('t_connection', 'loss'):
+        raise NotImplementedError(f"sort_criterium '{sort}' is not supported")
+    if n_carriers not in (1, 2):
+        raise ValueError('n_carriers must be 1 or 2')
+    if grid_w & (grid_w - 1) or grid_w < 256:
+        raise ValueError('grid_w must be a power of two >= 256')
+    M = int(conf['M'])
+    c = NbiotConf()
+    c.ratio = float(conf['ratio'])
+    c.max_d = float(conf.get('max_d') or 0.0)
+    c.M = M
+    c.buffer_lo, c.buffer_hi = int(conf['buffer_range'][0]), int(conf['buffer_range'][1])
+    c.reward_criteria = REWARD_IDS[crit]
+    c.sort_by_loss = int(sort == 'loss')
+    c.sc_adjustment = int(conf.get('sc_adjustment', True))
+    c.mcs_automatic = int(conf.get('mcs_automatic', True))
+    c.ce_mcs_automatic = int(conf.get('ce_mcs_automatic', True))
+    c.tx_all_buffer = int(conf.get('tx_all_buffer', True))
+    c.random_traffic = int(conf.get('random', False))
+    c.n_carriers = n_carriers
+    c.ue_cap = int(ue_cap if ue_cap is not None else M)
+    c.grid_w = int(grid_w)
+    c.hist_cap = int(hist_cap)
+    return c
+
+
+def record_to_info(rec, hist=None):
+    """One record -> the reference's `info` dict (same keys and value types as node_b.py:299-408)."""
+    state = STATE_NAMES[int(rec['state'])]
+    info = {'time': int(rec['time']), 'state': state, 'total_ues': int(rec['total_ues']),
+            'carrier_state': 1.0 - rec['carrier_busy'].astype(np.float64) / 12.0}
+    if state in ('Scheduling', 'RAR_window_end'):
+        n = int(rec['n_sel'])
+        info['ues'] = [int(v) for v in rec['ues'][:n]]
+        info['connection_time'] = [int(v) if i < n else 0.0 for i, v in enumerate(rec['connection_time'])]
+        info['loss'] = [float(v) for v in rec['loss']]
+        info['sinr'] = [float(v) for v in rec['sinr']]
+        info['buffer'] = [int(v) if i < n else 0.0 for i, v in enumerate(rec['buffer'])]
+        k = min(int(rec['n_rx']), STEP_LIST)
+        info['receptions'] = {int(a): int(b) for a, b in zip(rec['rx_id'][:k], rec['rx_delay'][:k])}
+        info['errors'] = [int(v) for v in rec['err_id'][:min(int(rec['n_err']), STEP_LIST)]]
+        info['unfit'] = [int(v) for v in rec['unfit_id'][:min(int(rec['n_unfit']), STEP_LIST)]]
+        k = min(int(rec['n_acc']), STEP_LIST)
+        info['access'] = {int(a): int(b) for a, b in zip(rec['acc_id'][:k], rec['acc_delay'][:k])}
+    elif state == 'RAR_window':
+        for key in ('ues_per_CE', 'RAR_in', 'RAR_sent', 'RAR_ids', 'RAR_detected', 'RAR_failed'):
+            info[key] = [int(v) for v in rec[key]]
+        info['valid_CE_control'] = bool(rec['valid_CE_control'])
+        info['NPDCCH_sf_left'] = int(rec['NPDCCH_sf_left'])
+        info['total_departures'] = int(rec['total_departures'])
+        conf = dict(zip(NPRACH_ITEMS, (int(v) for v in rec['nprach_conf'])))
+        for key in ('sc_C0', 'sc_C1', 'sc_C2', 'period_C0', 'period_C1', 'period_C2', 'th_C1', 'th_C0'):
+            info[key] = conf[key]
+        info['action'] = [int(v) for v in rec['action']]
+        info['final_action'] = info['action']
+    else:
+        for key in ('detection_ratios', 'colision_ratios', 'msg3_detection', 'msg3_sent', 'msg3_received', 'distribution'):
+            info[key] = [float(v) for v in rec[key]]
+        info['preambles'] = [int(v) for v in rec['preambles']]
+        info['NPRACH_detection'] = [[int(v) for v in rec['det_hist'][ce][:min(int(rec['n_occ'][ce]), MAX_OCC)]] for ce in range(3)]
+        info['NPRACH_collision'] = [[int(v) for v in rec['col_hist'][ce][:min(int(rec['n_occ'][ce]), MAX_OCC)]] for ce in range(3)]
+        for key in ('RA_occupation', 'NPUSCH_occupation', 'NPRACH_occupation', 'av_delay'):
+            info[key] = float(rec[key])
+        info['departures'] = int(rec['departures'])
+        if hist is not None:
+            info['incoming'], info['delays'], info['service_times'] = hist
+        info['NPRACH conf'] = dict(zip(NPRACH_ITEMS, (int(v) for v in rec['nprach_conf'])))
+    return info
