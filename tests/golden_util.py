@@ -1,0 +1,65 @@
+"""Loading and comparing the golden fixtures of tests/golden (made by tools/gen_golden.py from the
+unmodified Python reference)."""
+import glob
+import json
+import os
+
+import numpy as np
+
+from nb_iot_environment_b200.record import RECORD_DTYPE, FLOAT_FIELDS, INT_FIELDS, NON_PARITY_FIELDS
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+
+# float fields are compared to the reference's numpy/libm/scipy arithmetic: nbiot_math.h agrees to ~1e-15,
+# the contract (BASELINE.json north_star) is 1e-5 relative
+REF_RTOL = 1e-9
+
+
+class Golden:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+        self.meta = json.loads(bytes(z['meta']).decode())
+        assert self.meta['record_itemsize'] == RECORD_DTYPE.itemsize
+        assert self.meta['record_descr'] == str(RECORD_DTYPE.descr), 'record layout changed: regenerate the fixtures'
+        raw = z['records']
+        self.records = np.ascontiguousarray(raw).view(RECORD_DTYPE).reshape(raw.shape[0], raw.shape[1])
+        self.actions = z['actions'].astype(np.int32)
+        self.conf = self.meta['conf']
+        self.n_carriers = self.meta['n_carriers']
+        self.seeds = self.meta['seeds']
+        self.decisions = self.meta['decisions']
+        self.counters = self.meta['counters']
+        self.z = z
+
+    def hist(self, si):
+        """per NPRACH_update decision: (incoming, delays, service_times) in order of occurrence"""
+        inc, il = self.z[f'incoming_{si}'], self.z[f'incoming_len_{si}']
+        dl, sv, ll = self.z[f'delays_{si}'], self.z[f'service_{si}'], self.z[f'delays_len_{si}']
+        out, a, b = [], 0, 0
+        for n_i, n_d in zip(il, ll):
+            out.append((inc[a:a + n_i], dl[b:b + n_d], sv[b:b + n_d]))
+            a += n_i
+            b += n_d
+        return out
+
+    def events(self, si):
+        return self.z[f'events_{si}']
+
+
+def record_diff(a, b, rtol=0.0, skip=NON_PARITY_FIELDS):
+    """list of (field, a, b) that differ: integers exactly, floats exactly (rtol=0) or within rtol"""
+    out = []
+    for n in INT_FIELDS:
+        if n in skip:
+            continue
+        if not np.array_equal(a[n], b[n]):
+            out.append((n, a[n], b[n]))
+    for n in FLOAT_FIELDS:
+        if rtol == 0.0:
+            same = np.array_equal(a[n], b[n])
+        else:
+            same = np.allclose(a[n], b[n], rtol=rtol, atol=1e-12)
+        if not same:
+            out.append((n, a[n], b[n]))
+    return out

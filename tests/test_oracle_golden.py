@@ -1,0 +1,37 @@
+"""The CPU oracle (oracle/nbiot_oracle.c) against the golden traces of the unmodified Python
+reference: integer fields bit-exact, float fields to 1e-9 relative, same number of random draws."""
+import numpy as np
+import pytest
+
+from golden_util import CASES, Golden, record_diff, REF_RTOL
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_oracle_replays_reference_trace(case, oracle_lib):
+    from oracle.oracle_py import OracleCell
+    g = Golden(case)
+    for si, seed in enumerate(g.seeds):
+        cell = OracleCell(g.conf, seed, n_carriers=g.n_carriers)
+        cell.enable_event_log()
+        rec = cell.reset()
+        assert not record_diff(g.records[si, 0], rec, rtol=REF_RTOL)
+        hists = g.hist(si)
+        hi = 1 if g.records[si, 0]['state'] == 1 else 0      # the reset record is an NPRACH_update flavour
+        for d in range(g.decisions):
+            rec = cell.step(g.actions[si, d])
+            diff = record_diff(g.records[si, d + 1], rec, rtol=REF_RTOL)
+            assert not diff, f'{case} seed {seed} decision {d + 1}: {diff[:4]}'
+            if rec['state'] == 1:
+                inc, dl, sv = cell.hist()
+                ginc, gdl, gsv = hists[hi]
+                hi += 1
+                assert np.array_equal(dl, gdl) and np.array_equal(sv, gsv)
+                assert np.allclose(inc, ginc, rtol=REF_RTOL, atol=0)
+        c, gc = cell.counters(), g.counters[si]
+        for k, v in gc.items():
+            if k == 'av_delay':
+                assert c[k] == pytest.approx(v, rel=REF_RTOL)
+            else:
+                assert c[k] == v, k
+        ev = g.events(si)
+        assert np.array_equal(cell.event_log()[:len(ev)], ev)   # same pops in the same (time, seq) order
