@@ -1,0 +1,210 @@
+/*
+ * nbiot_state.h -- per-instance state of the batched NB-IoT cell simulator as it lives
+ * in HBM (and, for the hot header + carrier grid, in shared memory while a kernel runs).
+ *
+ * The reference keeps one cell in Python objects: a heap of events
+ * (system/event_manager.py:45-86), ordered lists / dicts of UE objects
+ * (system/population.py:64-70, system/node_b.py:147-152), a boolean 12 x W grid
+ * (system/carrier.py:430-444).  Here one instance is
+ *   - a fixed-size header (NbHdr): clock, FSM, counters, system-event slots, NPRACH
+ *     resource records, per-epoch info scratch;
+ *   - a ring of 12-bit column masks per carrier (the look-ahead grid);
+ *   - three random-access lists of 16-byte entries kept in list order (order is
+ *     semantic: it pairs preambles with UEs and picks the msg3 grantee);
+ *   - the connected queue as 16-byte entries kept sorted by (sort key, insertion stamp);
+ *   - the contention set (UEs between msg3 grant and msg4 / MAC timeout);
+ *   - a pool of 64-byte UE records addressed by slot, with a free-slot stack;
+ *   - the per-period info lists (incoming / delays / service_times) and the per-occasion
+ *     NPRACH histories.
+ * All arrays are instance-major so that the warp that owns an instance reads contiguous
+ * memory. Capacities are fixed at creation; exceeding one raises a per-instance fault.
+ */
+#ifndef NBIOT_STATE_H
+#define NBIOT_STATE_H
+
+#include <stdint.h>
+#include "nbiot_conf.h"
+#include "nbiot_record.h"
+
+#define NB_EV_POOL 64        /* pending RAR_window_end / Msg3 / NPUSCH_end events            */
+#define NB_OCC_RING 32       /* pending NPRACH occasions per CE level (look-ahead / 80 sf)   */
+#define NB_RAR_WIN 8         /* open RAR windows per CE level (300 sf window / 80 sf period) */
+#define NB_SCLOG 16          /* non-anchor NPRACH starts remembered (2-carrier cells)        */
+#define NB_RA_SLACK 64       /* tombstones tolerated in a random-access list                 */
+
+/* event types kept in the generic pool */
+enum { NB_EV_NONE = 0, NB_EV_RAR_END = 1, NB_EV_MSG3 = 2, NB_EV_NPUSCH_END = 3 };
+
+/* containers a UE can be in */
+enum { NB_IN_FREE = 0, NB_IN_RA = 1, NB_IN_CONTENTION = 2, NB_IN_CONNECTED = 3, NB_IN_SCHEDULED = 4 };
+
+/* 64-bit event key: (time << 32) | insertion count -- the heap order of the reference */
+#define NB_KEY(t, s) (((uint64_t)(uint32_t)(t) << 32) | (uint64_t)(uint32_t)(s))
+#define NB_KEY_NONE 0xFFFFFFFFFFFFFFFFULL
+
+typedef struct {            /* 16 B: one pending system event */
+    uint64_t key;
+    int32_t aux;            /* RAR_END: rar_w_id ; MSG3 / NPUSCH_END: UE slot */
+    uint8_t type, ce, pad0, pad1;
+} NbEvent;
+
+typedef struct {            /* 12 B: one NPRACH occasion generated with its look-ahead column */
+    int32_t t_start;        /* NPRACH_start fires at t_start (seq), NPRACH_end at t_start + N_sf (seq + 1) */
+    uint32_t seq;
+    uint16_t N_sf;          /* snapshot of the configuration in force when the column was generated */
+    uint8_t N_sc, pad;
+} NbOccasion;
+
+typedef struct {            /* 24 B: carrier.py NprachResource (:293-299, :339-343) */
+    int32_t t_start, t_next, sf_to_go, t_offset;
+    int16_t periodicity, N_sf;
+    uint8_t N_sc, sc_offset;
+    uint16_t mask;          /* subcarrier mask of the running NPRACH */
+} NbResource;
+
+typedef struct {            /* 16 B: entry of a random-access list (population.ra_lists) */
+    uint32_t wake_t;        /* BACKOFF: (wake_t, wake_seq) = key of its Backoff_end ; RA: preamble scratch */
+    uint32_t wake_seq;
+    int32_t rar_w_id;
+    uint16_t slot;
+    uint8_t st_ce;          /* UE state (low nibble) | CE_level << 4 ; 0xFF = removed (tombstone) */
+    uint8_t attempts;       /* ra_attempts, saturating */
+} NbRaEntry;
+#define NB_RA_TOMB 0xFFu
+
+typedef struct {            /* 16 B: entry of the connected queue, kept sorted by (k1, order) */
+    uint64_t k1;            /* t_connection, or the bits of loss when sort_criterium == 'loss' */
+    uint32_t order;         /* dict insertion stamp */
+    uint16_t slot;
+    uint8_t ce, pad;
+} NbConnEntry;
+
+typedef struct {            /* 16 B: UE in contention resolution; key = its MAC_timer event */
+    uint64_t key;
+    int32_t ue_id;
+    uint16_t slot, pad;
+} NbContEntry;
+
+typedef struct {            /* 64 B: reference system/user.py:35-70 minus never-read fields */
+    double loss, sinr;
+    int32_t id, t_arrival, t_connection, timestamp, acked_data, rar_w_id;
+    uint16_t buffer, retx_buffer, bits, tbs;
+    uint8_t I_tbs, N_rep, N_ru, CE_level, state, attempts, beta, new_data;
+    uint8_t where, pad[7];
+} NbUe;
+
+typedef struct {            /* per-occasion NPRACH histories of the current update period (cold) */
+    int16_t det[3][NBIOT_MAX_OCC];
+    int16_t col[3][NBIOT_MAX_OCC];
+} NbOccHist;
+
+typedef struct NbHdr {
+    /* ---- clock, FSM, random stream ---- */
+    uint64_t seed, draws;
+    uint64_t cur_key;                 /* key of the event being handled (orders lazily retired Backoff_end) */
+    int32_t time, state, fault;
+    uint32_t seq;                     /* event insertion counter (event_manager.py:48) */
+    int32_t events;
+    int32_t NPDCCH_sf_left, valid_CE_control, total_departures;
+    int32_t action3[3];
+    uint64_t ev_npdcch, ev_update;    /* keys of the two singleton NodeB events */
+    int32_t cur_ce, cur_wid, cur_t;   /* payload of the RAR_window_end being decided */
+    uint8_t ctrl_action[24];          /* the controller's shared action vector (controller.py:33) */
+    /* ---- NPRACH configuration ---- */
+    uint8_t nprach_conf[16];          /* NPRACH_items order */
+    int32_t RAR_window_size[3];
+    int32_t msg3_nrep[3];
+    /* ---- RAR bookkeeping (node_b.py:134-144) ---- */
+    int32_t rar_n[3];
+    int32_t RAR_UEs[3][NB_RAR_WIN], RAR_w_ids[3][NB_RAR_WIN];
+    int32_t RAR_in[3], RAR_ids[3], RAR_attmp[3], RAR_sent[3], RAR_detected[3], RAR_failed[3];
+    int32_t m3_cnt[3], m3_sent_sum[3], m3_recv_sum[3];
+    double m3_eff_sum[3];
+    int32_t occ_n[3], det_sum[3], col_sum[3];
+    double distribution[15];
+    int32_t k_dist;
+    /* ---- scheduling queue ---- */
+    int32_t n_sel;
+    int32_t sel_slot[4];
+    int32_t conn_n, cont_n, ra_n[3], n_scheduled, free_top;
+    uint32_t conn_order;
+    uint64_t next_mac;                /* cached min key over the contention set, NB_KEY_NONE if unknown/empty */
+    int32_t next_mac_idx, mac_valid;
+    /* ---- carrier ---- */
+    int32_t t_now, t_ahead;
+    NbResource res[2][3];
+    int32_t occ_head_start[3], occ_head_end[3], occ_tail[3];   /* ring cursors (monotone counters) */
+    NbOccasion occ[3][NB_OCC_RING];
+    int32_t sclog_n;
+    int32_t sclog_t[NB_SCLOG];
+    uint8_t sclog_sc[NB_SCLOG][4];
+    /* ---- population / access procedure ---- */
+    int32_t ue_count, CE_thresholds[2], preamble_trans_max, MAC_timer;
+    double probability_anchor;
+    int32_t detected_pre[3], collided_pre[3], contenders[3], RAR_counter[3];
+    /* ---- traffic generator ---- */
+    int32_t M_uniform, M_beta, M_beta_max, gen_t, gen_counter, pad_g;
+    double gen_p;
+    /* ---- performance monitor ---- */
+    int32_t perf_t, error_count, attempts_count, thr_count;
+    int64_t total_bits, msg3_resources, NPUSCH_resources, NPRACH_resources;
+    int32_t ue_arrivals[3], ue_departures[3], backoffs[3], ue_connections;
+    double av_delay;
+    int32_t n_rx, n_err, n_unfit, n_acc;
+    int32_t rx_id[NBIOT_STEP_LIST], rx_delay[NBIOT_STEP_LIST], err_id[NBIOT_STEP_LIST];
+    int32_t unfit_id[NBIOT_STEP_LIST], acc_id[NBIOT_STEP_LIST], acc_delay[NBIOT_STEP_LIST];
+    double rx_sum, rx_inv_sum, rx_log_sum;          /* running reward terms over this epoch's receptions */
+    int32_t n_incoming, n_departures;
+    int64_t sum_delays;
+    int64_t subframes_done;           /* simulated time advanced since reset (the throughput unit) */
+    /* ---- preamble scratch (NPRACH pass) ---- */
+    uint32_t pre_once[8], pre_twice[8];
+    /* ---- pending system events ---- */
+    uint64_t pool_free;               /* bit i set: pool[i] is free */
+    NbEvent pool[NB_EV_POOL];
+} NbHdr;
+
+/* device-side controller tables: the multi-agent split of reference controller.py:234-288 with
+ * DummyAgent internal agents (control_agents.py:83-113) compiled into write lists */
+typedef struct nbiot_ctrl {
+    uint32_t ext_state_mask;          /* bit s set: an external decision is needed in NodeB state s */
+    int32_t ext_k;                    /* number of action items the external agent sets          */
+    uint8_t ext_a_mask[24];           /* their indices in the 23-vector                           */
+    int8_t ext_post[24];              /* writes of the `next` chain after the external action     */
+    int8_t state_writes[4][24];       /* fixed actions of the internal agents of each NodeB state */
+    uint8_t init_action[24];          /* Controller._initialize_action result                     */
+} nbiot_ctrl_t;
+
+/* byte offsets of the per-instance arrays inside the caller-owned state buffer */
+typedef struct {
+    int32_t n_inst, ue_cap, grid_w, hist_cap, n_carriers, ra_cap, pad0, pad1;
+    uint64_t off_hdr, off_grid, off_ra, off_conn, off_cont, off_ue, off_free, off_occ;
+    uint64_t off_incoming, off_delays, off_service, off_rec, off_scratch, total;
+} NbLayout;
+
+static inline uint64_t nb_align256(uint64_t x) { return (x + 255u) & ~(uint64_t)255u; }
+
+static inline NbLayout nb_make_layout(const nbiot_conf_t *c, int n)
+{
+    NbLayout L;
+    L.n_inst = n; L.ue_cap = c->ue_cap; L.grid_w = c->grid_w; L.hist_cap = c->hist_cap;
+    L.n_carriers = c->n_carriers >= 2 ? 2 : 1; L.ra_cap = c->ue_cap + NB_RA_SLACK; L.pad0 = L.pad1 = 0;
+    uint64_t o = 0, N = (uint64_t)n;
+    L.off_hdr = o;      o = nb_align256(o + N * sizeof(NbHdr));
+    L.off_grid = o;     o = nb_align256(o + N * (uint64_t)L.n_carriers * (uint64_t)L.grid_w * 2u);
+    L.off_ra = o;       o = nb_align256(o + N * 3u * (uint64_t)L.ra_cap * sizeof(NbRaEntry));
+    L.off_conn = o;     o = nb_align256(o + N * (uint64_t)L.ue_cap * sizeof(NbConnEntry));
+    L.off_cont = o;     o = nb_align256(o + N * (uint64_t)L.ue_cap * sizeof(NbContEntry));
+    L.off_ue = o;       o = nb_align256(o + N * (uint64_t)L.ue_cap * sizeof(NbUe));
+    L.off_free = o;     o = nb_align256(o + N * (uint64_t)L.ue_cap * 2u);
+    L.off_occ = o;      o = nb_align256(o + N * sizeof(NbOccHist));
+    L.off_incoming = o; o = nb_align256(o + N * (uint64_t)L.hist_cap * 8u);
+    L.off_delays = o;   o = nb_align256(o + N * (uint64_t)L.hist_cap * 4u);
+    L.off_service = o;  o = nb_align256(o + N * (uint64_t)L.hist_cap * 4u);
+    L.off_rec = o;      o = nb_align256(o + N * sizeof(nbiot_record_t));
+    L.off_scratch = o;  o = nb_align256(o + N * (uint64_t)L.ra_cap * 2u);
+    L.total = o;
+    return L;
+}
+
+#endif /* NBIOT_STATE_H */

@@ -870,6 +870,7 @@ typedef struct { int carrier, i, I_tbs, delay, N_sc, N_rep, N_ru; } SchedParams;
 
 static int scheduling_action(Oracle *o, const int32_t *a, int RAR_action, SchedParams *p)   /* action_reader.py:25-66 */
 {
+    if (a[NB_A_CARRIER] >= o->n_carriers || a[NB_A_CARRIER] < 0) { o->fault |= NBIOT_FAULT_ACTION; return 0; }   /* IndexError in the reference */
     p->carrier = a[NB_A_CARRIER]; p->i = a[NB_A_ID]; p->N_ru = a[NB_A_NRU];
     p->N_rep = nb_n_rep_list[a[NB_A_NREP]];
     int I_mcs = a[NB_A_IMCS];

@@ -1,0 +1,94 @@
+// CPU build of the device simulation core (nb_iot_environment_b200/csrc/nbiot_core.cuh) for
+// debugging without a GPU: same source, same state layout, lanes emulated (see nbiot_warp.h).
+// TEST AID ONLY: built and loaded by tests/, never by the package.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nbiot_core.cuh"
+
+struct Emu {
+    nbiot_conf_t conf;
+    nbiot_ctrl_t ctrl;
+    NbLayout L;
+    uint8_t *state;
+    const uint16_t *lut2;
+    const uint8_t *mcs;
+    int32_t *evlog; int evlog_cap;
+};
+
+static NbCtx make_ctx(Emu *e, int i)
+{
+    NbCtx c;
+    const NbLayout &L = e->L;
+    uint8_t *s = e->state;
+    c.h = (NbHdr *)(s + L.off_hdr) + i;
+    c.grid = (uint16_t *)(s + L.off_grid) + (size_t)i * L.n_carriers * L.grid_w;
+    for (int k = 0; k < 3; ++k) c.ra[k] = (NbRaEntry *)(s + L.off_ra) + ((size_t)i * 3 + k) * L.ra_cap;
+    c.conn = (NbConnEntry *)(s + L.off_conn) + (size_t)i * L.ue_cap;
+    c.cont = (NbContEntry *)(s + L.off_cont) + (size_t)i * L.ue_cap;
+    c.ue = (NbUe *)(s + L.off_ue) + (size_t)i * L.ue_cap;
+    c.free_stack = (uint16_t *)(s + L.off_free) + (size_t)i * L.ue_cap;
+    c.occ = (NbOccHist *)(s + L.off_occ) + i;
+    c.incoming = (double *)(s + L.off_incoming) + (size_t)i * L.hist_cap;
+    c.delays = (int32_t *)(s + L.off_delays) + (size_t)i * L.hist_cap;
+    c.service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
+    c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
+    c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
+    c.lut2 = e->lut2; c.mcs = e->mcs; c.conf = &e->conf;
+    c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
+    c.evlog = (e->evlog && i == 0) ? e->evlog : NULL; c.evlog_cap = e->evlog_cap;
+    return c;
+}
+
+extern "C" {
+
+int emu_lanes(void) { return NB_LANES; }
+int emu_hdr_size(void) { return (int)sizeof(NbHdr); }
+
+void *emu_create(const nbiot_conf_t *conf, int n_inst, const uint64_t *seeds, const uint16_t *lut2, const uint8_t *mcs, const nbiot_ctrl_t *ctrl)
+{
+    Emu *e = (Emu *)calloc(1, sizeof(Emu));
+    e->conf = *conf; e->ctrl = *ctrl; e->lut2 = lut2; e->mcs = mcs;
+    e->L = nb_make_layout(conf, n_inst);
+    e->state = (uint8_t *)calloc(1, e->L.total);
+    for (int i = 0; i < n_inst; ++i) { NbCtx c = make_ctx(e, i); nbc_construct(c, seeds[i], &e->ctrl); }
+    return e;
+}
+
+void emu_destroy(void *p) { Emu *e = (Emu *)p; free(e->state); free(e); }
+void emu_set_ctrl(void *p, const nbiot_ctrl_t *ctrl) { ((Emu *)p)->ctrl = *ctrl; }
+void emu_set_evlog(void *p, int32_t *buf, int cap) { Emu *e = (Emu *)p; e->evlog = buf; e->evlog_cap = cap; }
+
+void emu_reset(void *p)
+{
+    Emu *e = (Emu *)p;
+    for (int i = 0; i < e->L.n_inst; ++i) { NbCtx c = make_ctx(e, i); nbc_reset(c); }
+}
+
+// ext_actions: [n_inst][ext_k] or NULL; steps_out: [n_inst] or NULL
+void emu_advance(void *p, const uint8_t *ext_actions, int until_time, int max_steps, int32_t *steps_out)
+{
+    Emu *e = (Emu *)p;
+    for (int i = 0; i < e->L.n_inst; ++i) {
+        NbCtx c = make_ctx(e, i);
+        int s = nbc_controller_advance(c, &e->ctrl, ext_actions ? ext_actions + (size_t)i * e->ctrl.ext_k : NULL, until_time, max_steps);
+        if (steps_out) steps_out[i] = s;
+    }
+}
+
+const void *emu_records(void *p) { Emu *e = (Emu *)p; return e->state + e->L.off_rec; }
+const void *emu_state(void *p) { return ((Emu *)p)->state; }
+void emu_layout(void *p, NbLayout *out) { *out = ((Emu *)p)->L; }
+
+// PerfMonitor counters of instance i (same order as orc_get_counters)
+void emu_counters(void *p, int i, int64_t out[16], double *av_delay)
+{
+    Emu *e = (Emu *)p; NbCtx c = make_ctx(e, i); NbHdr *h = c.h;
+    for (int k = 0; k < 3; ++k) { out[k] = h->ue_arrivals[k]; out[3 + k] = h->ue_departures[k]; out[6 + k] = h->backoffs[k]; }
+    out[9] = h->ue_connections; out[10] = h->error_count; out[11] = h->attempts_count; out[12] = h->total_bits;
+    out[13] = (int64_t)h->draws; out[14] = h->events; out[15] = h->ue_count;
+    *av_delay = h->av_delay;
+}
+
+}
