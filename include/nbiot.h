@@ -1,0 +1,132 @@
+/*
+ * nbiot.h -- C ABI of libnbiot_b200.so, the B200-native batched NB-IoT cell simulator.
+ *
+ * The reference has no native code and no vector environment: one
+ * cell is a graph of Python objects built by create_system(rng, conf)
+ * (system/system_creator.py:22-59) and driven through Controller.reset()/step()
+ * (controller.py:132-143, :234-260) behind gym_system.Environment
+ * (gym-system/gym_system/environment.py:22-37). Each entry point below names the reference
+ * interface it replaces for a BATCH of n_inst independent cells; the Python binding a
+ * maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
+ * NBIOT_E_* code otherwise, with a message available from nbiot_last_error(); calls on one handle
+ * are stream-ordered and asynchronous unless stated; a handle is single-owner (no internal
+ * locking); there is no CPU fallback -- without a CUDA device every compute call fails.
+ */
+#ifndef NBIOT_H
+#define NBIOT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "nbiot_conf.h"
+#include "nbiot_record.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBIOT_ABI_VERSION 1
+
+#define NBIOT_E_INVALID (-1)   /* bad argument */
+#define NBIOT_E_CUDA (-2)      /* CUDA runtime error (text in nbiot_last_error) */
+#define NBIOT_E_NOGPU (-3)     /* no usable CUDA device */
+#define NBIOT_E_SIZE (-4)      /* caller-provided buffer too small */
+
+typedef struct nbiot_handle nbiot_handle_t;
+struct nbiot_ctrl;             /* controller write tables, include/nbiot_ctrl.h */
+
+/* one observation item of Controller.get_obs (controller.py:105-120): obs = min(1, value / norm) */
+typedef struct nbiot_obs_item {
+    int32_t offset;            /* byte offset of the first element inside nbiot_record_t          */
+    int32_t kind;              /* 0: int32, 1: double, 2: carrier_state (1 - busy_u8 / 12)         */
+    int32_t length;            /* number of elements                                              */
+    uint32_t state_mask;       /* NodeB states whose info dict holds the key (others give zeros)  */
+    double norm;               /* parameters.obs_dict normalisation constant                      */
+} nbiot_obs_item_t;
+
+#define NBIOT_N_STATS 24       /* length of the nbiot_reduce_stats vector, see nbiot_stat_index    */
+enum nbiot_stat_index {
+    NBIOT_STAT_ARRIVALS_CE0 = 0,   /* PerfMonitor.ue_arrivals[3]    (perf_monitor.py:52)  */
+    NBIOT_STAT_DEPARTURES_CE0 = 3, /* PerfMonitor.ue_departures[3]  (:55)                 */
+    NBIOT_STAT_BACKOFFS_CE0 = 6,   /* PerfMonitor.backoffs[3]       (:56)                 */
+    NBIOT_STAT_CONNECTIONS = 9,    /* ue_connections (:53)                                */
+    NBIOT_STAT_ERRORS = 10,        /* error_count (:43)                                   */
+    NBIOT_STAT_ATTEMPTS = 11,      /* attempts_count (:44)                                */
+    NBIOT_STAT_TOTAL_BITS = 12,    /* total_bits (:46)                                    */
+    NBIOT_STAT_SUBFRAMES = 13,     /* simulated subframes advanced since reset (throughput unit) */
+    NBIOT_STAT_EVENTS = 14,        /* events handled                                      */
+    NBIOT_STAT_DRAWS = 15,         /* random counters consumed                            */
+    NBIOT_STAT_FAULTED = 16,       /* instances stopped by a fatal fault                  */
+    NBIOT_STAT_LIVE_UES = 17,      /* UEs currently in the cell (sum over instances)      */
+    NBIOT_STAT_SUM_DELAY_X1000 = 18, /* sum of PerfMonitor.av_delay * departures * 1000 (fixed point) */
+    NBIOT_STAT_TRUNCATED = 19      /* instances with a truncated info list                */
+};
+
+int nbiot_abi_version(void);
+const char *nbiot_last_error(void);
+
+/* Bytes of device memory one batch needs. The CALLER allocates them (e.g. a torch uint8 tensor)
+ * and keeps ownership: the buffer is the complete simulation state, so saving it is a checkpoint. */
+size_t nbiot_state_bytes(const nbiot_conf_t *conf, int n_inst);
+size_t nbiot_hdr_bytes(void);
+
+/* replaces create_system(rng, conf) + Controller(node, agents) for n_inst cells
+ * (system/system_creator.py:22-59, controller.py:30-41). seeds/lut2/mcs are host pointers:
+ * seeds[n_inst] Philox keys, lut2 = uint16[7*8*501] (LUT2.csv), mcs = uint8[500*30*3]
+ * (loss_tbs_to_mcs.p), see tools/make_tables.py. */
+int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_dev, size_t state_bytes,
+                 const uint64_t *seeds, const uint16_t *lut2, const uint8_t *mcs, const struct nbiot_ctrl *ctrl,
+                 void *stream, nbiot_handle_t **out);
+int nbiot_destroy(nbiot_handle_t *h);
+
+/* replaces Controller.set_ext_agent / replace_agent / DummyAgent.set_action (controller.py:71-75, :122-130) */
+int nbiot_set_controller(nbiot_handle_t *h, const struct nbiot_ctrl *ctrl, void *stream);
+
+/* replaces Controller.reset -> NodeB.reset (controller.py:132-143, system/node_b.py:163-189) */
+int nbiot_reset(nbiot_handle_t *h, void *stream);
+
+/* replaces Controller.step + to_next_step (controller.py:234-288), or Controller.run_until (:185-195)
+ * when ext_actions is NULL. ext_actions: device uint8[n_inst][ext_k]. until_time < 0: no time bound. */
+int nbiot_advance(nbiot_handle_t *h, const uint8_t *ext_actions_dev, int until_time, int max_steps, void *stream);
+
+/* device pointer to nbiot_record_t[n_inst] (reward + info dict of NodeB.get_node_info, node_b.py:278-418)
+ * and to the per-period lists incoming (double) / delays / service_times (int32), hist_cap entries each */
+int nbiot_records_ptr(nbiot_handle_t *h, void **records_dev);
+int nbiot_hist_ptrs(nbiot_handle_t *h, void **incoming_dev, void **delays_dev, void **service_dev, int *hist_cap);
+
+/* replaces Controller.get_obs (controller.py:105-120): obs_dev = double[n_inst][sum(length)],
+ * reward_dev = double[n_inst] (either may be NULL) */
+int nbiot_gather_obs(nbiot_handle_t *h, const nbiot_obs_item_t *items, int n_items, double *obs_dev, double *reward_dev, void *stream);
+
+/* episode statistics summed over the instances of this handle: out_dev = int64[NBIOT_N_STATS]
+ * (the vector that is all-reduced across GPUs) */
+int nbiot_reduce_stats(nbiot_handle_t *h, int64_t *out_dev, void *stream);
+
+/* the reference-facing call with HOST buffers: copies actions host->device, advances, gathers the
+ * observation, copies obs/reward device->host and synchronises (gym step on a batch).
+ * actions_host: uint8[n_inst][ext_k] or NULL; obs_host: double[n_inst][obs_dim]; reward_host: double[n_inst] */
+int nbiot_step_host(nbiot_handle_t *h, const uint8_t *actions_host, int until_time, int max_steps,
+                    const nbiot_obs_item_t *items, int n_items, double *obs_host, double *reward_host, void *stream);
+
+/* debugging: log (time, type) of every event of instance 0 into evlog_dev = int32[cap][2] */
+int nbiot_set_event_log(nbiot_handle_t *h, int32_t *evlog_dev, int cap);
+/* kernel launches issued through this handle so far */
+long long nbiot_launch_count(nbiot_handle_t *h);
+/* launch geometry chosen at creation: blocks, warps per block, dynamic shared memory per block */
+int nbiot_launch_geometry(nbiot_handle_t *h, int *blocks, int *warps_per_block, int *smem_bytes);
+
+/* host twins of the counter-based random stream (include/nbiot_rng.h): the same compiled arithmetic
+ * the kernels use, for the generator shim that drives the reference (rng argument of
+ * system/system_creator.py:22) */
+double nbiot_rng_u01(uint64_t seed, uint64_t ctr, uint32_t stream);
+void nbiot_rng_pair(uint64_t seed, uint64_t ctr, uint32_t stream, double *xy);
+double nbiot_rng_normal(uint64_t seed, uint64_t ctr, uint32_t stream);
+uint64_t nbiot_rng_bounded(uint64_t seed, uint64_t ctr, uint32_t stream, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* NBIOT_H */

@@ -1,0 +1,425 @@
+/*
+ * nbiot_kernels.cu -- sm_100a kernels and the C ABI (include/nbiot.h) of the batched NB-IoT cell
+ * simulator. One warp owns one cell instance for the whole launch:
+ *
+ *   1. the warp claims an instance index from a global work counter (persistent grid sized to
+ *      SMs x resident CTAs, so uneven per-instance work balances itself);
+ *   2. it stages the instance's hot state -- the NbHdr header and the carrier look-ahead ring --
+ *      from HBM into its slice of shared memory with 16-byte coalesced copies;
+ *   3. it runs the simulation core (nbiot_core.cuh) until the instance needs an external decision
+ *      (or reaches the time / step bound): the clock jumps from event to event, list scans run
+ *      32 entries at a time with ballot / popc ranks, the UE records, lists and info side buffers
+ *      stay in HBM (instance-major, contiguous per instance);
+ *   4. it writes the header and grid back with the same coalesced copies.
+ *
+ * The path is integer / control work on HBM-resident state: no tensor cores, no GEMM. The BLER and
+ * MCS tables are read through the read-only path and stay L2-resident (they are touched about 0.03
+ * times per simulated subframe, so staging 100 KB of tables per CTA would cost more than it saves;
+ * see DESIGN.md).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "nbiot.h"
+#include "nbiot_core.cuh"
+
+#define NB_WPB 4   /* warps (instances in flight) per CTA */
+
+struct NbKernelArgs {
+    uint8_t *state;
+    NbLayout L;
+    const nbiot_conf_t *conf;
+    const nbiot_ctrl_t *ctrl;
+    const uint16_t *lut2;
+    const uint8_t *mcs;
+    unsigned int *counter;
+    int32_t *evlog; int evlog_cap;
+    int smem_per_warp, hdr_bytes16, grid_bytes16;
+};
+
+struct nbiot_handle {
+    nbiot_conf_t conf;
+    nbiot_ctrl_t ctrl;
+    NbLayout L;
+    int device, n_inst;
+    uint8_t *state;
+    nbiot_conf_t *conf_dev;
+    nbiot_ctrl_t *ctrl_dev;
+    uint16_t *lut2_dev;
+    uint8_t *mcs_dev;
+    uint64_t *seeds_dev;
+    unsigned int *counter_dev;
+    int blocks, smem_bytes;
+    long long launches;
+    int32_t *evlog; int evlog_cap;
+    /* staging for nbiot_step_host */
+    uint8_t *act_dev; double *obs_dev, *rew_dev; nbiot_obs_item_t *items_dev;
+    uint8_t *act_pin; double *obs_pin, *rew_pin;
+    size_t act_cap, obs_cap, items_cap;
+};
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *fmt, const char *a = "", const char *b = "")
+{ snprintf(g_err, sizeof g_err, fmt, a, b); return code; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(NBIOT_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+/* ------------------------------------------------------------------ device side */
+__device__ __forceinline__ void nb_copy16(void *dst, const void *src, int n16)
+{
+    const uint4 *s = (const uint4 *)src; uint4 *d = (uint4 *)dst;
+    for (int i = threadIdx.x & 31; i < n16; i += 32) d[i] = s[i];
+}
+
+__device__ __forceinline__ NbCtx nb_make_ctx(const NbKernelArgs &A, int i, unsigned char *my_smem)
+{
+    NbCtx c;
+    const NbLayout &L = A.L;
+    uint8_t *s = A.state;
+    c.h = (NbHdr *)my_smem;
+    c.grid = (uint16_t *)(my_smem + A.hdr_bytes16 * 16);
+    for (int k = 0; k < 3; ++k) c.ra[k] = (NbRaEntry *)(s + L.off_ra) + ((size_t)i * 3 + k) * L.ra_cap;
+    c.conn = (NbConnEntry *)(s + L.off_conn) + (size_t)i * L.ue_cap;
+    c.cont = (NbContEntry *)(s + L.off_cont) + (size_t)i * L.ue_cap;
+    c.ue = (NbUe *)(s + L.off_ue) + (size_t)i * L.ue_cap;
+    c.free_stack = (uint16_t *)(s + L.off_free) + (size_t)i * L.ue_cap;
+    c.occ = (NbOccHist *)(s + L.off_occ) + i;
+    c.incoming = (double *)(s + L.off_incoming) + (size_t)i * L.hist_cap;
+    c.delays = (int32_t *)(s + L.off_delays) + (size_t)i * L.hist_cap;
+    c.service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
+    c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
+    c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
+    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = A.conf;
+    c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
+    c.evlog = i == 0 ? A.evlog : nullptr; c.evlog_cap = A.evlog_cap;
+    return c;
+}
+
+/* mode 0: construct + reset, 1: reset, 2: advance */
+__global__ void __launch_bounds__(NB_WPB * 32)
+nbiot_sim_kernel(NbKernelArgs A, int mode, const uint64_t *seeds, const uint8_t *ext_actions, int until_time, int max_steps)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *my = smem + (size_t)warp * A.smem_per_warp;
+    NbHdr *hdr_g = (NbHdr *)(A.state + A.L.off_hdr);
+    uint16_t *grid_g = (uint16_t *)(A.state + A.L.off_grid);
+    const size_t grid_elems = (size_t)A.L.n_carriers * A.L.grid_w;
+    const int ext_k = A.ctrl->ext_k;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(A.counter, 1u);
+        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (i >= A.L.n_inst) break;
+        NbCtx c = nb_make_ctx(A, i, my);
+        if (mode != 0) {
+            nb_copy16(my, hdr_g + i, A.hdr_bytes16);
+            nb_copy16(c.grid, grid_g + (size_t)i * grid_elems, A.grid_bytes16);
+        }
+        __syncwarp();
+        if (mode == 0) { nbc_construct(c, seeds[i], A.ctrl); nbc_reset(c); }
+        else if (mode == 1) nbc_reset(c);
+        else nbc_controller_advance(c, A.ctrl, ext_actions ? ext_actions + (size_t)i * ext_k : nullptr, until_time, max_steps);
+        __syncwarp();
+        nb_copy16(hdr_g + i, my, A.hdr_bytes16);
+        nb_copy16(grid_g + (size_t)i * grid_elems, c.grid, A.grid_bytes16);
+        __syncwarp();
+    }
+}
+
+/* Controller.get_obs (controller.py:105-120) for the whole batch: one thread per (instance, obs element) */
+__global__ void nbiot_obs_kernel(const nbiot_record_t *rec, int n_inst, const nbiot_obs_item_t *items, int n_items, int obs_dim,
+                                 double *obs, double *reward)
+{
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = n_inst * (obs_dim > 0 ? obs_dim : 1);
+    if (tid >= total) return;
+    int i = obs_dim > 0 ? tid / obs_dim : tid, j = obs_dim > 0 ? tid % obs_dim : 0;
+    const nbiot_record_t *r = rec + i;
+    if (reward && j == 0) reward[i] = r->reward;
+    if (!obs || obs_dim == 0) return;
+    int k = 0, base = 0;
+    while (k < n_items && j >= base + items[k].length) { base += items[k].length; ++k; }
+    if (k >= n_items) return;
+    nbiot_obs_item_t it = items[k];
+    int e = j - base;
+    double v = 0.0;
+    if ((it.state_mask >> r->state) & 1u) {
+        const unsigned char *p = (const unsigned char *)r + it.offset;
+        if (it.kind == 0) v = (double)((const int32_t *)p)[e];
+        else if (it.kind == 1) v = ((const double *)p)[e];
+        else v = 1.0 - (double)p[e] / 12.0;
+    }
+    v = v / it.norm;
+    obs[(size_t)i * obs_dim + j] = v < 1.0 ? v : 1.0;          /* min(1.0, v/norm): no lower clip */
+}
+
+__global__ void nbiot_stats_kernel(const NbHdr *hdr, int n_inst, unsigned long long *out)
+{
+    __shared__ unsigned long long acc[NBIOT_N_STATS];
+    for (int k = threadIdx.x; k < NBIOT_N_STATS; k += blockDim.x) acc[k] = 0ull;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_inst; i += gridDim.x * blockDim.x) {
+        const NbHdr *h = hdr + i;
+        long long v[NBIOT_N_STATS];
+        for (int k = 0; k < NBIOT_N_STATS; ++k) v[k] = 0;
+        for (int k = 0; k < 3; ++k) { v[k] = h->ue_arrivals[k]; v[3 + k] = h->ue_departures[k]; v[6 + k] = h->backoffs[k]; }
+        v[NBIOT_STAT_CONNECTIONS] = h->ue_connections; v[NBIOT_STAT_ERRORS] = h->error_count; v[NBIOT_STAT_ATTEMPTS] = h->attempts_count;
+        v[NBIOT_STAT_TOTAL_BITS] = h->total_bits; v[NBIOT_STAT_SUBFRAMES] = h->subframes_done; v[NBIOT_STAT_EVENTS] = h->events;
+        v[NBIOT_STAT_DRAWS] = (long long)h->draws; v[NBIOT_STAT_FAULTED] = (h->fault & NBIOT_FAULT_FATAL_MASK) ? 1 : 0;
+        v[NBIOT_STAT_LIVE_UES] = h->ue_count - (h->ue_departures[0] + h->ue_departures[1] + h->ue_departures[2]);
+        v[NBIOT_STAT_SUM_DELAY_X1000] = (long long)(h->av_delay * (double)(h->ue_departures[0] + h->ue_departures[1] + h->ue_departures[2]) * 1000.0);
+        v[NBIOT_STAT_TRUNCATED] = (h->fault & NBIOT_FAULT_LIST_TRUNC) ? 1 : 0;
+        for (int k = 0; k < NBIOT_N_STATS; ++k) if (v[k]) atomicAdd(&acc[k], (unsigned long long)v[k]);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < NBIOT_N_STATS; k += blockDim.x) if (acc[k]) atomicAdd(&out[k], acc[k]);
+}
+
+/* ------------------------------------------------------------------ host side */
+static NbKernelArgs make_args(nbiot_handle_t *h)
+{
+    NbKernelArgs A;
+    A.state = h->state; A.L = h->L; A.conf = h->conf_dev; A.ctrl = h->ctrl_dev; A.lut2 = h->lut2_dev; A.mcs = h->mcs_dev;
+    A.counter = h->counter_dev; A.evlog = h->evlog; A.evlog_cap = h->evlog_cap;
+    A.hdr_bytes16 = (int)(sizeof(NbHdr) / 16);
+    A.grid_bytes16 = (int)((size_t)h->L.n_carriers * h->L.grid_w * 2 / 16);
+    A.smem_per_warp = A.hdr_bytes16 * 16 + A.grid_bytes16 * 16;
+    return A;
+}
+
+static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, int until_time, int max_steps, cudaStream_t st)
+{
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->counter_dev, 0, sizeof(unsigned int), st));
+    NbKernelArgs A = make_args(h);
+    nbiot_sim_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, mode, h->seeds_dev, ext_actions, until_time, max_steps);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+extern "C" {
+
+int nbiot_abi_version(void) { return NBIOT_ABI_VERSION; }
+const char *nbiot_last_error(void) { return g_err; }
+
+size_t nbiot_state_bytes(const nbiot_conf_t *conf, int n_inst)
+{
+    if (!conf || n_inst <= 0) return 0;
+    return (size_t)nb_make_layout(conf, n_inst).total;
+}
+size_t nbiot_hdr_bytes(void) { return sizeof(NbHdr); }
+
+int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_dev, size_t state_bytes,
+                 const uint64_t *seeds, const uint16_t *lut2, const uint8_t *mcs, const struct nbiot_ctrl *ctrl,
+                 void *stream, nbiot_handle_t **out)
+{
+    static_assert(sizeof(NbHdr) % 16 == 0, "NbHdr must be a multiple of 16 bytes for the staged copies");
+    if (!conf || !state_dev || !seeds || !lut2 || !mcs || !ctrl || !out || n_inst <= 0) return set_err(NBIOT_E_INVALID, "nbiot_create: null or empty argument");
+    if (conf->ue_cap < 1 || conf->ue_cap > 65535) return set_err(NBIOT_E_INVALID, "nbiot_create: ue_cap must be in 1..65535");
+    if (conf->grid_w < 256 || (conf->grid_w & (conf->grid_w - 1))) return set_err(NBIOT_E_INVALID, "nbiot_create: grid_w must be a power of two >= 256");
+    if (conf->hist_cap < 1 || conf->n_carriers < 1 || conf->n_carriers > 2) return set_err(NBIOT_E_INVALID, "nbiot_create: bad hist_cap / n_carriers");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_err(NBIOT_E_NOGPU, "no CUDA device: this library has no CPU path");
+    if (device < 0 || device >= ndev) return set_err(NBIOT_E_INVALID, "nbiot_create: bad device index");
+    CK(cudaSetDevice(device));
+    NbLayout L = nb_make_layout(conf, n_inst);
+    if (state_bytes < L.total) return set_err(NBIOT_E_SIZE, "nbiot_create: state buffer smaller than nbiot_state_bytes()");
+    cudaStream_t st = (cudaStream_t)stream;
+    nbiot_handle_t *h = new nbiot_handle_t();
+    memset(h, 0, sizeof *h);
+    h->conf = *conf; h->ctrl = *ctrl; h->L = L; h->device = device; h->n_inst = n_inst; h->state = (uint8_t *)state_dev;
+    CK(cudaMalloc(&h->conf_dev, sizeof(nbiot_conf_t)));
+    CK(cudaMalloc(&h->ctrl_dev, sizeof(nbiot_ctrl_t)));
+    CK(cudaMalloc(&h->lut2_dev, NB_LUT_CURVES * NB_LUT_SNR_PTS * sizeof(uint16_t)));
+    CK(cudaMalloc(&h->mcs_dev, NB_MCS_LOSS_ROWS * NB_N_TBS * 3));
+    CK(cudaMalloc(&h->seeds_dev, sizeof(uint64_t) * (size_t)n_inst));
+    CK(cudaMalloc(&h->counter_dev, sizeof(unsigned int)));
+    CK(cudaMemcpyAsync(h->conf_dev, conf, sizeof(nbiot_conf_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ctrl_dev, ctrl, sizeof(nbiot_ctrl_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->lut2_dev, lut2, NB_LUT_CURVES * NB_LUT_SNR_PTS * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->mcs_dev, mcs, NB_MCS_LOSS_ROWS * NB_N_TBS * 3, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->seeds_dev, seeds, sizeof(uint64_t) * (size_t)n_inst, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));     /* the host arrays may go away after this call */
+    /* launch geometry: persistent grid = SMs x resident CTAs, capped by the work available */
+    NbKernelArgs A = make_args(h);
+    h->smem_bytes = NB_WPB * A.smem_per_warp;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if ((size_t)h->smem_bytes > prop.sharedMemPerBlockOptin) return set_err(NBIOT_E_INVALID, "grid_w too large for the shared memory of one CTA");
+    CK(cudaFuncSetAttribute(nbiot_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nbiot_sim_kernel, NB_WPB * 32, h->smem_bytes));
+    if (per_sm < 1) per_sm = 1;
+    int need = (n_inst + NB_WPB - 1) / NB_WPB;
+    int cap = prop.multiProcessorCount * per_sm;
+    h->blocks = need < cap ? need : cap;
+    int rc = launch_sim(h, 0, nullptr, -1, 0, st);     /* construct + reset every instance */
+    if (rc) return rc;
+    *out = h;
+    return 0;
+}
+
+int nbiot_destroy(nbiot_handle_t *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaFree(h->conf_dev); cudaFree(h->ctrl_dev); cudaFree(h->lut2_dev); cudaFree(h->mcs_dev); cudaFree(h->seeds_dev); cudaFree(h->counter_dev);
+    cudaFree(h->act_dev); cudaFree(h->obs_dev); cudaFree(h->rew_dev); cudaFree(h->items_dev);
+    cudaFreeHost(h->act_pin); cudaFreeHost(h->obs_pin); cudaFreeHost(h->rew_pin);
+    delete h;
+    return 0;
+}
+
+int nbiot_set_controller(nbiot_handle_t *h, const struct nbiot_ctrl *ctrl, void *stream)
+{
+    if (!h || !ctrl) return set_err(NBIOT_E_INVALID, "nbiot_set_controller: null argument");
+    CK(cudaSetDevice(h->device));
+    h->ctrl = *ctrl;
+    CK(cudaMemcpyAsync(h->ctrl_dev, &h->ctrl, sizeof(nbiot_ctrl_t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+int nbiot_reset(nbiot_handle_t *h, void *stream)
+{
+    if (!h) return set_err(NBIOT_E_INVALID, "nbiot_reset: null handle");
+    return launch_sim(h, 1, nullptr, -1, 0, (cudaStream_t)stream);
+}
+
+int nbiot_advance(nbiot_handle_t *h, const uint8_t *ext_actions_dev, int until_time, int max_steps, void *stream)
+{
+    if (!h) return set_err(NBIOT_E_INVALID, "nbiot_advance: null handle");
+    if (max_steps < 1) return set_err(NBIOT_E_INVALID, "nbiot_advance: max_steps must be >= 1");
+    return launch_sim(h, 2, ext_actions_dev, until_time, max_steps, (cudaStream_t)stream);
+}
+
+int nbiot_records_ptr(nbiot_handle_t *h, void **records_dev)
+{
+    if (!h || !records_dev) return set_err(NBIOT_E_INVALID, "nbiot_records_ptr: null argument");
+    *records_dev = h->state + h->L.off_rec;
+    return 0;
+}
+
+int nbiot_hist_ptrs(nbiot_handle_t *h, void **incoming_dev, void **delays_dev, void **service_dev, int *hist_cap)
+{
+    if (!h) return set_err(NBIOT_E_INVALID, "nbiot_hist_ptrs: null handle");
+    if (incoming_dev) *incoming_dev = h->state + h->L.off_incoming;
+    if (delays_dev) *delays_dev = h->state + h->L.off_delays;
+    if (service_dev) *service_dev = h->state + h->L.off_service;
+    if (hist_cap) *hist_cap = h->L.hist_cap;
+    return 0;
+}
+
+static int ensure_items(nbiot_handle_t *h, const nbiot_obs_item_t *items, int n_items, cudaStream_t st, int *obs_dim)
+{
+    int d = 0;
+    for (int k = 0; k < n_items; ++k) d += items[k].length;
+    *obs_dim = d;
+    if (n_items <= 0) return 0;
+    if ((size_t)n_items > h->items_cap) {
+        cudaFree(h->items_dev); h->items_dev = nullptr; h->items_cap = 0;
+        CK(cudaMalloc(&h->items_dev, sizeof(nbiot_obs_item_t) * (size_t)n_items));
+        h->items_cap = (size_t)n_items;
+    }
+    CK(cudaMemcpyAsync(h->items_dev, items, sizeof(nbiot_obs_item_t) * (size_t)n_items, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+int nbiot_gather_obs(nbiot_handle_t *h, const nbiot_obs_item_t *items, int n_items, double *obs_dev, double *reward_dev, void *stream)
+{
+    if (!h || (n_items > 0 && !items)) return set_err(NBIOT_E_INVALID, "nbiot_gather_obs: null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int obs_dim = 0;
+    int rc = ensure_items(h, items, n_items, st, &obs_dim);
+    if (rc) return rc;
+    int total = h->n_inst * (obs_dim > 0 ? obs_dim : 1);
+    nbiot_obs_kernel<<<(total + 255) / 256, 256, 0, st>>>((const nbiot_record_t *)(h->state + h->L.off_rec), h->n_inst, h->items_dev, n_items, obs_dim,
+                                                       obs_dim > 0 ? obs_dev : nullptr, reward_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+int nbiot_reduce_stats(nbiot_handle_t *h, int64_t *out_dev, void *stream)
+{
+    if (!h || !out_dev) return set_err(NBIOT_E_INVALID, "nbiot_reduce_stats: null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(out_dev, 0, sizeof(int64_t) * NBIOT_N_STATS, st));
+    int blocks = (h->n_inst + 127) / 128; if (blocks > 592) blocks = 592;
+    nbiot_stats_kernel<<<blocks, 128, 0, st>>>((const NbHdr *)(h->state + h->L.off_hdr), h->n_inst, (unsigned long long *)out_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+int nbiot_step_host(nbiot_handle_t *h, const uint8_t *actions_host, int until_time, int max_steps,
+                    const nbiot_obs_item_t *items, int n_items, double *obs_host, double *reward_host, void *stream)
+{
+    if (!h) return set_err(NBIOT_E_INVALID, "nbiot_step_host: null handle");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int k = h->ctrl.ext_k;
+    size_t act_bytes = actions_host ? (size_t)h->n_inst * (size_t)k : 0;
+    if (act_bytes > h->act_cap) {
+        cudaFree(h->act_dev); cudaFreeHost(h->act_pin); h->act_dev = nullptr; h->act_pin = nullptr; h->act_cap = 0;
+        CK(cudaMalloc(&h->act_dev, act_bytes)); CK(cudaMallocHost(&h->act_pin, act_bytes)); h->act_cap = act_bytes;
+    }
+    int obs_dim = 0;
+    int rc = ensure_items(h, items, n_items, st, &obs_dim);
+    if (rc) return rc;
+    size_t obs_elems = (size_t)h->n_inst * (size_t)(obs_dim > 0 ? obs_dim : 1);
+    if (obs_elems > h->obs_cap) {
+        cudaFree(h->obs_dev); cudaFree(h->rew_dev); cudaFreeHost(h->obs_pin); cudaFreeHost(h->rew_pin);
+        h->obs_dev = h->rew_dev = nullptr; h->obs_pin = h->rew_pin = nullptr; h->obs_cap = 0;
+        CK(cudaMalloc(&h->obs_dev, obs_elems * sizeof(double))); CK(cudaMalloc(&h->rew_dev, (size_t)h->n_inst * sizeof(double)));
+        CK(cudaMallocHost(&h->obs_pin, obs_elems * sizeof(double))); CK(cudaMallocHost(&h->rew_pin, (size_t)h->n_inst * sizeof(double)));
+        h->obs_cap = obs_elems;
+    }
+    if (actions_host) {
+        memcpy(h->act_pin, actions_host, act_bytes);
+        CK(cudaMemcpyAsync(h->act_dev, h->act_pin, act_bytes, cudaMemcpyHostToDevice, st));
+    }
+    rc = launch_sim(h, 2, actions_host ? h->act_dev : nullptr, until_time, max_steps, st);
+    if (rc) return rc;
+    int total = h->n_inst * (obs_dim > 0 ? obs_dim : 1);
+    nbiot_obs_kernel<<<(total + 255) / 256, 256, 0, st>>>((const nbiot_record_t *)(h->state + h->L.off_rec), h->n_inst, h->items_dev, n_items, obs_dim,
+                                                       obs_dim > 0 ? h->obs_dev : nullptr, h->rew_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    if (obs_host && obs_dim > 0) CK(cudaMemcpyAsync(h->obs_pin, h->obs_dev, (size_t)h->n_inst * obs_dim * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (reward_host) CK(cudaMemcpyAsync(h->rew_pin, h->rew_dev, (size_t)h->n_inst * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (obs_host && obs_dim > 0) memcpy(obs_host, h->obs_pin, (size_t)h->n_inst * obs_dim * sizeof(double));
+    if (reward_host) memcpy(reward_host, h->rew_pin, (size_t)h->n_inst * sizeof(double));
+    return 0;
+}
+
+int nbiot_set_event_log(nbiot_handle_t *h, int32_t *evlog_dev, int cap)
+{
+    if (!h) return set_err(NBIOT_E_INVALID, "nbiot_set_event_log: null handle");
+    h->evlog = evlog_dev; h->evlog_cap = evlog_dev ? cap : 0;
+    return 0;
+}
+
+long long nbiot_launch_count(nbiot_handle_t *h) { return h ? h->launches : 0; }
+
+int nbiot_launch_geometry(nbiot_handle_t *h, int *blocks, int *warps_per_block, int *smem_bytes)
+{
+    if (!h) return set_err(NBIOT_E_INVALID, "nbiot_launch_geometry: null handle");
+    if (blocks) *blocks = h->blocks;
+    if (warps_per_block) *warps_per_block = NB_WPB;
+    if (smem_bytes) *smem_bytes = h->smem_bytes;
+    return 0;
+}
+
+double nbiot_rng_u01(uint64_t seed, uint64_t ctr, uint32_t stream) { return nb_rng_u01(seed, ctr, stream); }
+void nbiot_rng_pair(uint64_t seed, uint64_t ctr, uint32_t stream, double *xy) { nb_rng_pair(seed, ctr, stream, &xy[0], &xy[1]); }
+double nbiot_rng_normal(uint64_t seed, uint64_t ctr, uint32_t stream) { return nb_rng_normal(seed, ctr, stream); }
+uint64_t nbiot_rng_bounded(uint64_t seed, uint64_t ctr, uint32_t stream, uint64_t n) { return nb_rng_bounded(seed, ctr, stream, n); }
+
+}   /* extern "C" */

@@ -24,6 +24,7 @@
 
 #include <stdint.h>
 #include "nbiot_conf.h"
+#include "nbiot_ctrl.h"
 #include "nbiot_record.h"
 
 #define NB_EV_POOL 64        /* pending RAR_window_end / Msg3 / NPUSCH_end events            */
@@ -98,7 +99,7 @@ typedef struct {            /* per-occasion NPRACH histories of the current upda
     int16_t col[3][NBIOT_MAX_OCC];
 } NbOccHist;
 
-typedef struct NbHdr {
+typedef struct __attribute__((aligned(16))) NbHdr {
     /* ---- clock, FSM, random stream ---- */
     uint64_t seed, draws;
     uint64_t cur_key;                 /* key of the event being handled (orders lazily retired Backoff_end) */
@@ -163,17 +164,6 @@ typedef struct NbHdr {
     uint64_t pool_free;               /* bit i set: pool[i] is free */
     NbEvent pool[NB_EV_POOL];
 } NbHdr;
-
-/* device-side controller tables: the multi-agent split of reference controller.py:234-288 with
- * DummyAgent internal agents (control_agents.py:83-113) compiled into write lists */
-typedef struct nbiot_ctrl {
-    uint32_t ext_state_mask;          /* bit s set: an external decision is needed in NodeB state s */
-    int32_t ext_k;                    /* number of action items the external agent sets          */
-    uint8_t ext_a_mask[24];           /* their indices in the 23-vector                           */
-    int8_t ext_post[24];              /* writes of the `next` chain after the external action     */
-    int8_t state_writes[4][24];       /* fixed actions of the internal agents of each NodeB state */
-    uint8_t init_action[24];          /* Controller._initialize_action result                     */
-} nbiot_ctrl_t;
 
 /* byte offsets of the per-instance arrays inside the caller-owned state buffer */
 typedef struct {

@@ -19,7 +19,7 @@
 
 #include <stdint.h>
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 
 #define NB_LANES 32
 #define NB_DEV __device__ __forceinline__
@@ -72,7 +72,7 @@ static inline uint32_t nbw_atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p;
 /* nbw_run(f): execute the lane-parallel section f. Product build: plain call (all 32 lanes are
  * already here). 32-lane emulation: the scalar code around it runs once, f runs on 32 fibers and
  * must return the same value on every lane. */
-#if defined(__CUDA_ARCH__) || NBIOT_EMU_LANES == 1
+#if defined(__CUDACC__) || NBIOT_EMU_LANES == 1
 template <class F> NB_DEV auto nbw_run(F f) -> decltype(f()) { return f(); }
 #else
 void nbw_emu_run(void (*tramp)(void *, int), void *closure);   /* runs tramp(closure, lane) on 32 fibers */

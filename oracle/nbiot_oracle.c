@@ -29,8 +29,11 @@
 #include <string.h>
 #include <stdio.h>
 #include <math.h>
+#include <pthread.h>
+#include <time.h>
 
 #include "nbiot_conf.h"
+#include "nbiot_ctrl.h"
 #include "nbiot_params.h"
 #include "nbiot_record.h"
 #include "nbiot_rng.h"
@@ -1293,6 +1296,96 @@ long long orc_run_fixed(Oracle *o, const int32_t *action, int until_time, nbiot_
     long long n = 0;
     while (o->time < until_time && !(o->fault & NBIOT_FAULT_FATAL_MASK)) { orc_step(o, action, last); n++; }
     return n;
+}
+
+/* ------------------------------------------------------------------ controller + multi-cell timing driver */
+/* Controller.step + to_next_step / run_until (controller.py:185-195, :234-288) with fixed-action internal
+ * agents, over the same write tables the CUDA path uses (include/nbiot_ctrl.h). ctrl_action is the shared
+ * 23-int vector of this cell (controller.py:33). Returns the number of NodeB steps. */
+static void ctrl_apply(int32_t *act, const int8_t *w) { for (int i = 0; i < NB_N_ACTIONS; ++i) if (w[i] >= 0) act[i] = w[i]; }
+
+int orc_ctrl_advance(Oracle *o, const nbiot_ctrl_t *ctrl, int32_t *ctrl_action, const uint8_t *ext_action, int until_time, int max_steps, nbiot_record_t *out)
+{
+    int steps = 0;
+    if (o->fault & NBIOT_FAULT_FATAL_MASK) return 0;
+    if (ext_action) {
+        for (int i = 0; i < ctrl->ext_k; ++i) ctrl_action[ctrl->ext_a_mask[i]] = ext_action[i];
+        ctrl_apply(ctrl_action, ctrl->ext_post);
+    } else ctrl_apply(ctrl_action, ctrl->state_writes[o->state]);
+    while (steps < max_steps && !(until_time >= 0 && o->time >= until_time)) {
+        if (steps > 0) ctrl_apply(ctrl_action, ctrl->state_writes[o->state]);
+        orc_step(o, ctrl_action, out);
+        steps += 1;
+        if (o->fault & NBIOT_FAULT_FATAL_MASK) break;
+        if ((ctrl->ext_state_mask >> o->state) & 1u) { ctrl_apply(ctrl_action, ctrl->state_writes[o->state]); break; }
+    }
+    return steps;
+}
+
+typedef struct {
+    const nbiot_conf_t *conf; const nbiot_ctrl_t *ctrl; const uint16_t *lut2; const uint8_t *mcs;
+    const uint64_t *seeds; const uint8_t *actions;   /* [steps][n_inst][ext_k] or NULL */
+    int n_inst, steps, until_time, first, stride;
+    long long subframes, node_steps; double seconds;
+} BenchJob;
+
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+
+static void *bench_worker(void *arg)
+{
+    BenchJob *j = (BenchJob *)arg;
+    nbiot_record_t rec;
+    /* construction and reset are outside the timed region, like the import/creation cost of the reference */
+    int mine = 0;
+    for (int i = j->first; i < j->n_inst; i += j->stride) mine++;
+    Oracle **cells = malloc(sizeof(Oracle *) * (size_t)(mine > 0 ? mine : 1));
+    int32_t (*acts)[24] = malloc(sizeof(int32_t[24]) * (size_t)(mine > 0 ? mine : 1));
+    int k = 0;
+    for (int i = j->first; i < j->n_inst; i += j->stride, ++k) {
+        cells[k] = orc_create(j->conf, j->seeds[i], j->lut2, j->mcs);
+        for (int a = 0; a < 24; ++a) acts[k][a] = j->ctrl->init_action[a];
+        orc_reset(cells[k], &rec);
+    }
+    double t0 = now_s();
+    long long sf = 0, ns = 0;
+    k = 0;
+    for (int i = j->first; i < j->n_inst; i += j->stride, ++k) {
+        int t_before = cells[k]->time;
+        if (j->actions)
+            for (int s = 0; s < j->steps; ++s)
+                ns += orc_ctrl_advance(cells[k], j->ctrl, acts[k], j->actions + ((size_t)s * j->n_inst + i) * j->ctrl->ext_k, -1, 1 << 30, &rec);
+        else ns += orc_ctrl_advance(cells[k], j->ctrl, acts[k], NULL, j->until_time, 1 << 30, &rec);
+        sf += cells[k]->time - t_before;
+    }
+    j->seconds = now_s() - t0;
+    j->subframes = sf; j->node_steps = ns;
+    for (k = 0; k < mine; ++k) orc_destroy(cells[k]);
+    free(cells); free(acts);
+    return NULL;
+}
+
+/* simulate n_inst cells on n_threads host threads (instances are dealt round-robin); returns the slowest
+ * thread's wall-clock seconds inside the step loop and the total simulated subframes */
+double orc_bench(const nbiot_conf_t *conf, const nbiot_ctrl_t *ctrl, const uint16_t *lut2, const uint8_t *mcs, const uint64_t *seeds,
+                 int n_inst, const uint8_t *actions, int steps, int until_time, int n_threads, long long *subframes, long long *node_steps)
+{
+    if (n_threads < 1) n_threads = 1;
+    BenchJob *jobs = calloc((size_t)n_threads, sizeof(BenchJob));
+    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)n_threads);
+    for (int t = 0; t < n_threads; ++t) {
+        BenchJob j = { conf, ctrl, lut2, mcs, seeds, actions, n_inst, steps, until_time, t, n_threads, 0, 0, 0.0 };
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, bench_worker, &jobs[t]);
+    }
+    double worst = 0; long long sf = 0, ns = 0;
+    for (int t = 0; t < n_threads; ++t) {
+        pthread_join(th[t], NULL);
+        if (jobs[t].seconds > worst) worst = jobs[t].seconds;
+        sf += jobs[t].subframes; ns += jobs[t].node_steps;
+    }
+    *subframes = sf; *node_steps = ns;
+    free(jobs); free(th);
+    return worst;
 }
 
 /* host twins of the random stream, for the Python shim that drives the reference */

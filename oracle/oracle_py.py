@@ -42,6 +42,8 @@ def lib():
         L.orc_rng_bounded.restype = ctypes.c_uint64
         L.orc_rng_bounded.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64]
         L.orc_rng_pair.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p]
+        L.orc_bench.restype = ctypes.c_double
+        L.orc_bench.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         assert L.orc_record_size() == RECORD_DTYPE.itemsize
         assert L.orc_conf_size() == ctypes.sizeof(NbiotConf)
         _LIB = L
@@ -112,3 +114,21 @@ class OracleCell:
 
     def event_log(self):
         return self._evlog[:self.L.orc_event_log_len(self.h)].copy()
+
+
+def bench(conf, ctrl, seeds, actions=None, steps=0, until_time=-1, n_threads=1):
+    """Time n cells on n_threads host threads (oracle/nbiot_oracle.c: orc_bench). actions: uint8[steps][n][ext_k]
+    external-agent actions, or None to run on the internal agents until `until_time`.
+    Returns (seconds of the slowest thread inside the step loop, simulated subframes, NodeB steps)."""
+    L = lib()
+    lut, mcs = tables()
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    sf, ns = ctypes.c_longlong(), ctypes.c_longlong()
+    ap = None
+    if actions is not None:
+        actions = np.ascontiguousarray(actions, dtype=np.uint8)
+        assert actions.shape == (steps, len(seeds), ctrl.ext_k)
+        ap = actions.ctypes.data
+    sec = L.orc_bench(ctypes.byref(conf), ctypes.byref(ctrl), lut.ctypes.data, mcs.ctypes.data, seeds.ctypes.data, len(seeds), ap,
+                      int(steps), int(until_time), int(n_threads), ctypes.byref(sf), ctypes.byref(ns))
+    return sec, sf.value, ns.value

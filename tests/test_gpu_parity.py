@@ -1,0 +1,203 @@
+"""Parity of the CUDA path, called through the C ABI, with the CPU oracle and with the golden traces of
+the unmodified Python reference. Integer fields bit-exact; float fields bit-exact against the oracle
+(both evaluate include/nbiot_math.h) and within 1e-9 relative of the reference's numpy arithmetic
+(the contract in BASELINE.json is 1e-5)."""
+import numpy as np
+import pytest
+
+from golden_util import CASES, Golden, record_diff, REF_RTOL
+
+pytestmark = pytest.mark.gpu
+
+CFG1 = {'ratio': 1.0, 'M': 1000, 'buffer_range': [100, 600], 'reward_criteria': 'throughput'}
+CAPS = {'manual_branches': dict(grid_w=4096), 'cfg3_npusch_random_policy': dict(grid_w=2048), 'cfg2_random_policy': dict(grid_w=2048),
+        'cfg4_two_carriers_bursty': dict(grid_w=2048)}
+
+# agent sets of the two shipped scenarios (scripts/nprach/evaluate_RL.py:46-77, scripts/npusch/experiments_RL.py:40-78)
+NPRACH_AGENTS = [
+    {'id': 0, 'action_items': ['id', 'Imcs', 'Nrep', 'carrier', 'delay', 'sc'], 'obs_items': [], 'next': -1, 'states': ['Scheduling']},
+    {'id': 1, 'action_items': ['ce_level', 'rar_Imcs', 'Nrep'], 'obs_items': [], 'next': -1, 'states': ['RAR_window']},
+    {'id': 2, 'action_items': ['rar_window', 'mac_timer', 'transmax', 'panchor', 'backoff'], 'obs_items': [], 'next': -1, 'states': ['RAR_window_end']},
+    {'id': 3, 'action_items': ['th_C1', 'th_C0', 'sc_C0', 'sc_C1', 'sc_C2', 'period_C0', 'period_C1', 'period_C2'],
+     'obs_items': ['detection_ratios', 'colision_ratios', 'msg3_detection', 'NPRACH_occupation', 'av_delay', 'distribution'],
+     'next': -1, 'states': ['NPRACH_update']},
+]
+NPUSCH_AGENTS = [
+    {'id': 0, 'action_items': ['id', 'Imcs', 'Nrep'], 'obs_items': ['total_ues', 'connection_time', 'loss', 'sinr', 'buffer', 'carrier_state'],
+     'next': 1, 'states': ['Scheduling']},
+    {'id': 1, 'action_items': ['carrier', 'delay', 'sc'], 'obs_items': [], 'next': -1, 'states': ['Scheduling']},
+    {'id': 2, 'action_items': ['carrier', 'ce_level', 'rar_Imcs', 'delay', 'sc', 'Nrep'], 'obs_items': [], 'next': -1, 'states': ['RAR_window']},
+    {'id': 3, 'action_items': ['backoff'], 'obs_items': [], 'next': -1, 'states': ['RAR_window_end']},
+    {'id': 4, 'action_items': ['th_C1', 'th_C0', 'sc_C0', 'sc_C1', 'sc_C2', 'period_C0', 'period_C1', 'period_C2'], 'obs_items': [],
+     'next': -1, 'states': ['NPRACH_update']},
+]
+CFG3 = {'M': 2000, 'ratio': 1, 'buffer_range': [100, 500], 'reward_criteria': 'average_delay', 'sc_adjustment': True, 'mcs_automatic': False}
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _built():
+    import __graft_entry__ as g
+    g.build()
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_golden_traces_and_oracle(case):
+    """NodeB.step-level replay of the reference's traces: every decision record of every seed."""
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from oracle.oracle_py import OracleCell
+    g = Golden(case)
+    caps = dict(ue_cap=g.conf['M'], grid_w=1024, hist_cap=1024)
+    caps.update(CAPS.get(case, {}))
+    env = BatchedNBIoTEnv(g.conf, num_envs=len(g.seeds), seeds=g.seeds, n_carriers=g.n_carriers, all_states_external=True, **caps)
+    cells = [OracleCell(g.conf, s, n_carriers=g.n_carriers) for s in g.seeds]
+    env.reset()
+    recs = env.records()
+    hists = [g.hist(si) for si in range(len(g.seeds))]
+    hidx = [0] * len(g.seeds)
+    for d in range(-1, g.decisions):
+        if d >= 0:
+            env.node_step(g.actions[:, d, :])
+            recs = env.records()
+        lists = None
+        for si, cell in enumerate(cells):
+            orec = cell.reset() if d < 0 else cell.step(g.actions[si, d])
+            diff = record_diff(orec, recs[si], rtol=0.0)
+            assert not diff, f'{case} seed {g.seeds[si]} decision {d + 1} vs oracle: {diff[:3]}'
+            diff = record_diff(g.records[si, d + 1], recs[si], rtol=REF_RTOL)
+            assert not diff, f'{case} seed {g.seeds[si]} decision {d + 1} vs reference: {diff[:3]}'
+            if recs[si]['state'] == 1:
+                if lists is None:
+                    lists = env.period_lists()
+                ginc, gdl, gsv = hists[si][hidx[si]]
+                hidx[si] += 1
+                assert np.array_equal(lists[1][si, :len(gdl)], gdl) and np.array_equal(lists[2][si, :len(gsv)], gsv)
+                assert np.allclose(lists[0][si, :len(ginc)], ginc, rtol=REF_RTOL, atol=0)
+    assert not (recs['fault'] & 0x1F).any()
+    env.close()
+
+
+def _random_ext_actions(rng, nvec, n):
+    return np.stack([rng.integers(0, m, size=n) for m in nvec], axis=1).astype(np.uint8)
+
+
+@pytest.mark.parametrize('scenario', ['nprach', 'npusch'])
+def test_controller_split_against_oracle(scenario):
+    """config 2 / config 3: the external agent acts, the internal fixed-action agents live on the device."""
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from oracle_controller import OracleController
+    if scenario == 'nprach':
+        conf, agents, ext, n_steps, N = dict(CFG1, ratio=0.5), NPRACH_AGENTS, 3, 12, 24
+    else:
+        conf, agents, ext, n_steps, N = CFG3, NPUSCH_AGENTS, 0, 400, 12
+    seeds = list(range(100, 100 + N))
+    env = BatchedNBIoTEnv(conf, agents_conf=agents, ext_agent=ext, num_envs=N, seeds=seeds, ue_cap=conf['M'], grid_w=2048, hist_cap=1024)
+    ctrls = [OracleController(conf, s, agents_conf=agents, ext_agent=ext) for s in seeds]
+    obs, infos = env.reset()
+    obs = obs.cpu().numpy()
+    for i, c in enumerate(ctrls):
+        assert np.array_equal(c.reset(), obs[i])
+    rng = np.random.default_rng(5)
+    nvec = env.action_nvec
+    assert env.obs_dim == (26 if scenario == 'nprach' else 57)
+    for step in range(n_steps):
+        a = _random_ext_actions(rng, nvec, N)
+        if scenario == 'nprach':
+            a[:, 0] = np.minimum(a[:, 0], a[:, 1])      # keep th_C1 <= th_C0 most of the time; both orders are legal
+        if step % 2 == 0:
+            obs, rew, term, trunc, infos = env.step(a)
+            obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
+            assert not term.any().item() and not trunc.any().item()
+        else:
+            obs, rew = env.step_host(a)                 # the host-buffer entry point must agree with the device one
+        recs = env.records()
+        for i, c in enumerate(ctrls):
+            o_obs, o_rew = c.step(a[i])
+            assert np.array_equal(o_obs, obs[i]), (step, i)
+            assert o_rew == rew[i]
+            assert not record_diff(c.rec, recs[i], rtol=0.0)
+        if scenario == 'nprach':
+            assert (recs['time'] == 3000 * (step + 1)).all()
+            info = infos[0] if step % 2 == 0 else None
+            if info is not None:
+                inc, dl, sv = ctrls[0].hist
+                assert info['delays'] == dl.tolist() and info['service_times'] == sv.tolist() and np.allclose(info['incoming'], inc)
+    env.close()
+
+
+def test_run_until_on_internal_agents():
+    """config 1 / 5 style: no external agent, default agents on the device, one launch to the horizon."""
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from oracle_controller import OracleController
+    N, T = 16, 30000
+    seeds = list(range(N))
+    env = BatchedNBIoTEnv(CFG1, num_envs=N, seeds=seeds, ue_cap=512, grid_w=2048)
+    env.reset()
+    env.run_until(T)
+    recs = env.records()
+    st = env.stats()
+    tot = np.zeros(3, dtype=np.int64)
+    for i, s in enumerate(seeds):
+        c = OracleController(CFG1, s)
+        c.reset()
+        c.run_until(T)
+        assert not record_diff(c.rec, recs[i], rtol=0.0), i
+        tot += np.asarray(c.cell.counters()['ue_departures'])
+    assert st['ue_departures'] == tot.tolist()
+    assert st['subframes'] == int(recs['time'].sum()) and st['faulted'] == 0
+    # a second call with the same horizon does nothing; a later horizon continues
+    env.run_until(T)
+    assert np.array_equal(env.records()['time'], recs['time'])
+    env.close()
+
+
+def test_batch_independence_and_determinism_at_scale():
+    """4096 cells (config 2 size): instance i of a large batch equals the same seed simulated alone,
+    two runs are identical, and the reduced statistics equal the sum of the per-instance records."""
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from oracle_controller import OracleController
+    N = 4096
+    conf = dict(CFG1, ratio=0.5)
+    rng = np.random.default_rng(11)
+    acts = [_random_ext_actions(rng, [15, 15, 4, 4, 4, 6, 6, 6], N) for _ in range(3)]
+    out = []
+    for rep in range(2):
+        env = BatchedNBIoTEnv(conf, agents_conf=NPRACH_AGENTS, ext_agent=3, num_envs=N, ue_cap=512, grid_w=2048)
+        env.reset()
+        for a in acts:
+            obs, rew, _, _, infos = env.step(a)
+        out.append((obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), env.records(), env.stats()))
+        env.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[0][2].tobytes() == out[1][2].tobytes()
+    recs, st = out[0][2], out[0][3]
+    assert not (recs['fault'] & 0x1F).any() and (recs['time'] == 9000).all()
+    assert st['subframes'] == 9000 * N
+    for i in (0, 1, 777, 4095):
+        c = OracleController(conf, i, agents_conf=NPRACH_AGENTS, ext_agent=3)
+        c.reset()
+        for a in acts:
+            o, r = c.step(a[i])
+        assert np.array_equal(o, out[0][0][i]) and r == out[0][1][i]
+        assert not record_diff(c.rec, recs[i], rtol=0.0)
+
+
+def test_faults_are_never_silent():
+    from nb_iot_environment_b200 import BatchedNBIoTEnv, parameters as par
+    # too few UE slots for the offered load: the instance stops and says so
+    env = BatchedNBIoTEnv({'M': 20000, 'ratio': 0.2, 'buffer_range': [256, 256], 'reward_criteria': 'throughput'}, num_envs=4, ue_cap=64)
+    env.reset()
+    env.run_until(20000)
+    recs, st = env.records(), env.stats()
+    assert (recs['fault'] & 1).all() and st['faulted'] == 4 and (recs['time'] < 20000).all()
+    env.close()
+    # an action the reference raises on (sc = 2 -> N_sc = 9, KeyError)
+    env = BatchedNBIoTEnv(CFG1, num_envs=2, all_states_external=True)
+    env.reset()
+    a = np.tile(np.asarray(par.default_action_vector(), dtype=np.uint8), (2, 1))
+    bad = a.copy()
+    bad[1, par.control_items['sc']] = 2
+    for _ in range(200):
+        env.node_step(bad)
+    recs = env.records()
+    assert recs['fault'][0] == 0 and recs['fault'][1] & 4
+    env.close()
