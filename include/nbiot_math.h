@@ -19,8 +19,12 @@
 
 #ifdef __CUDACC__
 #define NB_HD __host__ __device__ __forceinline__
+/* the transcendental kernels and the Philox block stay out of line on the device: one copy each keeps
+ * the simulation kernel inside the instruction cache */
+#define NB_HD_CALL static __host__ __device__ __noinline__
 #else
 #define NB_HD static inline
+#define NB_HD_CALL static inline
 #endif
 
 #if defined(__FP_FAST_FMA) && !defined(__CUDACC__) && !defined(NBIOT_NO_CONTRACT)
@@ -31,9 +35,9 @@
 #define NB_MUL(a, b) __dmul_rn((a), (b))
 #define NB_ADD(a, b) __dadd_rn((a), (b))
 #define NB_SUB(a, b) __dsub_rn((a), (b))
-#define NB_DIV(a, b) __ddiv_rn((a), (b))
+#define NB_DIV(a, b) nb_ddiv((a), (b))
 #define NB_FMA(a, b, c) __fma_rn((a), (b), (c))
-#define NB_SQRT(a) __dsqrt_rn((a))
+#define NB_SQRT(a) nb_dsqrt((a))
 #define NB_RINT(a) rint((a))
 #define NB_FLOOR(a) floor((a))
 #else
@@ -58,12 +62,22 @@
 #define NB_RAD2DEG 0x1.ca5dc1a63c1f8p+5  /* 180.0 / pi as numpy's degrees() uses it */
 #define NB_SQRT2 0x1.6a09e667f3bcdp+0
 
+#ifdef __CUDACC__
+/* IEEE division and square root expand to ~40 instructions each: keep one copy */
+static __device__ __noinline__ double nb_ddiv_dev(double a, double b) { return __ddiv_rn(a, b); }
+static __device__ __noinline__ double nb_dsqrt_dev(double a) { return __dsqrt_rn(a); }
+#endif
+#ifdef __CUDA_ARCH__
+#define nb_ddiv(a, b) nb_ddiv_dev((a), (b))
+#define nb_dsqrt(a) nb_dsqrt_dev((a))
+#endif
+
 NB_HD uint64_t nb_d2u(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
 NB_HD double nb_u2d(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
 NB_HD double nb_inf(void) { return nb_u2d(0x7ff0000000000000ULL); }
 
 /* natural logarithm, x > 0 and normal (x == 0 gives -inf) */
-NB_HD double nb_log(double x)
+NB_HD_CALL double nb_log(double x)
 {
     if (x == 0.0) return -nb_inf();
     uint64_t bits = nb_d2u(x);
@@ -96,7 +110,7 @@ NB_HD double nb_log(double x)
 NB_HD double nb_log10(double x) { return NB_MUL(nb_log(x), NB_INV_LN10); }
 
 /* e^x */
-NB_HD double nb_exp(double x)
+NB_HD_CALL double nb_exp(double x)
 {
     if (x > 709.0) return nb_inf();
     if (x < -708.0) return 0.0;
@@ -123,7 +137,7 @@ NB_HD double nb_exp(double x)
 }
 
 /* 10^x with a compensated product x*ln10 */
-NB_HD double nb_exp10(double x)
+NB_HD_CALL double nb_exp10(double x)
 {
     double hi = NB_MUL(x, NB_LN10);
     double lo = NB_FMA(x, NB_LN10, -hi);
@@ -133,7 +147,7 @@ NB_HD double nb_exp10(double x)
 }
 
 /* b^e for 0 <= b <= 1, e > 0 (success probability of a block of e*256 bits) */
-NB_HD double nb_pow01(double b, double e)
+NB_HD_CALL double nb_pow01(double b, double e)
 {
     if (b <= 0.0) return 0.0;
     if (b >= 1.0) return 1.0;
@@ -171,7 +185,7 @@ NB_HD double nb_cos_k(double y)
 }
 
 /* cos(2 pi u), u in [0,1): exact octant reduction, then a Taylor kernel */
-NB_HD double nb_cos2pi(double u)
+NB_HD_CALL double nb_cos2pi(double u)
 {
     double t = NB_MUL(u, 4.0);                  /* exact */
     double qf = NB_FLOOR(t);
@@ -192,7 +206,7 @@ NB_HD double nb_cos2pi(double u)
 }
 
 /* atan(t), t >= 0 */
-NB_HD double nb_atan_pos(double t)
+NB_HD_CALL double nb_atan_pos(double t)
 {
     int inv = t > 1.0;
     if (inv) t = NB_DIV(1.0, t);
@@ -216,7 +230,7 @@ NB_HD double nb_atan_pos(double t)
 }
 
 /* acos(x), -1 <= x <= 1 */
-NB_HD double nb_acos(double x)
+NB_HD_CALL double nb_acos(double x)
 {
     if (x <= -1.0) return NB_PI;
     if (x >= 1.0) return 0.0;
@@ -226,7 +240,7 @@ NB_HD double nb_acos(double x)
 
 /* regularised incomplete beta I_x(3,4): the CDF scipy.stats.beta(3,4) evaluates in
  * the reference traffic model (system/ue_generator.py:30,74) */
-NB_HD double nb_beta34_cdf(double x)
+NB_HD_CALL double nb_beta34_cdf(double x)
 {
     if (x <= 0.0) return 0.0;
     if (x >= 1.0) return 1.0;

@@ -110,6 +110,11 @@ NB_CONST double nb_nprach_x0[8] = { -26.65585077, -28.25585118, -29.85584994, -3
 NB_CONST double nb_nprach_k[8] = { 0.32267874, 0.32267874, 0.32267875, 0.32267874,
                                    0.32267859, 0.32267876, 0.3226787, 0.3226787 };
 
+/* NPRACH_items (parameters.py:136-153) -> index in the 23-int action, and their control_default_values */
+NB_CONST uint8_t nb_nprach_item_idx[16] = { NB_A_BACKOFF, NB_A_RAR_WINDOW, NB_A_MAC_TIMER, NB_A_TRANSMAX, NB_A_PANCHOR, NB_A_TH_C1, NB_A_TH_C0,
+    NB_A_PERIOD_C0, NB_A_REP_C0, NB_A_SC_C0, NB_A_PERIOD_C1, NB_A_REP_C1, NB_A_SC_C1, NB_A_PERIOD_C2, NB_A_REP_C2, NB_A_SC_C2 };
+NB_CONST uint8_t nb_nprach_default_conf[16] = { 3, 6, 2, 4, 12, 8, 11, 3, 0, 1, 2, 0, 1, 3, 2, 1 };
+
 /* LUT2.csv geometry (channel.py:61-79): 56 curves (7 I_tbs x 8 N_rep) x 501 SNR points, BLER * 2^15 */
 #define NB_LUT_SNR_PTS 501
 #define NB_LUT_CURVES 56

@@ -35,7 +35,7 @@ NB_HD uint32_t nb_mulhi32(uint32_t a, uint32_t b, uint32_t *lo)
     return (uint32_t)(p >> 32);
 }
 
-NB_HD nb_block_t nb_philox(uint64_t seed, uint64_t ctr, uint32_t stream)
+NB_HD_CALL nb_block_t nb_philox(uint64_t seed, uint64_t ctr, uint32_t stream)
 {
     uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -112,7 +112,7 @@ NB_HD uint64_t nb_rng_bounded(uint64_t seed, uint64_t ctr, uint32_t stream, uint
 }
 
 /* standard normal deviate */
-NB_HD double nb_rng_normal(uint64_t seed, uint64_t ctr, uint32_t stream)
+NB_HD_CALL double nb_rng_normal(uint64_t seed, uint64_t ctr, uint32_t stream)
 {
     nb_block_t b = nb_philox(seed, ctr, stream);
     /* u1 in (0,1]: (m+1)/2^53 keeps ln finite; u2 in [0,1) */

@@ -7,7 +7,7 @@ from .controller import NbiotCtrl
 from .record import NbiotConf
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnbiot_b200.so')
+LIB_PATH = os.environ.get('NBIOT_LIB') or os.path.join(_HERE, 'libnbiot_b200.so')   # NBIOT_LIB: an alternative build (tuning experiments)
 
 # every symbol include/nbiot.h declares
 SYMBOLS = ['nbiot_abi_version', 'nbiot_last_error', 'nbiot_state_bytes', 'nbiot_hdr_bytes', 'nbiot_create', 'nbiot_destroy',

@@ -30,9 +30,11 @@
 #include "nbiot_state.h"
 #include "nbiot_warp.h"
 
-struct NbCtx {
-    NbHdr *h;                 /* shared memory while a kernel runs */
-    uint16_t *grid;           /* [C][W] column masks, shared memory */
+/* Per-warp working context. It sits in shared memory directly in front of the staged header and grid
+ *   [ NbCtx | NbHdr | grid[C][W] ]
+ * so the hot state is reached from the one register holding &ctx with constant offsets (no pointer chase),
+ * and the compiler is told it is shared memory. The HBM-resident arrays are reached through the pointers. */
+struct __attribute__((aligned(16))) NbCtx {
     NbRaEntry *ra[3];
     NbConnEntry *conn;
     NbContEntry *cont;
@@ -46,31 +48,39 @@ struct NbCtx {
     const uint16_t *lut2;
     const uint8_t *mcs;
     const nbiot_conf_t *conf;
-    int W, ue_cap, ra_cap, hist_cap, C;
     int32_t *evlog;           /* optional (t, type) pop log for debugging */
-    int evlog_cap;
+    int W, ue_cap, ra_cap, hist_cap, C, evlog_cap;
 };
 
-#define NB_FAULT(c, bit) ((c).h->fault |= (int32_t)(bit))
-#define NB_FATAL(c) ((c).h->fault & (int32_t)NBIOT_FAULT_FATAL_MASK)
+#if defined(__CUDA_ARCH__)
+#define NB_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define NB_ASSUME_SHARED(p) ((void)0)
+#endif
+NB_DEV NbHdr *nbc_hdr(NbCtx &c) { NbHdr *h = (NbHdr *)((char *)&c + sizeof(NbCtx)); NB_ASSUME_SHARED(h); return h; }
+NB_DEV uint16_t *nbc_grid(NbCtx &c) { return (uint16_t *)((char *)nbc_hdr(c) + sizeof(NbHdr)); }
+#define NB_WARP_BYTES(C, W) (sizeof(NbCtx) + sizeof(NbHdr) + (size_t)(C) * (size_t)(W) * 2u)
+
+#define NB_FAULT(c, bit) (nbc_hdr(c)->fault |= (int32_t)(bit))
+#define NB_FATAL(c) (nbc_hdr(c)->fault & (int32_t)NBIOT_FAULT_FATAL_MASK)
 #define NB_STATE(e) ((e).st_ce & 15u)
 #define NB_CE(e) (((e).st_ce >> 4) & 3u)
 
 /* ------------------------------------------------------------------ scalar draws */
-NB_DEV double nbc_u01(NbCtx &c) { return nb_rng_u01(c.h->seed, c.h->draws++, NBIOT_STREAM_ENV); }
+NB_DEV double nbc_u01(NbCtx &c) { return nb_rng_u01(nbc_hdr(c)->seed, nbc_hdr(c)->draws++, NBIOT_STREAM_ENV); }
 NB_DEV double nbc_normal(NbCtx &c, double mu, double sigma)
-{ return NB_ADD(mu, NB_MUL(sigma, nb_rng_normal(c.h->seed, c.h->draws++, NBIOT_STREAM_ENV))); }
+{ return NB_ADD(mu, NB_MUL(sigma, nb_rng_normal(nbc_hdr(c)->seed, nbc_hdr(c)->draws++, NBIOT_STREAM_ENV))); }
 NB_DEV int nbc_bernoulli(NbCtx &c, double p) { return nbc_u01(c) < p ? 1 : 0; }
 NB_DEV int nbc_integers(NbCtx &c, int low, int high)
-{ return low + (int)nb_rng_bounded(c.h->seed, c.h->draws++, NBIOT_STREAM_ENV, (uint64_t)(high - low)); }
+{ return low + (int)nb_rng_bounded(nbc_hdr(c)->seed, nbc_hdr(c)->draws++, NBIOT_STREAM_ENV, (uint64_t)(high - low)); }
 
-NB_DEV int nbc_rep_index(int N_rep) { int r = 0; while ((1 << r) < N_rep) ++r; return r; }
+NB_DEV int nbc_rep_index(int N_rep) { int r = 0; NB_NOUNROLL while ((1 << r) < N_rep) ++r; return r; }
 NB_DEV int nbc_sf_per_ru(int N_sc) { return N_sc == 12 ? 1 : N_sc == 6 ? 2 : N_sc == 3 ? 4 : N_sc == 1 ? 8 : -1; }
 
 /* ------------------------------------------------------------------ event pool */
-NB_DEV void nbc_pool_push(NbCtx &c, uint64_t key, int type, int ce, int aux)
+NB_FN void nbc_pool_push(NbCtx &c, uint64_t key, int type, int ce, int aux)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     if (!h->pool_free) { NB_FAULT(c, NBIOT_FAULT_EVENT_SLOTS); return; }
     int i = nbw_ffsll(h->pool_free) - 1;
     h->pool_free &= ~(1ULL << i);
@@ -78,19 +88,29 @@ NB_DEV void nbc_pool_push(NbCtx &c, uint64_t key, int type, int ce, int aux)
     h->pool[i] = e;
 }
 
-NB_DEV void nbc_pool_release(NbCtx &c, int i) { c.h->pool[i].type = NB_EV_NONE; c.h->pool[i].key = NB_KEY_NONE; c.h->pool_free |= 1ULL << i; }
+NB_DEV void nbc_pool_release(NbCtx &c, int i) { nbc_hdr(c)->pool[i].type = NB_EV_NONE; nbc_hdr(c)->pool[i].key = NB_KEY_NONE; nbc_hdr(c)->pool_free |= 1ULL << i; }
 
 /* ------------------------------------------------------------------ carrier grid (carrier.py:414-605) */
-NB_DEV uint16_t *nbc_col(NbCtx &c, int carrier, int t) { return &c.grid[carrier * c.W + (t & (c.W - 1))]; }
+NB_DEV uint16_t *nbc_col(NbCtx &c, int carrier, int t) { return &nbc_grid(c)[carrier * c.W + (t & (c.W - 1))]; }
 
 /* OR `mask` into columns [from, from+count) of one carrier */
-NB_DEV void nbc_grid_or(NbCtx &c, int carrier, int from, int count, uint32_t mask)
+NB_FN void nbc_grid_or(NbCtx &c, int carrier, int from, int count, uint32_t mask)
 {
     nbw_run([&]() -> int {
+        NB_NOUNROLL
         for (int k = nbw_lane(); k < count; k += NB_LANES) *nbc_col(c, carrier, from + k) |= (uint16_t)mask;
         nbw_sync();
         return 0;
     });
+}
+
+/* refresh the fixed event slots of one CE level from its occasion ring */
+NB_DEV void nbc_occ_keys(NbHdr *h, int ce)
+{
+    uint64_t ks = NB_KEY_NONE, ke = NB_KEY_NONE;
+    if (h->occ_head_start[ce] < h->occ_tail[ce]) { NbOccasion o = h->occ[ce][h->occ_head_start[ce] % NB_OCC_RING]; ks = NB_KEY(o.t_start, o.seq); }
+    if (h->occ_head_end[ce] < h->occ_tail[ce]) { NbOccasion o = h->occ[ce][h->occ_head_end[ce] % NB_OCC_RING]; ke = NB_KEY(o.t_start + o.N_sf, o.seq + 1u); }
+    h->keys[2 + ce] = ks; h->keys[5 + ce] = ke;
 }
 
 /* NprachResource next-start search + mutation at an idle column (carrier.py:301-332) */
@@ -99,6 +119,7 @@ NB_DEV int nbc_res_next_start(NbResource &r, int col)
     int tau0 = col - r.t_offset;
     if (tau0 > r.t_next) {                       /* t_next was reduced or the offset moved: re-sync */
         r.t_next = r.t_start + r.periodicity;
+        NB_NOUNROLL
         while (r.t_next < tau0) r.t_next += r.periodicity;
     }
     int cand = r.t_next;
@@ -108,8 +129,9 @@ NB_DEV int nbc_res_next_start(NbResource &r, int col)
 
 NB_DEV void nbc_sclog_register(NbCtx &c, int t, int ce, int sc)   /* carrier.py:262-265 */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int n = h->sclog_n < NB_SCLOG ? h->sclog_n : NB_SCLOG;
+    NB_NOUNROLL
     for (int i = 0; i < n; ++i) if (h->sclog_t[i] == t) return;
     int w = h->sclog_n % NB_SCLOG;               /* ring: entries older than the oldest pending occasion are dead */
     h->sclog_t[w] = t;
@@ -120,29 +142,34 @@ NB_DEV void nbc_sclog_register(NbCtx &c, int t, int ce, int sc)   /* carrier.py:
 
 NB_DEV int nbc_sclog_check(NbCtx &c, int t, int ce)               /* carrier.py:267-271, :454-459 */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     if (c.C == 1 || t == 0) return 0;
     int n = h->sclog_n < NB_SCLOG ? h->sclog_n : NB_SCLOG;
+    NB_NOUNROLL
     for (int i = 0; i < n; ++i) if (h->sclog_t[i] == t) return h->sclog_sc[i][ce];
     return 0;
 }
 
 /* Carrier.extend_lookahead (carrier.py:473-479) with SFGenerator.next (:382-404) run by run */
-NB_DEV void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
+NB_FN void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int a = h->t_ahead, b = new_t_ahead;
     if (b <= a) return;
     if (b - h->t_now > c.W) { NB_FAULT(c, NBIOT_FAULT_LOOKAHEAD); return; }
     /* fresh columns start empty */
     nbw_run([&]() -> int {
+        NB_NOUNROLL
         for (int cc = 0; cc < c.C; ++cc)
+            NB_NOUNROLL
             for (int k = a + nbw_lane(); k < b; k += NB_LANES) *nbc_col(c, cc, k) = 0;
         nbw_sync();
         return 0;
     });
     int cursor[2][3];
+    NB_NOUNROLL
     for (int cc = 0; cc < c.C; ++cc)
+        NB_NOUNROLL
         for (int ce = 0; ce < 3; ++ce) {
             NbResource &r = h->res[cc][ce];
             cursor[cc][ce] = a;
@@ -156,7 +183,9 @@ NB_DEV void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
     for (;;) {
         /* earliest start in (column, carrier, CE) order */
         int best = b, bc = -1, bce = -1;
+        NB_NOUNROLL
         for (int cc = 0; cc < c.C; ++cc)
+            NB_NOUNROLL
             for (int ce = 0; ce < 3; ++ce) {
                 NbResource &r = h->res[cc][ce];
                 if (!r.N_sc || cursor[cc][ce] >= b) continue;
@@ -179,6 +208,7 @@ NB_DEV void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
             h->occ[bce][h->occ_tail[bce] % NB_OCC_RING] = o;
             h->occ_tail[bce] += 1;
             h->seq += 2;
+            nbc_occ_keys(h, bce);
         } else nbc_sclog_register(c, best, bce, 4 * r.N_sc);
     }
     h->t_ahead = b;
@@ -186,29 +216,33 @@ NB_DEV void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
 
 NB_DEV void nbc_erase_past_sf(NbCtx &c, int t)                   /* carrier.py:481-489 */
 {
-    if (t > c.h->t_now) c.h->t_now = t;
+    if (t > nbc_hdr(c)->t_now) nbc_hdr(c)->t_now = t;
     nbc_extend_lookahead(c, t + NB_HORIZON);
 }
 
 /* Carrier.allocate_resources (carrier.py:556-605): first fit over delays x carriers x offsets */
-NB_DEV int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int N_sc, int N_sf)
+NB_FN int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int N_sc, int N_sf)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     nbc_erase_past_sf(c, t);
     if (NB_FATAL(c)) return 0;
+    NB_NOUNROLL
     for (int d = delay; d <= 64; d *= 2) {
         int new_t_ahead = t + d + N_sf;
         nbc_extend_lookahead(c, new_t_ahead);
         if (NB_FATAL(c)) return 0;
         int from = h->t_now + d;
+        NB_NOUNROLL
         for (int ci = 0; ci < c.C; ++ci) {
             int cc = ci == 0 ? carrier_id : (carrier_id == 0 ? 1 : 0);
             uint32_t busy = (uint32_t)nbw_run([&]() -> int {
                 uint32_t v = 0;
+                NB_NOUNROLL
                 for (int k = nbw_lane(); k < N_sf; k += NB_LANES) v |= *nbc_col(c, cc, from + k);
                 return (int)nbw_or_u32(v);
             });
             uint32_t m0 = (1u << N_sc) - 1u;
+            NB_NOUNROLL
             for (int off = 0; off < 12; off += N_sc) {
                 uint32_t m = m0 << off;
                 if (!(busy & m)) {
@@ -222,7 +256,7 @@ NB_DEV int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int 
 }
 
 /* NodeB.allocate_resources (node_b.py:435-450): retry with other subcarrier counts */
-NB_DEV int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc, int N_ru, int N_rep, int *out_sc, int *out_sf)
+NB_FN int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc, int N_ru, int N_rep, int *out_sc, int *out_sf)
 {
     int spr = nbc_sf_per_ru(N_sc);
     if (spr < 0) { NB_FAULT(c, NBIOT_FAULT_ACTION); *out_sc = N_sc; *out_sf = 0; return 0; }
@@ -230,6 +264,7 @@ NB_DEV int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc,
     int t_ul_end = nbc_carrier_allocate(c, c_id, ref_t, delay, N_sc, N_sf);
     if (!t_ul_end && c.conf->sc_adjustment && !NB_FATAL(c)) {
         int row = N_sc == 1 ? 0 : N_sc == 3 ? 1 : N_sc == 6 ? 2 : 3;
+        NB_NOUNROLL
         for (int i = 0; i < 3; ++i) {
             n_sc = nb_sc_fallback[row][i];
             N_sf = nbc_sf_per_ru(n_sc) * N_ru * N_rep;
@@ -242,11 +277,13 @@ NB_DEV int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc,
 }
 
 /* compute_offsets (carrier.py:115-252): time/frequency packing of the three NPRACH resources */
-NB_DEV int nbc_compute_offsets(const int periods[3], const int N_sfs[3], const int N_scs[3], int sc_off[3], int sf_off[3])
+NB_FN int nbc_compute_offsets(const int periods[3], const int N_sfs[3], const int N_scs[3], int sc_off[3], int sf_off[3])
 {
+    NB_NOUNROLL
     for (int i = 0; i < 3; ++i) sc_off[i] = sf_off[i] = 0;
     int min_length = N_sfs[0] + N_sfs[1] + N_sfs[2];
     int crit[3], ncrit = 0, norm[3], nnorm = 0;
+    NB_NOUNROLL
     for (int i = 0; i < 3; ++i) { if (periods[i] == 240) crit[ncrit++] = i; else norm[nnorm++] = i; }
     int max_sf = N_sfs[0] > N_sfs[1] ? N_sfs[0] : N_sfs[1]; if (N_sfs[2] > max_sf) max_sf = N_sfs[2];
     int sum_sc = N_scs[0] + N_scs[1] + N_scs[2];
@@ -278,7 +315,9 @@ NB_DEV int nbc_compute_offsets(const int periods[3], const int N_sfs[3], const i
             min_length = N_sfs[2] + N_sfs[1]; sc_off[0] = N_scs[2]; sf_off[1] = N_sfs[2];
         } else {
             int a[3] = { 0, 1, 2 };              /* stable sort by (period, N_sc, N_sf) */
+            NB_NOUNROLL
             for (int x = 1; x < 3; ++x)
+                NB_NOUNROLL
                 for (int y = x; y > 0; --y) {
                     int p = a[y - 1], q = a[y];
                     int gt = periods[p] != periods[q] ? periods[p] > periods[q]
@@ -293,6 +332,7 @@ NB_DEV int nbc_compute_offsets(const int periods[3], const int N_sfs[3], const i
         if (N_scs[0] <= N_scs[1]) sf_off[0] = N_sfs[1]; else sf_off[1] = N_sfs[0];
     }
     int min_periodicity = -1;
+    NB_NOUNROLL
     for (int i = 0; i < 7; ++i)
         if (nb_nprach_period_list[i] >= min_length && (min_periodicity < 0 || nb_nprach_period_list[i] < min_periodicity))
             min_periodicity = nb_nprach_period_list[i];
@@ -301,10 +341,11 @@ NB_DEV int nbc_compute_offsets(const int periods[3], const int N_sfs[3], const i
 }
 
 /* Carrier.update_ra_parameters (carrier.py:610-650) + SFGenerator.update (:377-380) + NprachResource.update (:345-355) */
-NB_DEV void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int th_C0)
+NB_FN void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int th_C0)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int periods[3], N_sfs[3], N_scs[3];
+    NB_NOUNROLL
     for (int i = 0; i < 3; ++i) {
         periods[i] = nb_nprach_period_list[args[i][0]];
         N_sfs[i] = nb_nprach_nsf_list[args[i][1]];
@@ -313,7 +354,9 @@ NB_DEV void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int
     if (th_C0 == 0) { periods[0] = nb_nprach_period_list[0]; N_sfs[0] = 0; N_scs[0] = 0; }
     if (th_C1 == 0) { periods[1] = nb_nprach_period_list[0]; N_sfs[1] = 0; N_scs[1] = 0; }
     int per_carrier[2][3];
+    NB_NOUNROLL
     for (int cc = 0; cc < c.C; ++cc)
+        NB_NOUNROLL
         for (int i = 0; i < 3; ++i) {
             int take = N_scs[i] < 12 ? N_scs[i] : 12;
             per_carrier[cc][i] = take;
@@ -321,7 +364,9 @@ NB_DEV void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int
         }
     int sc_off[3], sf_off[3];
     (void)nbc_compute_offsets(periods, N_sfs, per_carrier[0], sc_off, sf_off);   /* validity ignored (carrier.py:638) */
+    NB_NOUNROLL
     for (int cc = 0; cc < c.C; ++cc)
+        NB_NOUNROLL
         for (int ce = 0; ce < 3; ++ce) {
             int rt = h->res[cc][0].t_start;
             if (h->res[cc][1].t_start > rt) rt = h->res[cc][1].t_start;
@@ -336,36 +381,37 @@ NB_DEV void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int
 }
 
 /* ------------------------------------------------------------------ NodeB helpers */
-NB_DEV int nbc_rar_sum(NbCtx &c, int ce) { int s = 0; for (int i = 0; i < c.h->rar_n[ce]; ++i) s += c.h->RAR_UEs[ce][i]; return s; }
+NB_FN int nbc_rar_sum(NbCtx &c, int ce) { int s = 0; NB_NOUNROLL for (int i = 0; i < nbc_hdr(c)->rar_n[ce]; ++i) s += nbc_hdr(c)->RAR_UEs[ce][i]; return s; }
 
-NB_DEV void nbc_update_state(NbCtx &c)                           /* node_b.py:264-276 */
+NB_FN void nbc_update_state(NbCtx &c)                           /* node_b.py:264-276 */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     if (nbc_rar_sum(c, 0) + nbc_rar_sum(c, 1) + nbc_rar_sum(c, 2)) h->state = NB_ST_RAR_WINDOW;
     else if (h->conn_n > 0) h->state = NB_ST_SCHEDULING;
     else h->state = NB_ST_IDLE;
 }
 
-NB_DEV void nbc_schedule_NPDCCH(NbCtx &c, int elapsed_sfs)       /* node_b.py:420-432 */
+NB_FN void nbc_schedule_NPDCCH(NbCtx &c, int elapsed_sfs)       /* node_b.py:420-432 */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int left = h->NPDCCH_sf_left - elapsed_sfs; if (left < 0) left = 0;
     int next_time = h->time + elapsed_sfs;
     if (!left) { next_time += NB_NPDCCH_PERIOD; left = NB_NPDCCH_SF; }
     h->NPDCCH_sf_left = left;
-    h->ev_npdcch = NB_KEY(next_time, h->seq);
+    h->keys[0] = NB_KEY(next_time, h->seq);
     h->seq += 1;
 }
 
 /* ------------------------------------------------------------------ random-access lists */
 /* order-preserving removal of tombstones */
-NB_DEV void nbc_ra_compact(NbCtx &c, int ce)
+NB_FN void nbc_ra_compact(NbCtx &c, int ce)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int n = h->ra_n[ce];
     NbRaEntry *L = c.ra[ce];
     int out = nbw_run([&]() -> int {
         int o = 0;
+        NB_NOUNROLL
         for (int base = 0; base < n; base += NB_LANES) {
             int i = base + nbw_lane();
             NbRaEntry e; e.st_ce = NB_RA_TOMB;
@@ -382,9 +428,9 @@ NB_DEV void nbc_ra_compact(NbCtx &c, int ce)
     h->ra_n[ce] = out;
 }
 
-NB_DEV void nbc_ra_append(NbCtx &c, int ce, int slot, int state, int ue_ce, int attempts, int rar_w_id)
+NB_FN void nbc_ra_append(NbCtx &c, int ce, int slot, int state, int ue_ce, int attempts, int rar_w_id)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     if (h->ra_n[ce] >= c.ra_cap) {
         nbc_ra_compact(c, ce);
         if (h->ra_n[ce] >= c.ra_cap) { NB_FAULT(c, NBIOT_FAULT_UE_SLOTS); return; }
@@ -407,11 +453,11 @@ NB_DEV double nbc_find_y(double x1, double y1, double x2, double y2, double x)  
 #define NB_S32 0.8660254037844386
 
 /* Channel.set_xy_loss / generate_xy / location / antenna_pattern (channel.py:100-118, :134-151) */
-NB_DEV double nbc_place_ue(NbCtx &c)
+NB_FN double nbc_place_ue(NbCtx &c)
 {
     double x, y;
     for (;;) {
-        nb_rng_pair(c.h->seed, c.h->draws++, NBIOT_STREAM_ENV, &x, &y);
+        nb_rng_pair(nbc_hdr(c)->seed, nbc_hdr(c)->draws++, NBIOT_STREAM_ENV, &x, &y);
         int in_cell = (y > nbc_find_y(0, NB_S34, 0.25, 0, x)) && (y > nbc_find_y(0.75, 0, 1, NB_S34, x)) &&
                       (y < nbc_find_y(0, NB_S34, 0.25, NB_S32, x)) && (y < nbc_find_y(0.75, NB_S32, 1, NB_S34, x)) && (y < NB_S32);
         if (in_cell) break;
@@ -431,9 +477,9 @@ NB_DEV double nbc_place_ue(NbCtx &c)
 }
 
 /* UEGenerator.generate_arrivals (ue_generator.py:54-81) + Population.get_new_arrivals (population.py:103-132) */
-NB_DEV void nbc_new_arrivals(NbCtx &c, int t)
+NB_FN void nbc_new_arrivals(NbCtx &c, int t)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     if (c.conf->random_traffic) {                 /* update_counter (ue_generator.py:45-52) */
         int new_count = t / NB_T_UNIFORM;
         if (new_count > h->gen_counter) { h->gen_counter = new_count; h->gen_p = NB_ADD(0.0, NB_MUL(0.8, nbc_u01(c))); }
@@ -456,6 +502,7 @@ NB_DEV void nbc_new_arrivals(NbCtx &c, int t)
     }
     h->gen_t = t;
     int total = arrivals + beta_arrivals;
+    NB_NOUNROLL
     for (int n = 0; n < total; ++n) {
         h->ue_count += 1;
         int buffer = c.conf->buffer_hi > c.conf->buffer_lo ? nbc_integers(c, c.conf->buffer_lo, c.conf->buffer_hi + 1) : c.conf->buffer_lo;
@@ -471,6 +518,7 @@ NB_DEV void nbc_new_arrivals(NbCtx &c, int t)
         u.loss = loss; u.sinr = 0.0; u.id = h->ue_count; u.t_arrival = t; u.t_connection = 0; u.timestamp = 0; u.acked_data = 0;
         u.rar_w_id = 0; u.buffer = (uint16_t)buffer; u.retx_buffer = 0; u.bits = 0; u.tbs = 0; u.I_tbs = 0; u.N_rep = 0; u.N_ru = 0;
         u.CE_level = (uint8_t)CE_level; u.state = NB_UE_RAO; u.attempts = 0; u.beta = (uint8_t)beta; u.new_data = 1; u.where = NB_IN_RA;
+        NB_NOUNROLL
         for (int k = 0; k < 7; ++k) u.pad[k] = 0;
         c.ue[slot] = u;
         nbc_ra_append(c, CE_level, slot, NB_UE_RAO, CE_level, 0, 0);
@@ -482,9 +530,9 @@ NB_DEV void nbc_new_arrivals(NbCtx &c, int t)
 /* ------------------------------------------------------------------ NPRACH pass */
 /* AccessProcedure.NPRACH_start (access_procedure.py:37-91), Population.NPRACH_start (population.py:168-188),
  * Channel.preamble_detection (channel.py:156-176) */
-NB_DEV void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
+NB_FN void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int t = occ.t_start, N_sc = occ.N_sc, N_sf = occ.N_sf, N_pream = 4 * occ.N_sc;
     int rep = 0; while (rep < 7 && nb_nprach_nsf_list[rep] != N_sf) ++rep;      /* N_sf_to_N_rep (carrier.py:25-26) */
     int counter = h->RAR_counter[ce];
@@ -497,6 +545,7 @@ NB_DEV void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
     /* pass 1: compact the list, pick the UEs waiting for an opportunity, in list order */
     int n_ues = nbw_run([&]() -> int {
         int o = 0, ns = 0;
+        NB_NOUNROLL
         for (int base = 0; base < n; base += NB_LANES) {
             int i = base + nbw_lane();
             NbRaEntry e; e.st_ce = NB_RA_TOMB; e.wake_t = e.wake_seq = 0; e.rar_w_id = 0; e.slot = 0; e.attempts = 0;
@@ -527,16 +576,19 @@ NB_DEV void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
         double p = h->probability_anchor;
         na_ues = nbw_run([&]() -> int {
             int s = 0;
+            NB_NOUNROLL
             for (int r = nbw_lane(); r < n_ues; r += NB_LANES) s += nb_rng_bernoulli(seed, ctr + (uint64_t)r, NBIOT_STREAM_ENV, p);
             return nbw_add_i32(s);
         });
         ctr += (uint64_t)n_ues;
         h->NPRACH_resources += (int64_t)Na_sc * N_sf;
     }
+    NB_NOUNROLL
     for (int w = 0; w < 8; ++w) { h->pre_once[w] = 0; h->pre_twice[w] = 0; }
     /* pass 2: one preamble per contender (counter ctr + rank), histogram into once/twice bit sets */
     nbw_run([&]() -> int {
         nbw_sync();
+        NB_NOUNROLL
         for (int r = nbw_lane(); r < n_ues; r += NB_LANES) {
             int pre = r < na_ues ? N_pream + (int)nb_rng_bounded(seed, ctr + (uint64_t)r, NBIOT_STREAM_ENV, (uint64_t)(4 * Na_sc))
                                  : (int)nb_rng_bounded(seed, ctr + (uint64_t)r, NBIOT_STREAM_ENV, (uint64_t)N_pream);
@@ -555,6 +607,7 @@ NB_DEV void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
     int n_single = 0;
     int detected = nbw_run([&]() -> int {
         int det_total = 0, q0 = 0;
+        NB_NOUNROLL
         for (int base = 0; base < n_ues; base += NB_LANES) {
             int r = base + nbw_lane();
             int idx = 0, pre = 0;
@@ -581,6 +634,7 @@ NB_DEV void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
     });
     h->draws = ctr + 2u * (uint64_t)n_single;
     int collided = 0;
+    NB_NOUNROLL
     for (int w = 0; w < 8; ++w) collided += nbw_popc(h->pre_twice[w]);
     h->detected_pre[ce] = detected;
     h->collided_pre[ce] = collided;
@@ -590,9 +644,9 @@ NB_DEV void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
 }
 
 /* AccessProcedure.NPRACH_end (access_procedure.py:93-116) + NodeB.start_RAR_window (node_b.py:524-554) */
-NB_DEV void nbc_NPRACH_end(NbCtx &c, int ce, int t)
+NB_FN void nbc_NPRACH_end(NbCtx &c, int ce, int t)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int counter = h->RAR_counter[ce];
     int n_ues = h->contenders[ce];
     int detections = h->detected_pre[ce];
@@ -614,13 +668,14 @@ NB_DEV void nbc_NPRACH_end(NbCtx &c, int ce, int t)
 }
 
 /* ------------------------------------------------------------------ contention set / MAC timers */
-NB_DEV void nbc_mac_refresh(NbCtx &c)
+NB_FN void nbc_mac_refresh(NbCtx &c)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int n = h->cont_n;
     uint64_t best = NB_KEY_NONE; int bidx = -1;
     nbw_run([&]() -> int {
         uint64_t k = NB_KEY_NONE; int idx = -1;
+        NB_NOUNROLL
         for (int i = nbw_lane(); i < n; i += NB_LANES) { uint64_t ki = c.cont[i].key; if (ki < k) { k = ki; idx = i; } }
         uint64_t m = nbw_min_u64(k);
         uint32_t who = nbw_ballot(k == m && idx >= 0);
@@ -633,19 +688,20 @@ NB_DEV void nbc_mac_refresh(NbCtx &c)
 
 NB_DEV void nbc_cont_remove(NbCtx &c, int idx)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     h->cont_n -= 1;
     if (idx != h->cont_n) c.cont[idx] = c.cont[h->cont_n];
     h->mac_valid = 0;
 }
 
 /* Population.msg3_grant (population.py:201-256): the first UE of the list that is in RAR state */
-NB_DEV void nbc_msg3_grant(NbCtx &c, int ce, int t, int t_msg3_end, int I_tbs, int N_rep)
+NB_FN void nbc_msg3_grant(NbCtx &c, int ce, int t, int t_msg3_end, int I_tbs, int N_rep)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     NbRaEntry *L = c.ra[ce];
     int n = h->ra_n[ce];
     int idx = nbw_run([&]() -> int {
+        NB_NOUNROLL
         for (int base = 0; base < n; base += NB_LANES) {
             int i = base + nbw_lane();
             int hit = i < n && L[i].st_ce != NB_RA_TOMB && NB_STATE(L[i]) == NB_UE_RAR;
@@ -671,7 +727,7 @@ NB_DEV void nbc_msg3_grant(NbCtx &c, int ce, int t, int t_msg3_end, int I_tbs, i
 }
 
 /* Population.MAC_timeout (population.py:151-163) */
-NB_DEV void nbc_MAC_timeout(NbCtx &c, int idx)
+NB_FN void nbc_MAC_timeout(NbCtx &c, int idx)
 {
     NbContEntry e = c.cont[idx];
     nbc_cont_remove(c, idx);
@@ -681,9 +737,9 @@ NB_DEV void nbc_MAC_timeout(NbCtx &c, int idx)
 }
 
 /* Population.RAR_window_end (population.py:258-306): unserved UEs of the window back off */
-NB_DEV void nbc_population_RAR_window_end(NbCtx &c, int t, int ce, int backoff, int rar_w_id)
+NB_FN void nbc_population_RAR_window_end(NbCtx &c, int t, int ce, int backoff, int rar_w_id)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     NbRaEntry *L = c.ra[ce];
     int n = h->ra_n[ce];
     uint64_t seed = h->seed, ctr = h->draws;
@@ -692,6 +748,7 @@ NB_DEV void nbc_population_RAR_window_end(NbCtx &c, int t, int ce, int backoff, 
     int n_nz = 0;
     int n_sel = nbw_run([&]() -> int {
         int ns = 0, nz = 0;
+        NB_NOUNROLL
         for (int base = 0; base < n; base += NB_LANES) {
             int i = base + nbw_lane();
             NbRaEntry e; e.st_ce = NB_RA_TOMB; e.wake_t = e.wake_seq = 0; e.rar_w_id = 0; e.slot = 0; e.attempts = 0;
@@ -728,9 +785,9 @@ NB_DEV void nbc_population_RAR_window_end(NbCtx &c, int t, int ce, int backoff, 
 }
 
 /* ------------------------------------------------------------------ connected queue */
-NB_DEV void nbc_conn_insert(NbCtx &c, int slot)
+NB_FN void nbc_conn_insert(NbCtx &c, int slot)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     NbUe *u = &c.ue[slot];
     uint64_t k1;
     if (c.conf->sort_by_loss) k1 = nb_d2u(u->loss);           /* loss > 0: the bit pattern orders like the value */
@@ -743,8 +800,10 @@ NB_DEV void nbc_conn_insert(NbCtx &c, int slot)
     nbw_run([&]() -> int {
         /* stable sort position: after every entry whose key is <= k1 (the new stamp is the largest) */
         int cnt = 0;
+        NB_NOUNROLL
         for (int i = nbw_lane(); i < n; i += NB_LANES) cnt += Q[i].k1 <= k1;
         int pos = nbw_add_i32(cnt);
+        NB_NOUNROLL
         for (int hi = n; hi > pos; hi -= NB_LANES) {
             int i = hi - 1 - nbw_lane();
             NbConnEntry m; m.k1 = 0; m.order = 0; m.slot = 0; m.ce = 0; m.pad = 0;
@@ -761,19 +820,21 @@ NB_DEV void nbc_conn_insert(NbCtx &c, int slot)
     u->where = NB_IN_CONNECTED;
 }
 
-NB_DEV void nbc_conn_remove(NbCtx &c, int slot)
+NB_FN void nbc_conn_remove(NbCtx &c, int slot)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int n = h->conn_n;
     NbConnEntry *Q = c.conn;
     int found = nbw_run([&]() -> int {
         int idx = -1;
+        NB_NOUNROLL
         for (int base = 0; base < n; base += NB_LANES) {
             int i = base + nbw_lane();
             uint32_t m = nbw_ballot(i < n && Q[i].slot == (uint16_t)slot);
             if (m) { idx = base + nbw_ffs(m) - 1; break; }
         }
         if (idx < 0) return -1;
+        NB_NOUNROLL
         for (int base = idx; base < n - 1; base += NB_LANES) {
             int i = base + nbw_lane();
             NbConnEntry m; m.k1 = 0; m.order = 0; m.slot = 0; m.ce = 0; m.pad = 0;
@@ -789,20 +850,22 @@ NB_DEV void nbc_conn_remove(NbCtx &c, int slot)
 
 /* the first N_users UEs of the sorted queue whose CE level the remaining NPDCCH subframes allow
  * (NodeB.get_node_info, node_b.py:301-312) */
-NB_DEV void nbc_conn_select(NbCtx &c)
+NB_FN void nbc_conn_select(NbCtx &c)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int max_CE = nb_ce_for_sf_left[h->NPDCCH_sf_left];
     int n = h->conn_n;
     NbConnEntry *Q = c.conn;
     int sel[4] = { -1, -1, -1, -1 };
     int cnt = nbw_run([&]() -> int {
         int ns = 0;
+        NB_NOUNROLL
         for (int base = 0; base < n && ns < NB_N_USERS; base += NB_LANES) {
             int i = base + nbw_lane();
             int ok = i < n && Q[i].ce <= max_CE;
             uint32_t slot = i < n ? Q[i].slot : 0u;
             uint32_t m = nbw_ballot(ok);
+            NB_NOUNROLL
             while (m && ns < NB_N_USERS) {
                 int src = nbw_ffs(m) - 1;
                 sel[ns++] = (int)nbw_shfl(slot, src);
@@ -812,11 +875,12 @@ NB_DEV void nbc_conn_select(NbCtx &c)
         return ns;
     });
     h->n_sel = cnt;
+    NB_NOUNROLL
     for (int i = 0; i < 4; ++i) h->sel_slot[i] = sel[i];
 }
 
 /* ------------------------------------------------------------------ receptions */
-NB_DEV double nbc_get_bler(NbCtx &c, double snr, int itbs, int nr)   /* channel.py:76-79 */
+NB_FN double nbc_get_bler(NbCtx &c, double snr, int itbs, int nr)   /* channel.py:76-79 */
 {
     if (!(snr > -30.0)) snr = -30.0;
     if (!(snr < 20.0)) snr = 20.0;
@@ -825,14 +889,16 @@ NB_DEV double nbc_get_bler(NbCtx &c, double snr, int itbs, int nr)   /* channel.
     return NB_DIV((double)NB_LDG(&c.lut2[(row * 8 + rep) * NB_LUT_SNR_PTS + idx]), NB_LUT_SCALE);
 }
 
-NB_DEV void nbc_distribution_update(NbCtx &c, double sample)       /* node_b.py:207-225 */
+NB_FN void nbc_distribution_update(NbCtx &c, double sample)       /* node_b.py:207-225 */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     if (h->k_dist > 1000) return;
     h->k_dist += 1;
     int idx = 14;
+    NB_NOUNROLL
     for (int i = 0; i < 14; ++i) if (NB_ADD(sample, 35.0) < (double)nb_threshold_list[i]) { idx = i; break; }
     double k = (double)h->k_dist;
+    NB_NOUNROLL
     for (int i = 0; i < 15; ++i) {
         double prob = h->distribution[i];
         h->distribution[i] = NB_ADD(prob, NB_DIV(NB_SUB(i == idx ? 1.0 : 0.0, prob), k));
@@ -841,9 +907,9 @@ NB_DEV void nbc_distribution_update(NbCtx &c, double sample)       /* node_b.py:
 
 /* RxProcedure.msg3_event (rx_procedure.py:29-51), Channel.msg3_detection / sinr_estimation
  * (channel.py:178-198, :221-234), NodeB.msg3_outcome (node_b.py:770-799) */
-NB_DEV void nbc_msg3_event(NbCtx &c, int slot, int t)
+NB_FN void nbc_msg3_event(NbCtx &c, int slot, int t)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     NbUe *u = &c.ue[slot];
     double LogF = nbc_normal(c, 0.0, NB_SIGMA_F);
     double rx_pw = NB_SUB(NB_SUB(NB_TX_PW, u->loss), LogF);
@@ -854,11 +920,13 @@ NB_DEV void nbc_msg3_event(NbCtx &c, int slot, int t)
     double p = nb_pow01(NB_SUB(1.0, bler), (double)NB_MSG3_TBS / 256.0);
     int connected = nbc_bernoulli(c, p);
     int uce = u->CE_level, i_ = 0, window_active = 0;
+    NB_NOUNROLL
     for (int i = 0; i < h->rar_n[uce]; ++i) if (h->RAR_w_ids[uce][i] == u->rar_w_id) { window_active = 1; i_ = i; break; }
     if (connected) {
         u->state = NB_UE_CONNECTED; u->t_connection = t;
         int n = h->cont_n;
         int idx = nbw_run([&]() -> int {                       /* population.msg4: leave the contention set */
+            NB_NOUNROLL
             for (int base = 0; base < n; base += NB_LANES) {
                 int i = base + nbw_lane();
                 uint32_t m = nbw_ballot(i < n && c.cont[i].slot == (uint16_t)slot);
@@ -886,9 +954,9 @@ NB_DEV void nbc_msg3_event(NbCtx &c, int slot, int t)
 
 /* RxProcedure.NPUSCH_end (rx_procedure.py:54-61), Channel.NPUSCH_detection (channel.py:236-256),
  * NodeB.NPUSCH_end (node_b.py:801-830), PerfMonitor.account_rx/account_error/unregister_ue */
-NB_DEV void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
+NB_FN void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     NbUe *u = &c.ue[slot];
     double LogF = nbc_normal(c, 0.0, NB_SIGMA_F);
     double rx_pw = NB_SUB(NB_SUB(NB_TX_PW, u->loss), LogF);
@@ -957,15 +1025,16 @@ NB_DEV int nbc_scheduling_action(NbCtx &c, const uint8_t *a, int RAR_action, NbS
 
 NB_DEV int nbc_rar_list_cmp(NbCtx &c, int a, int b)              /* Python list comparison of RAR_UEs[a], RAR_UEs[b] */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int na = h->rar_n[a], nb = h->rar_n[b], n = na < nb ? na : nb;
+    NB_NOUNROLL
     for (int i = 0; i < n; ++i) if (h->RAR_UEs[a][i] != h->RAR_UEs[b][i]) return h->RAR_UEs[a][i] < h->RAR_UEs[b][i] ? -1 : 1;
     return na == nb ? 0 : (na < nb ? -1 : 1);
 }
 
-NB_DEV void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:453-521 */
+NB_FN void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:453-521 */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     NbSched P;
     if (!nbc_scheduling_action(c, a, 1, &P)) return;
     int CE_level = P.i, I_tbs = P.I_tbs, N_ru = P.N_ru, N_rep = P.N_rep;
@@ -977,12 +1046,15 @@ NB_DEV void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:45
     int NPDCCH_sf = nb_npdcch_sf_per_ce[CE_level];
     if (!(RAR_ues[CE_level] > 0) || NPDCCH_sf > h->NPDCCH_sf_left || c.conf->ce_mcs_automatic) {
         int order[3] = { 0, 1, 2 };                            /* stable descending sort by list value */
+        NB_NOUNROLL
         for (int x = 1; x < 3; ++x)
+            NB_NOUNROLL
             for (int y = x; y > 0; --y) {
                 if (nbc_rar_list_cmp(c, order[y - 1], order[y]) < 0) { int tmp = order[y - 1]; order[y - 1] = order[y]; order[y] = tmp; }
                 else break;
             }
         valid_control = 0;
+        NB_NOUNROLL
         for (int x = 0; x < 3; ++x) {
             CE_level = order[x];
             NPDCCH_sf = nb_npdcch_sf_per_ce[CE_level];
@@ -1001,6 +1073,7 @@ NB_DEV void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:45
     if (t_ul_end) {
         nbc_msg3_grant(c, CE_level, reference_time, t_ul_end, I_tbs, N_rep);
         h->RAR_sent[CE_level] += 1;
+        NB_NOUNROLL
         for (int i = 0; i < h->rar_n[CE_level]; ++i) if (h->RAR_UEs[CE_level][i] > 0) { h->RAR_UEs[CE_level][i] -= 1; break; }
         h->msg3_resources += (int64_t)N_sc * n_sf;
     } else h->valid_CE_control = 0;
@@ -1008,9 +1081,9 @@ NB_DEV void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:45
     nbc_update_state(c);
 }
 
-NB_DEV void nbc_step_RAR_end(NbCtx &c, const uint8_t *a)         /* node_b.py:558-581 */
+NB_FN void nbc_step_RAR_end(NbCtx &c, const uint8_t *a)         /* node_b.py:558-581 */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int ce = h->cur_ce;
     if (a[NB_A_BACKOFF] > 11) { NB_FAULT(c, NBIOT_FAULT_ACTION); return; }
     int backoff = nb_backoff_list[a[NB_A_BACKOFF]];
@@ -1019,6 +1092,7 @@ NB_DEV void nbc_step_RAR_end(NbCtx &c, const uint8_t *a)         /* node_b.py:55
     nbc_population_RAR_window_end(c, h->cur_t, ce, backoff, h->cur_wid);
     if (h->rar_n[ce] > 0) {
         h->RAR_failed[ce] = h->RAR_UEs[ce][0];
+        NB_NOUNROLL
         for (int i = 1; i < h->rar_n[ce]; ++i) { h->RAR_UEs[ce][i - 1] = h->RAR_UEs[ce][i]; h->RAR_w_ids[ce][i - 1] = h->RAR_w_ids[ce][i]; }
         h->rar_n[ce] -= 1;
     }
@@ -1027,14 +1101,14 @@ NB_DEV void nbc_step_RAR_end(NbCtx &c, const uint8_t *a)         /* node_b.py:55
 
 NB_DEV void nbc_clear_info(NbCtx &c)                             /* perf_monitor.py:96-103 */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     h->n_rx = h->n_err = h->n_unfit = h->n_acc = 0;
     h->rx_sum = 0.0; h->rx_inv_sum = 0.0; h->rx_log_sum = 0.0;
 }
 
-NB_DEV void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:584-693 */
+NB_FN void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:584-693 */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     nbc_clear_info(c);
     if (h->n_sel == 0) { nbc_schedule_NPDCCH(c, h->NPDCCH_sf_left); nbc_update_state(c); return; }
     NbSched P;
@@ -1050,6 +1124,7 @@ NB_DEV void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:58
         if (li < 1214) li = 1214;
         if (li > 1713) { NB_FAULT(c, NBIOT_FAULT_MCS_KEY); return; }
         int ti = NB_N_TBS - 1;
+        NB_NOUNROLL
         for (int i = 0; i < NB_N_TBS; ++i) if (nb_tbs_list[i] >= u->buffer) { ti = i; break; }
         tbs = nb_tbs_list[ti];
         const uint8_t *e = &c.mcs[((li - 1214) * NB_N_TBS + ti) * 3];
@@ -1090,14 +1165,13 @@ NB_DEV void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:58
     nbc_update_state(c);
 }
 
-NB_DEV void nbc_step_update(NbCtx &c, const uint8_t *a)          /* node_b.py:695-768 */
+NB_FN void nbc_step_update(NbCtx &c, const uint8_t *a)          /* node_b.py:695-768 */
 {
-    NbHdr *h = c.h;
-    const int item_idx[16] = { NB_A_BACKOFF, NB_A_RAR_WINDOW, NB_A_MAC_TIMER, NB_A_TRANSMAX, NB_A_PANCHOR, NB_A_TH_C1, NB_A_TH_C0,
-        NB_A_PERIOD_C0, NB_A_REP_C0, NB_A_SC_C0, NB_A_PERIOD_C1, NB_A_REP_C1, NB_A_SC_C1, NB_A_PERIOD_C2, NB_A_REP_C2, NB_A_SC_C2 };
+    NbHdr *h = nbc_hdr(c);
     h->thr_count = 0;
     int conf[16];
-    for (int i = 0; i < 16; ++i) conf[i] = a[item_idx[i]];
+    NB_NOUNROLL
+    for (int i = 0; i < 16; ++i) conf[i] = a[nb_nprach_item_idx[i]];
     int sc_max = c.C == 1 ? 3 : 7;
     if (conf[1] > 7 || conf[2] > 7 || conf[3] > 10 || conf[4] > 15 || conf[5] > 14 || conf[6] > 14 || conf[7] > 6 || conf[10] > 6 ||
         conf[13] > 6 || conf[9] > sc_max || conf[12] > sc_max || conf[15] > sc_max) { NB_FAULT(c, NBIOT_FAULT_ACTION); return; }
@@ -1115,35 +1189,31 @@ NB_DEV void nbc_step_update(NbCtx &c, const uint8_t *a)          /* node_b.py:69
     h->probability_anchor = nb_panchor_den[conf[4]] ? NB_DIV(1.0, (double)nb_panchor_den[conf[4]]) : 0.0;
     const int args[3][3] = { { conf[7], rep_C0, conf[9] }, { conf[10], rep_C1, conf[12] }, { conf[13], rep_C2, conf[15] } };
     nbc_carrier_update_ra(c, args, th_C1, th_C0);
+    NB_NOUNROLL
     for (int ce = 0; ce < 3; ++ce) h->RAR_window_size[ce] = RAR_window_size;
+    NB_NOUNROLL
     for (int i = 0; i < 16; ++i) h->nprach_conf[i] = (uint8_t)conf[i];
-    h->ev_update = NB_KEY(h->cur_t + NB_NPRACH_UPDATE_PERIOD, h->seq);
+    h->keys[1] = NB_KEY(h->cur_t + NB_NPRACH_UPDATE_PERIOD, h->seq);
     h->seq += 1;
     nbc_update_state(c);
 }
 
 /* ------------------------------------------------------------------ event selection */
-/* candidate codes: 0 NPDCCH_arrival, 1 NPRACH_update, 2+ce NPRACH_start, 5+ce NPRACH_end, 8 MAC_timer, 16+i pool[i] */
-NB_DEV uint64_t nbc_next_event(NbCtx &c, int *code)
+/* candidate codes: 0 NPDCCH_arrival, 1 NPRACH_update, 2+ce NPRACH_start, 5+ce NPRACH_end, 8 MAC_timer, 16+i pool[i].
+ * The minimum (time, insertion count) key over the fixed slots and the pool = the reference's heap pop. */
+NB_FN uint64_t nbc_next_event(NbCtx &c, int *code)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     if (!h->mac_valid) nbc_mac_refresh(c);
+    h->keys[8] = h->cont_n > 0 ? h->next_mac : NB_KEY_NONE;
     uint64_t best = NB_KEY_NONE; int bcode = -1;
     nbw_run([&]() -> int {
+        nbw_sync();
         uint64_t k = NB_KEY_NONE; int cd = -1;
-        for (int j = nbw_lane(); j < 9 + NB_EV_POOL; j += NB_LANES) {
-            uint64_t kj = NB_KEY_NONE; int cj = -1;
-            if (j == 0) { kj = h->ev_npdcch; cj = 0; }
-            else if (j == 1) { kj = h->ev_update; cj = 1; }
-            else if (j < 5) {
-                int ce = j - 2;
-                if (h->occ_head_start[ce] < h->occ_tail[ce]) { NbOccasion o = h->occ[ce][h->occ_head_start[ce] % NB_OCC_RING]; kj = NB_KEY(o.t_start, o.seq); cj = j; }
-            } else if (j < 8) {
-                int ce = j - 5;
-                if (h->occ_head_end[ce] < h->occ_tail[ce]) { NbOccasion o = h->occ[ce][h->occ_head_end[ce] % NB_OCC_RING]; kj = NB_KEY(o.t_start + o.N_sf, o.seq + 1u); cj = j; }
-            } else if (j == 8) { kj = h->cont_n > 0 ? h->next_mac : NB_KEY_NONE; cj = 8; }
-            else { int i = j - 9; if (!((h->pool_free >> i) & 1ULL)) { kj = h->pool[i].key; cj = 16 + i; } }
-            if (kj < k) { k = kj; cd = cj; }
+        NB_NOUNROLL
+        for (int j = nbw_lane(); j < 16 + NB_EV_POOL; j += NB_LANES) {
+            uint64_t kj = j < 16 ? h->keys[j] : h->pool[j - 16].key;
+            if (kj < k) { k = kj; cd = j; }
         }
         uint64_t m = nbw_min_u64(k);
         uint32_t who = nbw_ballot(k == m && cd >= 0);
@@ -1155,15 +1225,18 @@ NB_DEV uint64_t nbc_next_event(NbCtx &c, int *code)
     return best;
 }
 
-NB_DEV void nbc_log_event(NbCtx &c, int t, int type)
+NB_FN void nbc_log_event(NbCtx &c, int t, int code)
 {
-    if (c.evlog && c.h->events < c.evlog_cap) { c.evlog[2 * c.h->events] = t; c.evlog[2 * c.h->events + 1] = type; }
+    NbHdr *h = nbc_hdr(c);
+    /* oracle numbering: 0 NPDCCH_arrival 1 NPRACH_update 2 RAR_window_end 3 NPRACH_start 4 NPRACH_end 5 Msg3 6 NPUSCH_end 7 MAC_timer */
+    int type = code < 2 ? code : code < 5 ? 3 : code < 8 ? 4 : code == 8 ? 7 : (h->pool[code - 16].type == NB_EV_RAR_END ? 2 : h->pool[code - 16].type == NB_EV_MSG3 ? 5 : 6);
+    if (h->events < c.evlog_cap) { c.evlog[2 * h->events] = t; c.evlog[2 * h->events + 1] = type; }
 }
 
 /* NodeB.advance_fel (node_b.py:191-204) + check_event (:248-261): run until a decision is needed */
-NB_DEV void nbc_advance_fel(NbCtx &c)
+NB_FN void nbc_advance_fel(NbCtx &c)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     for (;;) {
         int code; uint64_t key = nbc_next_event(c, &code);
         if (code < 0) { NB_FAULT(c, NBIOT_FAULT_EVENT_SLOTS); return; }
@@ -1172,39 +1245,37 @@ NB_DEV void nbc_advance_fel(NbCtx &c)
         h->time = t; h->cur_key = key;
         nbc_erase_past_sf(c, t);                               /* carrier_set.step(t) */
         if (NB_FATAL(c)) return;
+        if (c.evlog) nbc_log_event(c, t, code);
+        h->events += 1;
         if (code == 0) {
-            nbc_log_event(c, t, 0); h->events += 1;
-            h->ev_npdcch = NB_KEY_NONE;
+            h->keys[0] = NB_KEY_NONE;
             if (h->state == NB_ST_RAR_WINDOW || h->state == NB_ST_SCHEDULING) return;
             nbc_schedule_NPDCCH(c, h->NPDCCH_sf_left);
         } else if (code == 1) {
-            nbc_log_event(c, t, 1); h->events += 1;
-            h->ev_update = NB_KEY_NONE; h->cur_t = t; h->state = NB_ST_NPRACH_UPDATE;
+            h->keys[1] = NB_KEY_NONE; h->cur_t = t; h->state = NB_ST_NPRACH_UPDATE;
             return;
         } else if (code < 5) {
             int ce = code - 2;
-            nbc_log_event(c, t, 3); h->events += 1;
             NbOccasion o = h->occ[ce][h->occ_head_start[ce] % NB_OCC_RING];
             h->occ_head_start[ce] += 1;
+            nbc_occ_keys(h, ce);
             nbc_NPRACH_start(c, ce, o);
         } else if (code < 8) {
             int ce = code - 5;
-            nbc_log_event(c, t, 4); h->events += 1;
             h->occ_head_end[ce] += 1;
+            nbc_occ_keys(h, ce);
             nbc_NPRACH_end(c, ce, t);
         } else if (code == 8) {
-            nbc_log_event(c, t, 7); h->events += 1;
             nbc_MAC_timeout(c, h->next_mac_idx);
         } else {
             int i = code - 16;
             NbEvent e = h->pool[i];
             nbc_pool_release(c, i);
             if (e.type == NB_EV_RAR_END) {
-                nbc_log_event(c, t, 2); h->events += 1;
                 h->cur_ce = e.ce; h->cur_wid = e.aux; h->cur_t = t; h->state = NB_ST_RAR_WINDOW_END;
                 return;
-            } else if (e.type == NB_EV_MSG3) { nbc_log_event(c, t, 5); h->events += 1; nbc_msg3_event(c, e.aux, t); }
-            else { nbc_log_event(c, t, 6); h->events += 1; nbc_NPUSCH_end(c, e.aux, t); }
+            } else if (e.type == NB_EV_MSG3) nbc_msg3_event(c, e.aux, t);
+            else { nbc_NPUSCH_end(c, e.aux, t); }
         }
         if (NB_FATAL(c)) return;
     }
@@ -1213,7 +1284,7 @@ NB_DEV void nbc_advance_fel(NbCtx &c)
 /* ------------------------------------------------------------------ decision record */
 NB_DEV double nbc_reward(NbCtx &c)                               /* perf_monitor.py:253-322 */
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int n = h->n_rx;
     switch (c.conf->reward_criteria) {
     case NB_RW_THROUGHPUT: return (double)h->thr_count;
@@ -1226,88 +1297,106 @@ NB_DEV double nbc_reward(NbCtx &c)                               /* perf_monitor
     }
 }
 
-/* NodeB.get_node_info (node_b.py:278-418): the side effects always happen, the record is only
- * materialised when an external agent (or the host) will look at it */
-NB_DEV void nbc_node_info(NbCtx &c, int write_record, double reward)
+/* materialise the decision record (reward + info dict of NodeB.get_node_info, node_b.py:278-418) in HBM;
+ * only called when an external agent or the host will look at it (cold path) */
+NB_FN void nbc_write_record(NbCtx &c, double reward, double occ_nprach, double occ_ra, double occ_npusch)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     nbiot_record_t *r = c.rec;
-    if (write_record) {
-        nbw_run([&]() -> int {
-            uint32_t *w = (uint32_t *)r;
-            for (int i = nbw_lane(); i < (int)(sizeof(nbiot_record_t) / 4); i += NB_LANES) w[i] = 0u;
-            nbw_sync();
-            for (int j = nbw_lane(); j < NB_HORIZON; j += NB_LANES) r->carrier_busy[j] = (uint8_t)nbw_popc(*nbc_col(c, 0, h->t_now + j) & 0xFFFu);
-            nbw_sync();
-            return 0;
-        });
-        r->reward = reward; r->time = h->time; r->state = h->state; r->total_ues = h->conn_n;
-    }
+    nbw_run([&]() -> int {
+        uint32_t *w = (uint32_t *)r;
+        NB_NOUNROLL
+        for (int i = nbw_lane(); i < (int)(sizeof(nbiot_record_t) / 4); i += NB_LANES) w[i] = 0u;
+        nbw_sync();
+        NB_NOUNROLL
+        for (int j = nbw_lane(); j < NB_HORIZON; j += NB_LANES) r->carrier_busy[j] = (uint8_t)nbw_popc(*nbc_col(c, 0, h->t_now + j) & 0xFFFu);
+        nbw_sync();
+        return 0;
+    });
+    r->reward = reward; r->time = h->time; r->state = h->state; r->total_ues = h->conn_n;
     if (h->state == NB_ST_SCHEDULING || h->state == NB_ST_RAR_WINDOW_END) {
-        nbc_conn_select(c);
-        if (write_record) {
-            r->n_sel = h->n_sel;
-            for (int i = 0; i < h->n_sel; ++i) {
-                NbUe *u = &c.ue[h->sel_slot[i]];
-                r->ues[i] = u->id; r->connection_time[i] = h->time - u->t_connection; r->loss[i] = u->loss; r->buffer[i] = u->buffer;
-                if (!u->new_data) { double v = u->sinr; if (!(v > -40.0)) v = -40.0; if (!(v < 30.0)) v = 30.0; r->sinr[i] = NB_ADD(v, 40.0); }
-            }
-            r->n_rx = h->n_rx; r->n_err = h->n_err; r->n_unfit = h->n_unfit; r->n_acc = h->n_acc;
-            if (h->n_rx > NBIOT_STEP_LIST || h->n_err > NBIOT_STEP_LIST || h->n_unfit > NBIOT_STEP_LIST || h->n_acc > NBIOT_STEP_LIST)
-                NB_FAULT(c, NBIOT_FAULT_LIST_TRUNC);
-            for (int i = 0; i < NBIOT_STEP_LIST; ++i) {
-                if (i < h->n_rx) { r->rx_id[i] = h->rx_id[i]; r->rx_delay[i] = h->rx_delay[i]; }
-                if (i < h->n_err) r->err_id[i] = h->err_id[i];
-                if (i < h->n_unfit) r->unfit_id[i] = h->unfit_id[i];
-                if (i < h->n_acc) { r->acc_id[i] = h->acc_id[i]; r->acc_delay[i] = h->acc_delay[i]; }
-            }
+        r->n_sel = h->n_sel;
+        NB_NOUNROLL
+        for (int i = 0; i < h->n_sel; ++i) {
+            NbUe *u = &c.ue[h->sel_slot[i]];
+            r->ues[i] = u->id; r->connection_time[i] = h->time - u->t_connection; r->loss[i] = u->loss; r->buffer[i] = u->buffer;
+            if (!u->new_data) { double v = u->sinr; if (!(v > -40.0)) v = -40.0; if (!(v < 30.0)) v = 30.0; r->sinr[i] = NB_ADD(v, 40.0); }
+        }
+        r->n_rx = h->n_rx; r->n_err = h->n_err; r->n_unfit = h->n_unfit; r->n_acc = h->n_acc;
+        if (h->n_rx > NBIOT_STEP_LIST || h->n_err > NBIOT_STEP_LIST || h->n_unfit > NBIOT_STEP_LIST || h->n_acc > NBIOT_STEP_LIST)
+            NB_FAULT(c, NBIOT_FAULT_LIST_TRUNC);
+        NB_NOUNROLL
+        for (int i = 0; i < NBIOT_STEP_LIST; ++i) {
+            if (i < h->n_rx) { r->rx_id[i] = h->rx_id[i]; r->rx_delay[i] = h->rx_delay[i]; }
+            if (i < h->n_err) r->err_id[i] = h->err_id[i];
+            if (i < h->n_unfit) r->unfit_id[i] = h->unfit_id[i];
+            if (i < h->n_acc) { r->acc_id[i] = h->acc_id[i]; r->acc_delay[i] = h->acc_delay[i]; }
         }
     } else if (h->state == NB_ST_RAR_WINDOW) {
-        if (write_record) {
-            int max_CE = nb_ce_for_sf_left[h->NPDCCH_sf_left];
-            for (int i = 0; i < 3; ++i) {
-                r->ues_per_CE[i] = i <= max_CE ? nbc_rar_sum(c, i) : 0;
-                r->RAR_in[i] = h->RAR_in[i]; r->RAR_sent[i] = h->RAR_sent[i]; r->RAR_ids[i] = h->RAR_ids[i];
-                r->RAR_detected[i] = h->RAR_detected[i]; r->RAR_failed[i] = h->RAR_failed[i]; r->action[i] = h->action3[i];
-            }
-            r->valid_CE_control = h->valid_CE_control; r->NPDCCH_sf_left = h->NPDCCH_sf_left; r->total_departures = h->total_departures;
-            for (int i = 0; i < 16; ++i) r->nprach_conf[i] = h->nprach_conf[i];
+        int max_CE = nb_ce_for_sf_left[h->NPDCCH_sf_left];
+        NB_NOUNROLL
+        for (int i = 0; i < 3; ++i) {
+            r->ues_per_CE[i] = i <= max_CE ? nbc_rar_sum(c, i) : 0;
+            r->RAR_in[i] = h->RAR_in[i]; r->RAR_sent[i] = h->RAR_sent[i]; r->RAR_ids[i] = h->RAR_ids[i];
+            r->RAR_detected[i] = h->RAR_detected[i]; r->RAR_failed[i] = h->RAR_failed[i]; r->action[i] = h->action3[i];
         }
-        h->RAR_failed[0] = h->RAR_failed[1] = h->RAR_failed[2] = 0;
+        r->valid_CE_control = h->valid_CE_control; r->NPDCCH_sf_left = h->NPDCCH_sf_left; r->total_departures = h->total_departures;
+        NB_NOUNROLL
+        for (int i = 0; i < 16; ++i) r->nprach_conf[i] = h->nprach_conf[i];
     } else {
+        int nd = h->n_departures;
+        r->NPRACH_occupation = occ_nprach; r->RA_occupation = occ_ra; r->NPUSCH_occupation = occ_npusch;
+        r->av_delay = nd ? NB_DIV((double)h->sum_delays, (double)nd) : 0.0;
+        NB_NOUNROLL
+        for (int ce = 0; ce < 3; ++ce) {
+            r->preambles[ce] = (h->nprach_conf[9 + 3 * ce] + 1) * 12;
+            int n = h->m3_cnt[ce]; double dn = (double)(n > 1 ? n : 1);
+            r->msg3_detection[ce] = NB_DIV(h->m3_eff_sum[ce], dn);
+            r->msg3_sent[ce] = NB_DIV((double)h->m3_sent_sum[ce], dn);
+            r->msg3_received[ce] = NB_DIV((double)h->m3_recv_sum[ce], dn);
+            int no = h->occ_n[ce]; double dno = (double)(no > 1 ? no : 1);
+            r->detection_ratios[ce] = NB_DIV(NB_DIV((double)h->det_sum[ce], dno), (double)r->preambles[ce]);
+            r->colision_ratios[ce] = NB_DIV(NB_DIV((double)h->col_sum[ce], dno), (double)r->preambles[ce]);
+            r->n_occ[ce] = no;
+            int lim = no < NBIOT_MAX_OCC ? no : NBIOT_MAX_OCC;
+            NB_NOUNROLL
+            for (int i = 0; i < lim; ++i) { r->det_hist[ce][i] = c.occ->det[ce][i]; r->col_hist[ce][i] = c.occ->col[ce][i]; }
+        }
+        NB_NOUNROLL
+        for (int i = 0; i < 15; ++i) r->distribution[i] = h->distribution[i];
+        r->departures = nd; r->n_incoming = h->n_incoming;
+        NB_NOUNROLL
+        for (int i = 0; i < 16; ++i) r->nprach_conf[i] = h->nprach_conf[i];
+    }
+    r->fault = h->fault;
+    r->draws_lo = (int32_t)(uint32_t)h->draws; r->draws_hi = (int32_t)(uint32_t)(h->draws >> 32);
+    r->events = h->events;
+}
+
+/* NodeB.get_node_info (node_b.py:278-418): its side effects always happen, the record is only materialised
+ * when somebody will read it */
+NB_FN void nbc_node_info(NbCtx &c, int write_record, double reward)
+{
+    NbHdr *h = nbc_hdr(c);
+    double occ_nprach = 0.0, occ_ra = 0.0, occ_npusch = 0.0;
+    if (h->state == NB_ST_SCHEDULING || h->state == NB_ST_RAR_WINDOW_END) nbc_conn_select(c);
+    else if (h->state == NB_ST_NPRACH_UPDATE && h->time != 0) {
         /* PerfMonitor.estimate_carrier_resources (perf_monitor.py:204-222) */
-        double occ_nprach = 0.0, occ_ra = 0.0, occ_npusch = 0.0;
-        if (h->time != 0) {
-            int period = h->time - h->perf_t;
-            int64_t total = 12LL * c.C * period;
-            int64_t signalling = h->NPRACH_resources + h->msg3_resources;
+        int period = h->time - h->perf_t;
+        int64_t total = 12LL * c.C * period;
+        int64_t signalling = h->NPRACH_resources + h->msg3_resources;
+        if (write_record) {
             occ_nprach = NB_DIV((double)h->NPRACH_resources, (double)total);
             occ_ra = NB_DIV((double)signalling, (double)total);
             occ_npusch = NB_DIV((double)h->NPUSCH_resources, (double)(total - signalling));
-            h->msg3_resources = 0; h->NPRACH_resources = 0; h->NPUSCH_resources = 0;
-            h->perf_t = h->time;
         }
-        if (write_record) {
-            int nd = h->n_departures;
-            r->NPRACH_occupation = occ_nprach; r->RA_occupation = occ_ra; r->NPUSCH_occupation = occ_npusch;
-            r->av_delay = nd ? NB_DIV((double)h->sum_delays, (double)nd) : 0.0;
-            r->preambles[0] = (h->nprach_conf[9] + 1) * 12; r->preambles[1] = (h->nprach_conf[12] + 1) * 12; r->preambles[2] = (h->nprach_conf[15] + 1) * 12;
-            for (int ce = 0; ce < 3; ++ce) {
-                int n = h->m3_cnt[ce]; double dn = (double)(n > 1 ? n : 1);
-                r->msg3_detection[ce] = NB_DIV(h->m3_eff_sum[ce], dn);
-                r->msg3_sent[ce] = NB_DIV((double)h->m3_sent_sum[ce], dn);
-                r->msg3_received[ce] = NB_DIV((double)h->m3_recv_sum[ce], dn);
-                int no = h->occ_n[ce]; double dno = (double)(no > 1 ? no : 1);
-                r->detection_ratios[ce] = NB_DIV(NB_DIV((double)h->det_sum[ce], dno), (double)r->preambles[ce]);
-                r->colision_ratios[ce] = NB_DIV(NB_DIV((double)h->col_sum[ce], dno), (double)r->preambles[ce]);
-                r->n_occ[ce] = no;
-                int lim = no < NBIOT_MAX_OCC ? no : NBIOT_MAX_OCC;
-                for (int i = 0; i < lim; ++i) { r->det_hist[ce][i] = c.occ->det[ce][i]; r->col_hist[ce][i] = c.occ->col[ce][i]; }
-            }
-            for (int i = 0; i < 15; ++i) r->distribution[i] = h->distribution[i];
-            r->departures = nd; r->n_incoming = h->n_incoming;
-            for (int i = 0; i < 16; ++i) r->nprach_conf[i] = h->nprach_conf[i];
-        }
+        h->msg3_resources = 0; h->NPRACH_resources = 0; h->NPUSCH_resources = 0;
+        h->perf_t = h->time;
+    }
+    if (write_record) nbc_write_record(c, reward, occ_nprach, occ_ra, occ_npusch);
+    if (h->state == NB_ST_RAR_WINDOW) { h->RAR_failed[0] = 0; h->RAR_failed[1] = 0; h->RAR_failed[2] = 0; }
+    else if (h->state == NB_ST_NPRACH_UPDATE) {
+        NB_NOUNROLL
         for (int ce = 0; ce < 3; ++ce) {
             h->m3_cnt[ce] = 0; h->m3_sent_sum[ce] = 0; h->m3_recv_sum[ce] = 0; h->m3_eff_sum[ce] = 0.0;
             h->occ_n[ce] = 0; h->det_sum[ce] = 0; h->col_sum[ce] = 0;
@@ -1315,49 +1404,51 @@ NB_DEV void nbc_node_info(NbCtx &c, int write_record, double reward)
         /* the period lists stay readable in the side buffers until the next departure / connection */
         h->n_departures = 0; h->n_incoming = 0; h->sum_delays = 0;
     }
-    if (write_record) {
-        r->fault = h->fault;
-        r->draws_lo = (int32_t)(uint32_t)h->draws; r->draws_hi = (int32_t)(uint32_t)(h->draws >> 32);
-        r->events = h->events;
-    }
 }
 
 /* ------------------------------------------------------------------ instance life cycle */
 /* NodeB.__init__ / create_system values that survive reset() (node_b.py:87-104, population.py:41-49,
  * ue_generator.py:23-37) */
-NB_DEV void nbc_construct(NbCtx &c, uint64_t seed, const nbiot_ctrl_t *ctrl)
+NB_FN void nbc_construct(NbCtx &c, uint64_t seed, const nbiot_ctrl_t *ctrl)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     nbw_run([&]() -> int {
         uint32_t *w = (uint32_t *)h;
+        NB_NOUNROLL
         for (int i = nbw_lane(); i < (int)(sizeof(NbHdr) / 4); i += NB_LANES) w[i] = 0u;
         nbw_sync();
         return 0;
     });
     h->seed = seed;
     h->NPDCCH_sf_left = NB_NPDCCH_SF;
-    const uint8_t default_conf[16] = { 3, 6, 2, 4, 12, 8, 11, 3, 0, 1, 2, 0, 1, 3, 2, 1 };
-    for (int i = 0; i < 16; ++i) h->nprach_conf[i] = default_conf[i];
+    NB_NOUNROLL
+    for (int i = 0; i < 16; ++i) h->nprach_conf[i] = nb_nprach_default_conf[i];
+    NB_NOUNROLL
     for (int i = 0; i < 3; ++i) h->RAR_window_size[i] = 4 * NB_NPDCCH_PERIOD;
     h->valid_CE_control = 1;
     h->msg3_nrep[0] = 1; h->msg3_nrep[1] = 4; h->msg3_nrep[2] = 16;
     h->CE_thresholds[0] = -102; h->CE_thresholds[1] = -85;
     h->preamble_trans_max = 2; h->MAC_timer = 64;
     h->gen_p = 0.5; h->gen_counter = 0;
+    NB_NOUNROLL
     for (int i = 0; i < 24; ++i) h->ctrl_action[i] = ctrl->init_action[i];
 }
 
 /* NodeB.reset (node_b.py:163-189) with MessageSwitch.reset (message_switch.py:48-54) */
-NB_DEV void nbc_reset(NbCtx &c)
+NB_FN void nbc_reset(NbCtx &c)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     h->fault = 0; h->draws = 0; h->events = 0; h->subframes_done = 0;
     h->seq = 0; h->pool_free = ~0ULL;
+    NB_NOUNROLL
+    for (int i = 0; i < 16; ++i) h->keys[i] = NB_KEY_NONE;
+    NB_NOUNROLL
     for (int i = 0; i < NB_EV_POOL; ++i) { h->pool[i].type = NB_EV_NONE; h->pool[i].key = NB_KEY_NONE; }
     /* population.reset */
     h->ra_n[0] = h->ra_n[1] = h->ra_n[2] = 0; h->cont_n = 0; h->ue_count = 0; h->mac_valid = 0; h->next_mac = NB_KEY_NONE; h->next_mac_idx = -1;
     int cap = c.ue_cap;
     nbw_run([&]() -> int {
+        NB_NOUNROLL
         for (int i = nbw_lane(); i < cap; i += NB_LANES) c.free_stack[i] = (uint16_t)(cap - 1 - i);
         nbw_sync();
         return 0;
@@ -1365,14 +1456,18 @@ NB_DEV void nbc_reset(NbCtx &c)
     h->free_top = cap;
     /* carrier_set.reset (carrier.py:430-444) */
     h->t_now = 0; h->t_ahead = 0; h->sclog_n = 0;
+    NB_NOUNROLL
     for (int cc = 0; cc < 2; ++cc)
+        NB_NOUNROLL
         for (int ce = 0; ce < 3; ++ce) {
             NbResource r; r.t_start = 0; r.t_next = 2; r.sf_to_go = 0; r.t_offset = 0; r.periodicity = 2; r.N_sf = (int16_t)ce; r.N_sc = 0; r.sc_offset = 0; r.mask = 0;
             h->res[cc][ce] = r;
         }
+    NB_NOUNROLL
     for (int ce = 0; ce < 3; ++ce) { h->occ_head_start[ce] = h->occ_head_end[ce] = h->occ_tail[ce] = 0; }
     /* perf_monitor.reset (perf_monitor.py:41-59) */
     h->perf_t = 0; h->error_count = 0; h->attempts_count = 0; h->thr_count = 0; h->total_bits = 0;
+    NB_NOUNROLL
     for (int i = 0; i < 3; ++i) { h->ue_arrivals[i] = 0; h->ue_departures[i] = 0; h->backoffs[i] = 0; }
     h->ue_connections = 0; h->av_delay = 0.0; h->msg3_resources = 0; h->NPUSCH_resources = 0; h->NPRACH_resources = 0;
     nbc_clear_info(c);
@@ -1382,18 +1477,21 @@ NB_DEV void nbc_reset(NbCtx &c)
     h->M_beta = c.conf->M - h->M_uniform; h->M_beta_max = h->M_beta; h->gen_t = 0;
     /* access_procedure.reset (access_procedure.py:28-35) */
     h->probability_anchor = 0.0;
+    NB_NOUNROLL
     for (int i = 0; i < 3; ++i) { h->detected_pre[i] = 0; h->collided_pre[i] = 0; h->contenders[i] = 0; h->RAR_counter[i] = 0; h->occ_n[i] = 0; h->det_sum[i] = 0; h->col_sum[i] = 0; }
     /* reset_storage (node_b.py:131-161) */
+    NB_NOUNROLL
     for (int i = 0; i < 3; ++i) {
         h->rar_n[i] = 0; h->RAR_in[i] = 0; h->RAR_ids[i] = 0; h->RAR_attmp[i] = 0; h->RAR_sent[i] = 0; h->RAR_detected[i] = 0; h->RAR_failed[i] = 0;
         h->m3_cnt[i] = 0; h->m3_sent_sum[i] = 0; h->m3_recv_sum[i] = 0; h->m3_eff_sum[i] = 0.0;
     }
     h->conn_n = 0; h->conn_order = 0; h->n_sel = 0; h->n_scheduled = 0;
     h->n_incoming = 0; h->n_departures = 0; h->sum_delays = 0;
+    NB_NOUNROLL
     for (int i = 0; i < 15; ++i) h->distribution[i] = 0.0;
     h->k_dist = 0;
     h->state = NB_ST_NPRACH_UPDATE; h->time = 0;
-    h->ev_update = NB_KEY(0, 0); h->ev_npdcch = NB_KEY(0, 1); h->seq = 2;
+    h->keys[1] = NB_KEY(0, 0); h->keys[0] = NB_KEY(0, 1); h->seq = 2;
     nbc_advance_fel(c);
     nbc_node_info(c, 1, 0.0);
 }
@@ -1401,7 +1499,7 @@ NB_DEV void nbc_reset(NbCtx &c)
 /* NodeB.step (node_b.py:228-245): apply the action for the current state, run to the next decision */
 NB_DEV void nbc_node_step(NbCtx &c, const uint8_t *a)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     switch (h->state) {
     case NB_ST_SCHEDULING: nbc_step_data(c, a); break;
     case NB_ST_RAR_WINDOW: nbc_step_RAR_window(c, a); break;
@@ -1412,8 +1510,8 @@ NB_DEV void nbc_node_step(NbCtx &c, const uint8_t *a)
     if (!NB_FATAL(c)) nbc_advance_fel(c);
 }
 
-NB_DEV void nbc_apply_writes(NbCtx &c, const int8_t *w)
-{ for (int i = 0; i < NB_N_ACTIONS; ++i) if (w[i] >= 0) c.h->ctrl_action[i] = (uint8_t)w[i]; }
+NB_FN void nbc_apply_writes(NbCtx &c, const int8_t *w)
+{ NB_NOUNROLL for (int i = 0; i < NB_N_ACTIONS; ++i) if (w[i] >= 0) nbc_hdr(c)->ctrl_action[i] = (uint8_t)w[i]; }
 
 /* Controller.step + to_next_step (controller.py:234-288), or Controller.run_until (:185-195) when
  * there is no external agent, for one instance.
@@ -1425,15 +1523,17 @@ NB_DEV void nbc_apply_writes(NbCtx &c, const int8_t *w)
  * ctrl->state_writes[s] holds the fixed actions of the internal agents of state s; for a state of
  * the external agent it holds only the agents listed before it (controller.py:283-288).
  * Returns the number of NodeB steps taken; the decision record is rewritten iff it is > 0. */
-NB_DEV int nbc_controller_advance(NbCtx &c, const nbiot_ctrl_t *ctrl, const uint8_t *ext_action, int until_time, int max_steps)
+NB_FN int nbc_controller_advance(NbCtx &c, const nbiot_ctrl_t *ctrl, const uint8_t *ext_action, int until_time, int max_steps)
 {
-    NbHdr *h = c.h;
+    NbHdr *h = nbc_hdr(c);
     int steps = 0;
     if (NB_FATAL(c)) { c.rec->fault = h->fault; return 0; }
     if (ext_action) {
+        NB_NOUNROLL
         for (int i = 0; i < ctrl->ext_k; ++i) h->ctrl_action[ctrl->ext_a_mask[i]] = ext_action[i];
         nbc_apply_writes(c, ctrl->ext_post);
     } else nbc_apply_writes(c, ctrl->state_writes[h->state]);
+    NB_NOUNROLL
     while (steps < max_steps && !(until_time >= 0 && h->time >= until_time)) {
         if (steps > 0) {
             nbc_node_info(c, 0, 0.0);                          /* an internal agent looks at nothing */

@@ -25,7 +25,12 @@
 #include "nbiot.h"
 #include "nbiot_core.cuh"
 
+#ifndef NB_WPB
 #define NB_WPB 4   /* warps (instances in flight) per CTA */
+#endif
+#ifndef NB_MIN_CTAS
+#define NB_MIN_CTAS 7   /* __launch_bounds__ second argument: resident CTAs per SM the register budget must allow */
+#endif
 
 struct NbKernelArgs {
     uint8_t *state;
@@ -72,13 +77,10 @@ __device__ __forceinline__ void nb_copy16(void *dst, const void *src, int n16)
     for (int i = threadIdx.x & 31; i < n16; i += 32) d[i] = s[i];
 }
 
-__device__ __forceinline__ NbCtx nb_make_ctx(const NbKernelArgs &A, int i, unsigned char *my_smem)
+__device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int i)
 {
-    NbCtx c;
     const NbLayout &L = A.L;
     uint8_t *s = A.state;
-    c.h = (NbHdr *)my_smem;
-    c.grid = (uint16_t *)(my_smem + A.hdr_bytes16 * 16);
     for (int k = 0; k < 3; ++k) c.ra[k] = (NbRaEntry *)(s + L.off_ra) + ((size_t)i * 3 + k) * L.ra_cap;
     c.conn = (NbConnEntry *)(s + L.off_conn) + (size_t)i * L.ue_cap;
     c.cont = (NbContEntry *)(s + L.off_cont) + (size_t)i * L.ue_cap;
@@ -93,39 +95,56 @@ __device__ __forceinline__ NbCtx nb_make_ctx(const NbKernelArgs &A, int i, unsig
     c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = A.conf;
     c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
     c.evlog = i == 0 ? A.evlog : nullptr; c.evlog_cap = A.evlog_cap;
-    return c;
 }
 
-/* mode 0: construct + reset, 1: reset, 2: advance */
-__global__ void __launch_bounds__(NB_WPB * 32)
-nbiot_sim_kernel(NbKernelArgs A, int mode, const uint64_t *seeds, const uint8_t *ext_actions, int until_time, int max_steps)
+/* Claim instances from the work counter; stage [ctx | header | grid] in this warp's shared-memory slice;
+ * run `body`; write header and grid back. */
+template <bool LOAD, class Body>
+__device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, Body body)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *my = smem + (size_t)warp * A.smem_per_warp;
+    NbCtx &c = *(NbCtx *)my;
+    unsigned char *hdr_s = my + sizeof(NbCtx), *grid_s = hdr_s + sizeof(NbHdr);
     NbHdr *hdr_g = (NbHdr *)(A.state + A.L.off_hdr);
     uint16_t *grid_g = (uint16_t *)(A.state + A.L.off_grid);
     const size_t grid_elems = (size_t)A.L.n_carriers * A.L.grid_w;
-    const int ext_k = A.ctrl->ext_k;
     for (;;) {
         int i = 0;
         if (lane == 0) i = (int)atomicAdd(A.counter, 1u);
         i = __shfl_sync(0xFFFFFFFFu, i, 0);
         if (i >= A.L.n_inst) break;
-        NbCtx c = nb_make_ctx(A, i, my);
-        if (mode != 0) {
-            nb_copy16(my, hdr_g + i, A.hdr_bytes16);
-            nb_copy16(c.grid, grid_g + (size_t)i * grid_elems, A.grid_bytes16);
+        if (lane == 0) nb_fill_ctx(c, A, i);
+        if (LOAD) {
+            nb_copy16(hdr_s, hdr_g + i, A.hdr_bytes16);
+            nb_copy16(grid_s, grid_g + (size_t)i * grid_elems, A.grid_bytes16);
         }
         __syncwarp();
-        if (mode == 0) { nbc_construct(c, seeds[i], A.ctrl); nbc_reset(c); }
-        else if (mode == 1) nbc_reset(c);
-        else nbc_controller_advance(c, A.ctrl, ext_actions ? ext_actions + (size_t)i * ext_k : nullptr, until_time, max_steps);
+        body(c, i);
         __syncwarp();
-        nb_copy16(hdr_g + i, my, A.hdr_bytes16);
-        nb_copy16(grid_g + (size_t)i * grid_elems, c.grid, A.grid_bytes16);
+        nb_copy16(hdr_g + i, hdr_s, A.hdr_bytes16);
+        nb_copy16(grid_g + (size_t)i * grid_elems, grid_s, A.grid_bytes16);
         __syncwarp();
     }
+}
+
+/* the hot kernel: Controller.step / run_until for every instance */
+__global__ void __launch_bounds__(NB_WPB * 32, NB_MIN_CTAS)
+nbiot_sim_kernel(NbKernelArgs A, const uint8_t *ext_actions, int until_time, int max_steps)
+{
+    const int ext_k = A.ctrl->ext_k;
+    nb_for_each_instance<true>(A, [&](NbCtx &c, int i) {
+        nbc_controller_advance(c, A.ctrl, ext_actions ? ext_actions + (size_t)i * ext_k : nullptr, until_time, max_steps);
+    });
+}
+
+/* create_system + NodeB.reset (construct = 1) or NodeB.reset alone */
+__global__ void __launch_bounds__(NB_WPB * 32)
+nbiot_reset_kernel(NbKernelArgs A, int construct, const uint64_t *seeds)
+{
+    if (construct) nb_for_each_instance<false>(A, [&](NbCtx &c, int i) { nbc_construct(c, seeds[i], A.ctrl); nbc_reset(c); });
+    else nb_for_each_instance<true>(A, [&](NbCtx &c, int) { nbc_reset(c); });
 }
 
 /* Controller.get_obs (controller.py:105-120) for the whole batch: one thread per (instance, obs element) */
@@ -185,7 +204,7 @@ static NbKernelArgs make_args(nbiot_handle_t *h)
     A.counter = h->counter_dev; A.evlog = h->evlog; A.evlog_cap = h->evlog_cap;
     A.hdr_bytes16 = (int)(sizeof(NbHdr) / 16);
     A.grid_bytes16 = (int)((size_t)h->L.n_carriers * h->L.grid_w * 2 / 16);
-    A.smem_per_warp = A.hdr_bytes16 * 16 + A.grid_bytes16 * 16;
+    A.smem_per_warp = (int)sizeof(NbCtx) + A.hdr_bytes16 * 16 + A.grid_bytes16 * 16;
     return A;
 }
 
@@ -194,7 +213,8 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->counter_dev, 0, sizeof(unsigned int), st));
     NbKernelArgs A = make_args(h);
-    nbiot_sim_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, mode, h->seeds_dev, ext_actions, until_time, max_steps);
+    if (mode == 2) nbiot_sim_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, ext_actions, until_time, max_steps);
+    else nbiot_reset_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, mode == 0 ? 1 : 0, h->seeds_dev);
     CK(cudaGetLastError());
     h->launches += 1;
     return 0;
@@ -250,6 +270,7 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     CK(cudaGetDeviceProperties(&prop, device));
     if ((size_t)h->smem_bytes > prop.sharedMemPerBlockOptin) return set_err(NBIOT_E_INVALID, "grid_w too large for the shared memory of one CTA");
     CK(cudaFuncSetAttribute(nbiot_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CK(cudaFuncSetAttribute(nbiot_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nbiot_sim_kernel, NB_WPB * 32, h->smem_bytes));
     if (per_sm < 1) per_sm = 1;

@@ -108,7 +108,9 @@ typedef struct __attribute__((aligned(16))) NbHdr {
     int32_t events;
     int32_t NPDCCH_sf_left, valid_CE_control, total_departures;
     int32_t action3[3];
-    uint64_t ev_npdcch, ev_update;    /* keys of the two singleton NodeB events */
+    /* keys of the fixed event slots, NB_KEY_NONE when nothing is pending:
+     * 0 NPDCCH_arrival, 1 NPRACH_update, 2+ce next NPRACH_start, 5+ce next NPRACH_end, 8 next MAC_timer */
+    uint64_t keys[16];
     int32_t cur_ce, cur_wid, cur_t;   /* payload of the RAR_window_end being decided */
     uint8_t ctrl_action[24];          /* the controller's shared action vector (controller.py:33) */
     /* ---- NPRACH configuration ---- */

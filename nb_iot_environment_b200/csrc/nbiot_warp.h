@@ -23,8 +23,9 @@
 
 #define NB_LANES 32
 #define NB_DEV __device__ __forceinline__
-#define NB_DEV_NOINLINE __device__ __noinline__
+#define NB_FN __device__ __noinline__
 #define NB_FULL 0xFFFFFFFFu
+#define NB_NOUNROLL _Pragma("unroll 1")
 NB_DEV int nbw_lane() { return (int)(threadIdx.x & 31u); }
 NB_DEV void nbw_sync() { __syncwarp(NB_FULL); }
 NB_DEV uint32_t nbw_ballot(int p) { return __ballot_sync(NB_FULL, p); }
@@ -44,8 +45,9 @@ NB_DEV int nbw_ffsll(uint64_t v) { return __ffsll((long long)v); }
 #endif
 #define NB_LANES NBIOT_EMU_LANES
 #define NB_DEV static inline
-#define NB_DEV_NOINLINE static
+#define NB_FN static
 #define NB_LDG(p) (*(p))
+#define NB_NOUNROLL
 static inline int nbw_popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int nbw_ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int nbw_popcll(uint64_t v) { return __builtin_popcountll(v); }

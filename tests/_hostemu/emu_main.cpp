@@ -17,29 +17,44 @@ struct Emu {
     int32_t *evlog; int evlog_cap;
 };
 
-static NbCtx make_ctx(Emu *e, int i)
-{
-    NbCtx c;
-    const NbLayout &L = e->L;
-    uint8_t *s = e->state;
-    c.h = (NbHdr *)(s + L.off_hdr) + i;
-    c.grid = (uint16_t *)(s + L.off_grid) + (size_t)i * L.n_carriers * L.grid_w;
-    for (int k = 0; k < 3; ++k) c.ra[k] = (NbRaEntry *)(s + L.off_ra) + ((size_t)i * 3 + k) * L.ra_cap;
-    c.conn = (NbConnEntry *)(s + L.off_conn) + (size_t)i * L.ue_cap;
-    c.cont = (NbContEntry *)(s + L.off_cont) + (size_t)i * L.ue_cap;
-    c.ue = (NbUe *)(s + L.off_ue) + (size_t)i * L.ue_cap;
-    c.free_stack = (uint16_t *)(s + L.off_free) + (size_t)i * L.ue_cap;
-    c.occ = (NbOccHist *)(s + L.off_occ) + i;
-    c.incoming = (double *)(s + L.off_incoming) + (size_t)i * L.hist_cap;
-    c.delays = (int32_t *)(s + L.off_delays) + (size_t)i * L.hist_cap;
-    c.service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
-    c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
-    c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
-    c.lut2 = e->lut2; c.mcs = e->mcs; c.conf = &e->conf;
-    c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
-    c.evlog = (e->evlog && i == 0) ? e->evlog : NULL; c.evlog_cap = e->evlog_cap;
-    return c;
-}
+// mirrors the kernel's staging: [NbCtx | NbHdr | grid] in one scratch slice, copied in and out
+struct Staged {
+    Emu *e; int i; unsigned char *buf; NbCtx *c;
+    Staged(Emu *e_, int i_, bool load) : e(e_), i(i_)
+    {
+        const NbLayout &L = e->L;
+        size_t gbytes = (size_t)L.n_carriers * L.grid_w * 2;
+        buf = (unsigned char *)aligned_alloc(16, sizeof(NbCtx) + sizeof(NbHdr) + gbytes);
+        c = (NbCtx *)buf;
+        uint8_t *s = e->state;
+        for (int k = 0; k < 3; ++k) c->ra[k] = (NbRaEntry *)(s + L.off_ra) + ((size_t)i * 3 + k) * L.ra_cap;
+        c->conn = (NbConnEntry *)(s + L.off_conn) + (size_t)i * L.ue_cap;
+        c->cont = (NbContEntry *)(s + L.off_cont) + (size_t)i * L.ue_cap;
+        c->ue = (NbUe *)(s + L.off_ue) + (size_t)i * L.ue_cap;
+        c->free_stack = (uint16_t *)(s + L.off_free) + (size_t)i * L.ue_cap;
+        c->occ = (NbOccHist *)(s + L.off_occ) + i;
+        c->incoming = (double *)(s + L.off_incoming) + (size_t)i * L.hist_cap;
+        c->delays = (int32_t *)(s + L.off_delays) + (size_t)i * L.hist_cap;
+        c->service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
+        c->scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
+        c->rec = (nbiot_record_t *)(s + L.off_rec) + i;
+        c->lut2 = e->lut2; c->mcs = e->mcs; c->conf = &e->conf;
+        c->W = L.grid_w; c->ue_cap = L.ue_cap; c->ra_cap = L.ra_cap; c->hist_cap = L.hist_cap; c->C = L.n_carriers;
+        c->evlog = (e->evlog && i == 0) ? e->evlog : NULL; c->evlog_cap = e->evlog_cap;
+        if (load) {
+            memcpy(buf + sizeof(NbCtx), (NbHdr *)(s + L.off_hdr) + i, sizeof(NbHdr));
+            memcpy(buf + sizeof(NbCtx) + sizeof(NbHdr), (uint16_t *)(s + L.off_grid) + (size_t)i * L.n_carriers * L.grid_w, gbytes);
+        }
+    }
+    ~Staged()
+    {
+        const NbLayout &L = e->L;
+        size_t gbytes = (size_t)L.n_carriers * L.grid_w * 2;
+        memcpy((NbHdr *)(e->state + L.off_hdr) + i, buf + sizeof(NbCtx), sizeof(NbHdr));
+        memcpy((uint16_t *)(e->state + L.off_grid) + (size_t)i * L.n_carriers * L.grid_w, buf + sizeof(NbCtx) + sizeof(NbHdr), gbytes);
+        free(buf);
+    }
+};
 
 extern "C" {
 
@@ -52,7 +67,7 @@ void *emu_create(const nbiot_conf_t *conf, int n_inst, const uint64_t *seeds, co
     e->conf = *conf; e->ctrl = *ctrl; e->lut2 = lut2; e->mcs = mcs;
     e->L = nb_make_layout(conf, n_inst);
     e->state = (uint8_t *)calloc(1, e->L.total);
-    for (int i = 0; i < n_inst; ++i) { NbCtx c = make_ctx(e, i); nbc_construct(c, seeds[i], &e->ctrl); }
+    for (int i = 0; i < n_inst; ++i) { Staged st(e, i, false); nbc_construct(*st.c, seeds[i], &e->ctrl); }
     return e;
 }
 
@@ -63,7 +78,7 @@ void emu_set_evlog(void *p, int32_t *buf, int cap) { Emu *e = (Emu *)p; e->evlog
 void emu_reset(void *p)
 {
     Emu *e = (Emu *)p;
-    for (int i = 0; i < e->L.n_inst; ++i) { NbCtx c = make_ctx(e, i); nbc_reset(c); }
+    for (int i = 0; i < e->L.n_inst; ++i) { Staged st(e, i, true); nbc_reset(*st.c); }
 }
 
 // ext_actions: [n_inst][ext_k] or NULL; steps_out: [n_inst] or NULL
@@ -71,8 +86,8 @@ void emu_advance(void *p, const uint8_t *ext_actions, int until_time, int max_st
 {
     Emu *e = (Emu *)p;
     for (int i = 0; i < e->L.n_inst; ++i) {
-        NbCtx c = make_ctx(e, i);
-        int s = nbc_controller_advance(c, &e->ctrl, ext_actions ? ext_actions + (size_t)i * e->ctrl.ext_k : NULL, until_time, max_steps);
+        Staged st(e, i, true);
+        int s = nbc_controller_advance(*st.c, &e->ctrl, ext_actions ? ext_actions + (size_t)i * e->ctrl.ext_k : NULL, until_time, max_steps);
         if (steps_out) steps_out[i] = s;
     }
 }
@@ -84,7 +99,7 @@ void emu_layout(void *p, NbLayout *out) { *out = ((Emu *)p)->L; }
 // PerfMonitor counters of instance i (same order as orc_get_counters)
 void emu_counters(void *p, int i, int64_t out[16], double *av_delay)
 {
-    Emu *e = (Emu *)p; NbCtx c = make_ctx(e, i); NbHdr *h = c.h;
+    Emu *e = (Emu *)p; NbHdr *h = (NbHdr *)(e->state + e->L.off_hdr) + i;
     for (int k = 0; k < 3; ++k) { out[k] = h->ue_arrivals[k]; out[3 + k] = h->ue_departures[k]; out[6 + k] = h->backoffs[k]; }
     out[9] = h->ue_connections; out[10] = h->error_count; out[11] = h->attempts_count; out[12] = h->total_bits;
     out[13] = (int64_t)h->draws; out[14] = h->events; out[15] = h->ue_count;
