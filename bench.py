@@ -44,7 +44,7 @@ AGENTS = [
      'next': -1, 'states': ['NPRACH_update']},
 ]
 EXT_AGENT = 3
-CAPS = dict(ue_cap=512, grid_w=2048, hist_cap=512)
+CAPS = dict(ue_cap=512, grid_w=int(os.environ.get('NBIOT_BENCH_GRID_W', '2048')), hist_cap=512)
 METRIC = 'simulated subframe-instances/sec'
 UNIT = 'subframe-instances/s'
 WORKLOAD = ('configs[1]: NPRACH control scenario (scripts/nprach, M=1000, ratio=0.5, NPRACH agent external, '
@@ -171,7 +171,8 @@ def main():
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     N = args.instances
-    seeds = np.arange(N, dtype=np.uint64) + np.uint64(rank * N)
+    from nb_iot_environment_b200.sharding import shard_seeds, allreduce_stats
+    seeds = shard_seeds(N * world, rank, world)              # instance g of the job has Philox key g on any number of GPUs
     env = BatchedNBIoTEnv(CONF, agents_conf=AGENTS, ext_agent=EXT_AGENT, num_envs=N, seeds=seeds, device=local_rank, **CAPS)
     total_steps = W + 2 * K
     acts_host = ext_actions(total_steps, N, seed=1234 + rank)
@@ -211,9 +212,7 @@ def main():
         ev[s][2].record()
         live.append(env.stats_tensor()[17:18].clone())
     stats_now = env.stats_tensor().clone()
-    if dist is not None:
-        allred = stats_now.clone()
-        dist.all_reduce(allred)                                          # the one collective of the path: episode statistics
+    job_stats = allreduce_stats(stats_now.clone())                       # the one collective of the path: episode statistics (NCCL)
     barrier()
     wall1 = time.perf_counter() - t_wall0
     sim_ms = [ev[s][0].elapsed_time(ev[s][1]) for s in range(K)]
@@ -269,7 +268,8 @@ def main():
         'dtype': 'int32+f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'instances_per_gpu': N, 'subframes_per_step': SF_PER_STEP, 'l2': 'flushed between timed steps (256 MiB write)',
                    'caps': CAPS, 'timing': 'CUDA events on the launching stream; max over ranks of the summed step times',
-                   'faulted_instances': faulted, 'launch_geometry': env.launch_geometry()},
+                   'faulted_instances': int(job_stats[16].item()), 'max_lookahead_columns': int(job_stats[20].item()),
+                   'max_live_ues_per_cell': int(job_stats[21].item()), 'launch_geometry': env.launch_geometry()},
         'clocks': sampler.summary(),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(N * 8), 'd2h_bytes_per_step': int(N * env.obs_dim * 8 + N * 8),
                 'ms_per_step': 1e3 * e2e_s / K, 'api': 'BatchedNBIoTEnv.step_host -> nbiot_step_host (pinned staging, synchronous)'},

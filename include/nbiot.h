@@ -61,7 +61,9 @@ enum nbiot_stat_index {
     NBIOT_STAT_FAULTED = 16,       /* instances stopped by a fatal fault                  */
     NBIOT_STAT_LIVE_UES = 17,      /* UEs currently in the cell (sum over instances)      */
     NBIOT_STAT_SUM_DELAY_X1000 = 18, /* sum of PerfMonitor.av_delay * departures * 1000 (fixed point) */
-    NBIOT_STAT_TRUNCATED = 19      /* instances with a truncated info list                */
+    NBIOT_STAT_TRUNCATED = 19,     /* instances with a truncated info list                */
+    NBIOT_STAT_MAX_LOOKAHEAD = 20, /* MAX over instances: carrier columns kept ahead (<= grid_w)     */
+    NBIOT_STAT_MAX_LIVE_UES = 21   /* MAX over instances: simultaneous live UEs (<= ue_cap)          */
 };
 
 int nbiot_abi_version(void);
@@ -100,8 +102,8 @@ int nbiot_hist_ptrs(nbiot_handle_t *h, void **incoming_dev, void **delays_dev, v
  * reward_dev = double[n_inst] (either may be NULL) */
 int nbiot_gather_obs(nbiot_handle_t *h, const nbiot_obs_item_t *items, int n_items, double *obs_dev, double *reward_dev, void *stream);
 
-/* episode statistics summed over the instances of this handle: out_dev = int64[NBIOT_N_STATS]
- * (the vector that is all-reduced across GPUs) */
+/* episode statistics over the instances of this handle: out_dev = int64[NBIOT_N_STATS]; entries below
+ * NBIOT_STAT_MAX_LOOKAHEAD are sums (all-reduce with SUM across GPUs), the last two are maxima (MAX) */
 int nbiot_reduce_stats(nbiot_handle_t *h, int64_t *out_dev, void *stream);
 
 /* the reference-facing call with HOST buffers: copies actions host->device, advances, gathers the

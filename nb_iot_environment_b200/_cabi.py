@@ -18,7 +18,8 @@ SYMBOLS = ['nbiot_abi_version', 'nbiot_last_error', 'nbiot_state_bytes', 'nbiot_
 N_STATS = 24
 STAT_NAMES = {0: 'ue_arrivals', 3: 'ue_departures', 6: 'backoffs', 9: 'ue_connections', 10: 'error_count', 11: 'attempts_count',
               12: 'total_bits', 13: 'subframes', 14: 'events', 15: 'draws', 16: 'faulted', 17: 'live_ues', 18: 'sum_delay_x1000',
-              19: 'truncated'}
+              19: 'truncated', 20: 'max_lookahead', 21: 'max_live_ues'}
+N_SUM_STATS = 20      # entries [0, 20) are sums, the rest maxima
 
 
 class ObsItem(ctypes.Structure):

@@ -91,18 +91,63 @@ NB_FN void nbc_pool_push(NbCtx &c, uint64_t key, int type, int ce, int aux)
 NB_DEV void nbc_pool_release(NbCtx &c, int i) { nbc_hdr(c)->pool[i].type = NB_EV_NONE; nbc_hdr(c)->pool[i].key = NB_KEY_NONE; nbc_hdr(c)->pool_free |= 1ULL << i; }
 
 /* ------------------------------------------------------------------ carrier grid (carrier.py:414-605) */
+/* The look-ahead grid is a ring of W 12-bit column masks per carrier (uint16 each). Window operations
+ * work on aligned 16-byte chunks of 8 columns: one chunk per lane per step, 256 columns per warp step. */
+struct __attribute__((aligned(16))) NbChunk { uint32_t w[4]; };
+
+NB_DEV NbChunk *nbc_chunk(NbCtx &c, int carrier, int q) { return (NbChunk *)&nbc_grid(c)[carrier * c.W + ((q << 3) & (c.W - 1))]; }
 NB_DEV uint16_t *nbc_col(NbCtx &c, int carrier, int t) { return &nbc_grid(c)[carrier * c.W + (t & (c.W - 1))]; }
 
-/* OR `mask` into columns [from, from+count) of one carrier */
-NB_FN void nbc_grid_or(NbCtx &c, int carrier, int from, int count, uint32_t mask)
+/* 32-bit lane mask of word j (columns lo+2j, lo+2j+1) restricted to columns [first, last) of the chunk */
+NB_DEV uint32_t nbc_word_mask(int j, int first, int last)
+{ return ((2 * j >= first && 2 * j < last) ? 0xFFFFu : 0u) | ((2 * j + 1 >= first && 2 * j + 1 < last) ? 0xFFFF0000u : 0u); }
+
+/* OR of the column masks of [a, a+n), n >= 1 */
+NB_FN uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
 {
-    nbw_run([&]() -> int {
+    return (uint32_t)nbw_run([&]() -> int {
+        uint32_t acc = 0;
+        int q0 = a >> 3, q1 = (a + n - 1) >> 3;
         NB_NOUNROLL
-        for (int k = nbw_lane(); k < count; k += NB_LANES) *nbc_col(c, carrier, from + k) |= (uint16_t)mask;
+        for (int q = q0 + nbw_lane(); q <= q1; q += NB_LANES) {
+            NbChunk v = *nbc_chunk(c, carrier, q);
+            int lo = q << 3, first = a - lo, last = a + n - lo;
+            if (first <= 0 && last >= 8) acc |= v.w[0] | v.w[1] | v.w[2] | v.w[3];
+            else {
+                NB_NOUNROLL
+                for (int w = 0; w < 4; ++w) acc |= v.w[w] & nbc_word_mask(w, first, last);
+            }
+        }
+        acc = (acc | (acc >> 16)) & 0xFFFu;
+        return (int)nbw_or_u32(acc);
+    });
+}
+
+/* columns [a, a+n): OR `mask` in (set = 1) or clear them (set = 0) */
+NB_FN void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, int set)
+{
+    if (n <= 0) return;
+    nbw_run([&]() -> int {
+        uint32_t m2 = mask | (mask << 16);
+        int q0 = a >> 3, q1 = (a + n - 1) >> 3;
+        NB_NOUNROLL
+        for (int q = q0 + nbw_lane(); q <= q1; q += NB_LANES) {
+            NbChunk *p = nbc_chunk(c, carrier, q);
+            int lo = q << 3, first = a - lo, last = a + n - lo;
+            NbChunk v = *p;
+            NB_NOUNROLL
+            for (int w = 0; w < 4; ++w) {
+                uint32_t wm = (first <= 0 && last >= 8) ? 0xFFFFFFFFu : nbc_word_mask(w, first, last);
+                v.w[w] = set ? (v.w[w] | (m2 & wm)) : (v.w[w] & ~wm);
+            }
+            *p = v;
+        }
         nbw_sync();
         return 0;
     });
 }
+
+NB_DEV void nbc_grid_or(NbCtx &c, int carrier, int from, int count, uint32_t mask) { nbc_grid_update(c, carrier, from, count, mask, 1); }
 
 /* refresh the fixed event slots of one CE level from its occasion ring */
 NB_DEV void nbc_occ_keys(NbHdr *h, int ce)
@@ -156,16 +201,11 @@ NB_FN void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
     NbHdr *h = nbc_hdr(c);
     int a = h->t_ahead, b = new_t_ahead;
     if (b <= a) return;
+    if (b - h->t_now > h->max_lookahead) h->max_lookahead = b - h->t_now;
     if (b - h->t_now > c.W) { NB_FAULT(c, NBIOT_FAULT_LOOKAHEAD); return; }
     /* fresh columns start empty */
-    nbw_run([&]() -> int {
-        NB_NOUNROLL
-        for (int cc = 0; cc < c.C; ++cc)
-            NB_NOUNROLL
-            for (int k = a + nbw_lane(); k < b; k += NB_LANES) *nbc_col(c, cc, k) = 0;
-        nbw_sync();
-        return 0;
-    });
+    NB_NOUNROLL
+    for (int cc = 0; cc < c.C; ++cc) nbc_grid_update(c, cc, a, b - a, 0u, 0);
     int cursor[2][3];
     NB_NOUNROLL
     for (int cc = 0; cc < c.C; ++cc)
@@ -235,12 +275,7 @@ NB_FN int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int N
         NB_NOUNROLL
         for (int ci = 0; ci < c.C; ++ci) {
             int cc = ci == 0 ? carrier_id : (carrier_id == 0 ? 1 : 0);
-            uint32_t busy = (uint32_t)nbw_run([&]() -> int {
-                uint32_t v = 0;
-                NB_NOUNROLL
-                for (int k = nbw_lane(); k < N_sf; k += NB_LANES) v |= *nbc_col(c, cc, from + k);
-                return (int)nbw_or_u32(v);
-            });
+            uint32_t busy = nbc_grid_busy(c, cc, from, N_sf);
             uint32_t m0 = (1u << N_sc) - 1u;
             NB_NOUNROLL
             for (int off = 0; off < 12; off += N_sc) {
@@ -381,7 +416,7 @@ NB_FN void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int 
 }
 
 /* ------------------------------------------------------------------ NodeB helpers */
-NB_FN int nbc_rar_sum(NbCtx &c, int ce) { int s = 0; NB_NOUNROLL for (int i = 0; i < nbc_hdr(c)->rar_n[ce]; ++i) s += nbc_hdr(c)->RAR_UEs[ce][i]; return s; }
+NB_DEV int nbc_rar_sum(NbCtx &c, int ce) { return nbc_hdr(c)->rar_tot[ce]; }   /* sum(RAR_UEs[ce]), kept incrementally */
 
 NB_FN void nbc_update_state(NbCtx &c)                           /* node_b.py:264-276 */
 {
@@ -513,6 +548,7 @@ NB_FN void nbc_new_arrivals(NbCtx &c, int t)
         int CE_level = P_RSRP < (double)h->CE_thresholds[0] ? 2 : (P_RSRP < (double)h->CE_thresholds[1] ? 1 : 0);
         if (h->free_top <= 0) { NB_FAULT(c, NBIOT_FAULT_UE_SLOTS); return; }
         h->free_top -= 1;
+        if (c.ue_cap - h->free_top > h->max_live) h->max_live = c.ue_cap - h->free_top;
         int slot = c.free_stack[h->free_top];
         NbUe u;
         u.loss = loss; u.sinr = 0.0; u.id = h->ue_count; u.t_arrival = t; u.t_connection = 0; u.timestamp = 0; u.acked_data = 0;
@@ -652,7 +688,7 @@ NB_FN void nbc_NPRACH_end(NbCtx &c, int ce, int t)
     int detections = h->detected_pre[ce];
     if (n_ues > 0) {
         if (h->rar_n[ce] >= NB_RAR_WIN) { NB_FAULT(c, NBIOT_FAULT_EVENT_SLOTS); return; }
-        h->RAR_UEs[ce][h->rar_n[ce]] = detections;
+        h->RAR_UEs[ce][h->rar_n[ce]] = detections; h->rar_tot[ce] += detections;
         h->RAR_w_ids[ce][h->rar_n[ce]] = counter;
         h->rar_n[ce] += 1;
         h->state = NB_ST_RAR_WINDOW;
@@ -898,11 +934,16 @@ NB_FN void nbc_distribution_update(NbCtx &c, double sample)       /* node_b.py:2
     NB_NOUNROLL
     for (int i = 0; i < 14; ++i) if (NB_ADD(sample, 35.0) < (double)nb_threshold_list[i]) { idx = i; break; }
     double k = (double)h->k_dist;
-    NB_NOUNROLL
-    for (int i = 0; i < 15; ++i) {
-        double prob = h->distribution[i];
-        h->distribution[i] = NB_ADD(prob, NB_DIV(NB_SUB(i == idx ? 1.0 : 0.0, prob), k));
-    }
+    nbw_run([&]() -> int {                                     /* one interval per lane */
+        nbw_sync();
+        NB_NOUNROLL
+        for (int i = nbw_lane(); i < 15; i += NB_LANES) {
+            double prob = h->distribution[i];
+            h->distribution[i] = NB_ADD(prob, NB_DIV(NB_SUB(i == idx ? 1.0 : 0.0, prob), k));
+        }
+        nbw_sync();
+        return 0;
+    });
 }
 
 /* RxProcedure.msg3_event (rx_procedure.py:29-51), Channel.msg3_detection / sinr_estimation
@@ -947,7 +988,7 @@ NB_FN void nbc_msg3_event(NbCtx &c, int slot, int t)
         h->ue_connections += 1;
     } else if (window_active) {
         u->state = NB_UE_RAR;
-        h->RAR_UEs[uce][i_] += 1;
+        h->RAR_UEs[uce][i_] += 1; h->rar_tot[uce] += 1;
     }
     nbc_update_state(c);
 }
@@ -1074,7 +1115,7 @@ NB_FN void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:453
         nbc_msg3_grant(c, CE_level, reference_time, t_ul_end, I_tbs, N_rep);
         h->RAR_sent[CE_level] += 1;
         NB_NOUNROLL
-        for (int i = 0; i < h->rar_n[CE_level]; ++i) if (h->RAR_UEs[CE_level][i] > 0) { h->RAR_UEs[CE_level][i] -= 1; break; }
+        for (int i = 0; i < h->rar_n[CE_level]; ++i) if (h->RAR_UEs[CE_level][i] > 0) { h->RAR_UEs[CE_level][i] -= 1; h->rar_tot[CE_level] -= 1; break; }
         h->msg3_resources += (int64_t)N_sc * n_sf;
     } else h->valid_CE_control = 0;
     nbc_schedule_NPDCCH(c, NPDCCH_sf);
@@ -1091,7 +1132,7 @@ NB_FN void nbc_step_RAR_end(NbCtx &c, const uint8_t *a)         /* node_b.py:558
     if (nb_backoff_list[period_i + 1] > backoff) backoff = nb_backoff_list[period_i + 1];
     nbc_population_RAR_window_end(c, h->cur_t, ce, backoff, h->cur_wid);
     if (h->rar_n[ce] > 0) {
-        h->RAR_failed[ce] = h->RAR_UEs[ce][0];
+        h->RAR_failed[ce] = h->RAR_UEs[ce][0]; h->rar_tot[ce] -= h->RAR_UEs[ce][0];
         NB_NOUNROLL
         for (int i = 1; i < h->rar_n[ce]; ++i) { h->RAR_UEs[ce][i - 1] = h->RAR_UEs[ce][i]; h->RAR_w_ids[ce][i - 1] = h->RAR_w_ids[ce][i]; }
         h->rar_n[ce] -= 1;
@@ -1409,7 +1450,7 @@ NB_FN void nbc_node_info(NbCtx &c, int write_record, double reward)
 /* ------------------------------------------------------------------ instance life cycle */
 /* NodeB.__init__ / create_system values that survive reset() (node_b.py:87-104, population.py:41-49,
  * ue_generator.py:23-37) */
-NB_FN void nbc_construct(NbCtx &c, uint64_t seed, const nbiot_ctrl_t *ctrl)
+NB_FN void nbc_construct(NbCtx &c, uint64_t seed, const NbCtrlDev *ctrl)
 {
     NbHdr *h = nbc_hdr(c);
     nbw_run([&]() -> int {
@@ -1455,7 +1496,7 @@ NB_FN void nbc_reset(NbCtx &c)
     });
     h->free_top = cap;
     /* carrier_set.reset (carrier.py:430-444) */
-    h->t_now = 0; h->t_ahead = 0; h->sclog_n = 0;
+    h->t_now = 0; h->t_ahead = 0; h->sclog_n = 0; h->max_lookahead = 0; h->max_live = 0;
     NB_NOUNROLL
     for (int cc = 0; cc < 2; ++cc)
         NB_NOUNROLL
@@ -1482,7 +1523,7 @@ NB_FN void nbc_reset(NbCtx &c)
     /* reset_storage (node_b.py:131-161) */
     NB_NOUNROLL
     for (int i = 0; i < 3; ++i) {
-        h->rar_n[i] = 0; h->RAR_in[i] = 0; h->RAR_ids[i] = 0; h->RAR_attmp[i] = 0; h->RAR_sent[i] = 0; h->RAR_detected[i] = 0; h->RAR_failed[i] = 0;
+        h->rar_n[i] = 0; h->rar_tot[i] = 0; h->RAR_in[i] = 0; h->RAR_ids[i] = 0; h->RAR_attmp[i] = 0; h->RAR_sent[i] = 0; h->RAR_detected[i] = 0; h->RAR_failed[i] = 0;
         h->m3_cnt[i] = 0; h->m3_sent_sum[i] = 0; h->m3_recv_sum[i] = 0; h->m3_eff_sum[i] = 0.0;
     }
     h->conn_n = 0; h->conn_order = 0; h->n_sel = 0; h->n_scheduled = 0;
@@ -1510,8 +1551,14 @@ NB_DEV void nbc_node_step(NbCtx &c, const uint8_t *a)
     if (!NB_FATAL(c)) nbc_advance_fel(c);
 }
 
-NB_FN void nbc_apply_writes(NbCtx &c, const int8_t *w)
-{ NB_NOUNROLL for (int i = 0; i < NB_N_ACTIONS; ++i) if (w[i] >= 0) nbc_hdr(c)->ctrl_action[i] = (uint8_t)w[i]; }
+/* fixed actions of internal agents: one value per set bit of the table's mask */
+NB_FN void nbc_apply_writes(NbCtx &c, const NbWrites *w)
+{
+    uint32_t m = NB_LDG(&w->mask);
+    NbHdr *h = nbc_hdr(c);
+    NB_NOUNROLL
+    while (m) { int i = nbw_ffs(m) - 1; m &= m - 1; h->ctrl_action[i] = NB_LDG(&w->val[i]); }
+}
 
 /* Controller.step + to_next_step (controller.py:234-288), or Controller.run_until (:185-195) when
  * there is no external agent, for one instance.
@@ -1523,7 +1570,7 @@ NB_FN void nbc_apply_writes(NbCtx &c, const int8_t *w)
  * ctrl->state_writes[s] holds the fixed actions of the internal agents of state s; for a state of
  * the external agent it holds only the agents listed before it (controller.py:283-288).
  * Returns the number of NodeB steps taken; the decision record is rewritten iff it is > 0. */
-NB_FN int nbc_controller_advance(NbCtx &c, const nbiot_ctrl_t *ctrl, const uint8_t *ext_action, int until_time, int max_steps)
+NB_FN int nbc_controller_advance(NbCtx &c, const NbCtrlDev *ctrl, const uint8_t *ext_action, int until_time, int max_steps)
 {
     NbHdr *h = nbc_hdr(c);
     int steps = 0;
@@ -1531,18 +1578,18 @@ NB_FN int nbc_controller_advance(NbCtx &c, const nbiot_ctrl_t *ctrl, const uint8
     if (ext_action) {
         NB_NOUNROLL
         for (int i = 0; i < ctrl->ext_k; ++i) h->ctrl_action[ctrl->ext_a_mask[i]] = ext_action[i];
-        nbc_apply_writes(c, ctrl->ext_post);
-    } else nbc_apply_writes(c, ctrl->state_writes[h->state]);
+        nbc_apply_writes(c, &ctrl->ext_post);
+    } else nbc_apply_writes(c, &ctrl->state_writes[h->state]);
     NB_NOUNROLL
     while (steps < max_steps && !(until_time >= 0 && h->time >= until_time)) {
         if (steps > 0) {
             nbc_node_info(c, 0, 0.0);                          /* an internal agent looks at nothing */
-            nbc_apply_writes(c, ctrl->state_writes[h->state]);
+            nbc_apply_writes(c, &ctrl->state_writes[h->state]);
         }
         nbc_node_step(c, h->ctrl_action);
         steps += 1;
         if (NB_FATAL(c)) break;
-        if ((ctrl->ext_state_mask >> h->state) & 1u) { nbc_apply_writes(c, ctrl->state_writes[h->state]); break; }
+        if ((ctrl->ext_state_mask >> h->state) & 1u) { nbc_apply_writes(c, &ctrl->state_writes[h->state]); break; }
     }
     if (steps > 0) nbc_node_info(c, 1, nbc_reward(c));
     else c.rec->fault = h->fault;

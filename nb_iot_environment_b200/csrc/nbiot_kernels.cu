@@ -36,7 +36,7 @@ struct NbKernelArgs {
     uint8_t *state;
     NbLayout L;
     const nbiot_conf_t *conf;
-    const nbiot_ctrl_t *ctrl;
+    const NbCtrlDev *ctrl;
     const uint16_t *lut2;
     const uint8_t *mcs;
     unsigned int *counter;
@@ -51,7 +51,7 @@ struct nbiot_handle {
     int device, n_inst;
     uint8_t *state;
     nbiot_conf_t *conf_dev;
-    nbiot_ctrl_t *ctrl_dev;
+    NbCtrlDev *ctrl_dev;
     uint16_t *lut2_dev;
     uint8_t *mcs_dev;
     uint64_t *seeds_dev;
@@ -190,10 +190,13 @@ __global__ void nbiot_stats_kernel(const NbHdr *hdr, int n_inst, unsigned long l
         v[NBIOT_STAT_LIVE_UES] = h->ue_count - (h->ue_departures[0] + h->ue_departures[1] + h->ue_departures[2]);
         v[NBIOT_STAT_SUM_DELAY_X1000] = (long long)(h->av_delay * (double)(h->ue_departures[0] + h->ue_departures[1] + h->ue_departures[2]) * 1000.0);
         v[NBIOT_STAT_TRUNCATED] = (h->fault & NBIOT_FAULT_LIST_TRUNC) ? 1 : 0;
-        for (int k = 0; k < NBIOT_N_STATS; ++k) if (v[k]) atomicAdd(&acc[k], (unsigned long long)v[k]);
+        for (int k = 0; k < NBIOT_STAT_MAX_LOOKAHEAD; ++k) if (v[k]) atomicAdd(&acc[k], (unsigned long long)v[k]);
+        atomicMax(&acc[NBIOT_STAT_MAX_LOOKAHEAD], (unsigned long long)h->max_lookahead);
+        atomicMax(&acc[NBIOT_STAT_MAX_LIVE_UES], (unsigned long long)h->max_live);
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < NBIOT_N_STATS; k += blockDim.x) if (acc[k]) atomicAdd(&out[k], acc[k]);
+    for (int k = threadIdx.x; k < NBIOT_N_STATS; k += blockDim.x)
+        if (acc[k]) { if (k < NBIOT_STAT_MAX_LOOKAHEAD) atomicAdd(&out[k], acc[k]); else atomicMax(&out[k], acc[k]); }
 }
 
 /* ------------------------------------------------------------------ host side */
@@ -252,13 +255,14 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     memset(h, 0, sizeof *h);
     h->conf = *conf; h->ctrl = *ctrl; h->L = L; h->device = device; h->n_inst = n_inst; h->state = (uint8_t *)state_dev;
     CK(cudaMalloc(&h->conf_dev, sizeof(nbiot_conf_t)));
-    CK(cudaMalloc(&h->ctrl_dev, sizeof(nbiot_ctrl_t)));
+    CK(cudaMalloc(&h->ctrl_dev, sizeof(NbCtrlDev)));
     CK(cudaMalloc(&h->lut2_dev, NB_LUT_CURVES * NB_LUT_SNR_PTS * sizeof(uint16_t)));
     CK(cudaMalloc(&h->mcs_dev, NB_MCS_LOSS_ROWS * NB_N_TBS * 3));
     CK(cudaMalloc(&h->seeds_dev, sizeof(uint64_t) * (size_t)n_inst));
     CK(cudaMalloc(&h->counter_dev, sizeof(unsigned int)));
     CK(cudaMemcpyAsync(h->conf_dev, conf, sizeof(nbiot_conf_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->ctrl_dev, ctrl, sizeof(nbiot_ctrl_t), cudaMemcpyHostToDevice, st));
+    NbCtrlDev cd = nb_make_ctrl_dev(ctrl);
+    CK(cudaMemcpyAsync(h->ctrl_dev, &cd, sizeof(NbCtrlDev), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->lut2_dev, lut2, NB_LUT_CURVES * NB_LUT_SNR_PTS * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->mcs_dev, mcs, NB_MCS_LOSS_ROWS * NB_N_TBS * 3, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->seeds_dev, seeds, sizeof(uint64_t) * (size_t)n_inst, cudaMemcpyHostToDevice, st));
@@ -299,7 +303,8 @@ int nbiot_set_controller(nbiot_handle_t *h, const struct nbiot_ctrl *ctrl, void 
     if (!h || !ctrl) return set_err(NBIOT_E_INVALID, "nbiot_set_controller: null argument");
     CK(cudaSetDevice(h->device));
     h->ctrl = *ctrl;
-    CK(cudaMemcpyAsync(h->ctrl_dev, &h->ctrl, sizeof(nbiot_ctrl_t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    NbCtrlDev cd = nb_make_ctrl_dev(&h->ctrl);
+    CK(cudaMemcpyAsync(h->ctrl_dev, &cd, sizeof(NbCtrlDev), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }

@@ -118,7 +118,7 @@ typedef struct __attribute__((aligned(16))) NbHdr {
     int32_t RAR_window_size[3];
     int32_t msg3_nrep[3];
     /* ---- RAR bookkeeping (node_b.py:134-144) ---- */
-    int32_t rar_n[3];
+    int32_t rar_n[3], rar_tot[3];
     int32_t RAR_UEs[3][NB_RAR_WIN], RAR_w_ids[3][NB_RAR_WIN];
     int32_t RAR_in[3], RAR_ids[3], RAR_attmp[3], RAR_sent[3], RAR_detected[3], RAR_failed[3];
     int32_t m3_cnt[3], m3_sent_sum[3], m3_recv_sum[3];
@@ -135,6 +135,7 @@ typedef struct __attribute__((aligned(16))) NbHdr {
     int32_t next_mac_idx, mac_valid;
     /* ---- carrier ---- */
     int32_t t_now, t_ahead;
+    int32_t max_lookahead, max_live;  /* high-water marks since reset: columns kept ahead, live UEs (capacity planning) */
     NbResource res[2][3];
     int32_t occ_head_start[3], occ_head_end[3], occ_tail[3];   /* ring cursors (monotone counters) */
     NbOccasion occ[3][NB_OCC_RING];
@@ -166,6 +167,29 @@ typedef struct __attribute__((aligned(16))) NbHdr {
     uint64_t pool_free;               /* bit i set: pool[i] is free */
     NbEvent pool[NB_EV_POOL];
 } NbHdr;
+
+/* device-side form of nbiot_ctrl_t (include/nbiot_ctrl.h): write tables as (bit mask, values) */
+typedef struct { uint32_t mask; uint8_t val[24]; uint32_t pad; } NbWrites;
+typedef struct {
+    uint32_t ext_state_mask; int32_t ext_k;
+    uint8_t ext_a_mask[24];
+    NbWrites ext_post, state_writes[4];
+    uint8_t init_action[24];
+} NbCtrlDev;
+
+static inline NbCtrlDev nb_make_ctrl_dev(const nbiot_ctrl_t *c)
+{
+    NbCtrlDev d;
+    d.ext_state_mask = c->ext_state_mask; d.ext_k = c->ext_k;
+    for (int i = 0; i < 24; ++i) { d.ext_a_mask[i] = c->ext_a_mask[i]; d.init_action[i] = c->init_action[i]; }
+    for (int t = 0; t < 5; ++t) {
+        NbWrites *w = t < 4 ? &d.state_writes[t] : &d.ext_post;
+        const int8_t *src = t < 4 ? c->state_writes[t] : c->ext_post;
+        w->mask = 0; w->pad = 0;
+        for (int i = 0; i < 24; ++i) { w->val[i] = 0; if (i < 23 && src[i] >= 0) { w->mask |= 1u << i; w->val[i] = (uint8_t)src[i]; } }
+    }
+    return d;
+}
 
 /* byte offsets of the per-instance arrays inside the caller-owned state buffer */
 typedef struct {

@@ -9,7 +9,7 @@
 
 struct Emu {
     nbiot_conf_t conf;
-    nbiot_ctrl_t ctrl;
+    NbCtrlDev ctrl;
     NbLayout L;
     uint8_t *state;
     const uint16_t *lut2;
@@ -64,7 +64,7 @@ int emu_hdr_size(void) { return (int)sizeof(NbHdr); }
 void *emu_create(const nbiot_conf_t *conf, int n_inst, const uint64_t *seeds, const uint16_t *lut2, const uint8_t *mcs, const nbiot_ctrl_t *ctrl)
 {
     Emu *e = (Emu *)calloc(1, sizeof(Emu));
-    e->conf = *conf; e->ctrl = *ctrl; e->lut2 = lut2; e->mcs = mcs;
+    e->conf = *conf; e->ctrl = nb_make_ctrl_dev(ctrl); e->lut2 = lut2; e->mcs = mcs;
     e->L = nb_make_layout(conf, n_inst);
     e->state = (uint8_t *)calloc(1, e->L.total);
     for (int i = 0; i < n_inst; ++i) { Staged st(e, i, false); nbc_construct(*st.c, seeds[i], &e->ctrl); }
@@ -72,7 +72,7 @@ void *emu_create(const nbiot_conf_t *conf, int n_inst, const uint64_t *seeds, co
 }
 
 void emu_destroy(void *p) { Emu *e = (Emu *)p; free(e->state); free(e); }
-void emu_set_ctrl(void *p, const nbiot_ctrl_t *ctrl) { ((Emu *)p)->ctrl = *ctrl; }
+void emu_set_ctrl(void *p, const nbiot_ctrl_t *ctrl) { ((Emu *)p)->ctrl = nb_make_ctrl_dev(ctrl); }
 void emu_set_evlog(void *p, int32_t *buf, int cap) { Emu *e = (Emu *)p; e->evlog = buf; e->evlog_cap = cap; }
 
 void emu_reset(void *p)
