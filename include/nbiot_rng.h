@@ -39,8 +39,8 @@ NB_HD_CALL nb_block_t nb_philox(uint64_t seed, uint64_t ctr, uint32_t stream)
 {
     uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#ifdef __CUDA_ARCH__
-#pragma unroll
+#if defined(__CUDA_ARCH__) && !defined(NB_PHILOX_UNROLL)
+#pragma unroll 1   /* rolled: 10x fewer instruction-cache lines for the same work */
 #endif
     for (int r = 0; r < 10; ++r) {
         uint32_t lo0, lo1;

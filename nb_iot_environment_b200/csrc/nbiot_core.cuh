@@ -48,6 +48,7 @@ struct __attribute__((aligned(16))) NbCtx {
     const uint16_t *lut2;
     const uint8_t *mcs;
     const nbiot_conf_t *conf;
+    const NbCtrlDev *ctrl;    /* controller tables (shared memory in the kernels) */
     int32_t *evlog;           /* optional (t, type) pop log for debugging */
     int W, ue_cap, ra_cap, hist_cap, C, evlog_cap;
 };
@@ -102,31 +103,78 @@ NB_DEV uint16_t *nbc_col(NbCtx &c, int carrier, int t) { return &nbc_grid(c)[car
 NB_DEV uint32_t nbc_word_mask(int j, int first, int last)
 { return ((2 * j >= first && 2 * j < last) ? 0xFFFFu : 0u) | ((2 * j + 1 >= first && 2 * j + 1 < last) ? 0xFFFF0000u : 0u); }
 
-/* OR of the column masks of [a, a+n), n >= 1 */
+/* this lane's share of the OR of columns [a, a+n) read chunk-wise (no reduction) */
+NB_DEV uint32_t nbc_scan_chunks(NbCtx &c, int carrier, int a, int n)
+{
+    uint32_t acc = 0;
+    if (n <= 0) return 0u;
+    int q0 = a >> 3, q1 = (a + n - 1) >> 3;
+    NB_NOUNROLL
+    for (int q = q0 + nbw_lane(); q <= q1; q += NB_LANES) {
+        NbChunk v = *nbc_chunk(c, carrier, q);
+        int lo = q << 3, first = a - lo, last = a + n - lo;
+        if (first <= 0 && last >= 8) acc |= v.w[0] | v.w[1] | v.w[2] | v.w[3];
+        else {
+            NB_NOUNROLL
+            for (int w = 0; w < 4; ++w) acc |= v.w[w] & nbc_word_mask(w, first, last);
+        }
+    }
+    return acc;
+}
+
+#ifndef NB_GRID_MODE
+#define NB_GRID_MODE 0     /* 0: one column per lane per step; 1: 8-column chunks; 2: chunks + 32-column block summaries */
+#endif
+#if NB_GRID_MODE == 0
 NB_FN uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
 {
     return (uint32_t)nbw_run([&]() -> int {
-        uint32_t acc = 0;
-        int q0 = a >> 3, q1 = (a + n - 1) >> 3;
+        uint32_t v = 0;
         NB_NOUNROLL
-        for (int q = q0 + nbw_lane(); q <= q1; q += NB_LANES) {
-            NbChunk v = *nbc_chunk(c, carrier, q);
-            int lo = q << 3, first = a - lo, last = a + n - lo;
-            if (first <= 0 && last >= 8) acc |= v.w[0] | v.w[1] | v.w[2] | v.w[3];
-            else {
-                NB_NOUNROLL
-                for (int w = 0; w < 4; ++w) acc |= v.w[w] & nbc_word_mask(w, first, last);
-            }
+        for (int k = nbw_lane(); k < n; k += NB_LANES) v |= *nbc_col(c, carrier, a + k);
+        return (int)nbw_or_u32(v);
+    });
+}
+NB_FN void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, int set)
+{
+    nbw_run([&]() -> int {
+        NB_NOUNROLL
+        for (int k = nbw_lane(); k < n; k += NB_LANES) { uint16_t *p = nbc_col(c, carrier, a + k); *p = set ? (uint16_t)(*p | mask) : (uint16_t)0; }
+        nbw_sync();
+        return 0;
+    });
+}
+#else
+/* OR of the column masks of [a, a+n), n >= 1: whole 32-column blocks come from the block summaries,
+ * the ragged head and tail are read chunk-wise, so the cost does not grow with the window length */
+NB_FN uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
+{
+    NbHdr *h = nbc_hdr(c);
+    int nblk = c.W >> 5;
+    return (uint32_t)nbw_run([&]() -> int {
+        int e = a + n, hb = (a + 31) & ~31, te = e & ~31;
+        uint32_t acc;
+        if (hb >= te) acc = nbc_scan_chunks(c, carrier, a, n);
+        else {
+            acc = nbc_scan_chunks(c, carrier, a, hb - a) | nbc_scan_chunks(c, carrier, te, e - te);
+#if NB_GRID_MODE == 2
+            NB_NOUNROLL
+            for (int b = (hb >> 5) + nbw_lane(); b < (te >> 5); b += NB_LANES) acc |= h->blk[carrier][b & (nblk - 1)];
+#else
+            acc |= nbc_scan_chunks(c, carrier, hb, te - hb);
+#endif
         }
         acc = (acc | (acc >> 16)) & 0xFFFu;
         return (int)nbw_or_u32(acc);
     });
 }
 
-/* columns [a, a+n): OR `mask` in (set = 1) or clear them (set = 0) */
+/* columns [a, a+n): OR `mask` in (set = 1) or start them empty (set = 0, only used for freshly generated columns) */
 NB_FN void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, int set)
 {
     if (n <= 0) return;
+    NbHdr *h = nbc_hdr(c);
+    int nblk = c.W >> 5;
     nbw_run([&]() -> int {
         uint32_t m2 = mask | (mask << 16);
         int q0 = a >> 3, q1 = (a + n - 1) >> 3;
@@ -142,10 +190,22 @@ NB_FN void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, i
             }
             *p = v;
         }
+#if NB_GRID_MODE == 2
+        /* block summaries: a block restarts empty when its first column is generated; marking ORs the mask in */
+        int b0 = a >> 5, b1 = (a + n - 1) >> 5;
+        NB_NOUNROLL
+        for (int b = b0 + nbw_lane(); b <= b1; b += NB_LANES) {
+            uint16_t *s = &h->blk[carrier][b & (nblk - 1)];
+            if (set) *s = (uint16_t)(*s | mask);
+            else if ((b << 5) >= a) *s = 0;
+        }
+#endif
         nbw_sync();
         return 0;
     });
 }
+
+#endif
 
 NB_DEV void nbc_grid_or(NbCtx &c, int carrier, int from, int count, uint32_t mask) { nbc_grid_update(c, carrier, from, count, mask, 1); }
 
@@ -1554,10 +1614,10 @@ NB_DEV void nbc_node_step(NbCtx &c, const uint8_t *a)
 /* fixed actions of internal agents: one value per set bit of the table's mask */
 NB_FN void nbc_apply_writes(NbCtx &c, const NbWrites *w)
 {
-    uint32_t m = NB_LDG(&w->mask);
+    uint32_t m = w->mask;                                      /* tables live in shared memory: plain loads */
     NbHdr *h = nbc_hdr(c);
     NB_NOUNROLL
-    while (m) { int i = nbw_ffs(m) - 1; m &= m - 1; h->ctrl_action[i] = NB_LDG(&w->val[i]); }
+    while (m) { int i = nbw_ffs(m) - 1; m &= m - 1; h->ctrl_action[i] = w->val[i]; }
 }
 
 /* Controller.step + to_next_step (controller.py:234-288), or Controller.run_until (:185-195) when

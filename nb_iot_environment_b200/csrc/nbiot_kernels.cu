@@ -77,7 +77,7 @@ __device__ __forceinline__ void nb_copy16(void *dst, const void *src, int n16)
     for (int i = threadIdx.x & 31; i < n16; i += 32) d[i] = s[i];
 }
 
-__device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int i)
+__device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int i, const NbCtrlDev *s_ctrl)
 {
     const NbLayout &L = A.L;
     uint8_t *s = A.state;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
     c.service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
     c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
     c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
-    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = A.conf;
+    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = A.conf; c.ctrl = s_ctrl;
     c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
     c.evlog = i == 0 ? A.evlog : nullptr; c.evlog_cap = A.evlog_cap;
 }
@@ -103,6 +103,9 @@ template <bool LOAD, class Body>
 __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, Body body)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ NbCtrlDev s_ctrl;                       /* the controller tables, once per CTA */
+    for (int k = threadIdx.x; k < (int)(sizeof(NbCtrlDev) / 4); k += blockDim.x) ((uint32_t *)&s_ctrl)[k] = ((const uint32_t *)A.ctrl)[k];
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *my = smem + (size_t)warp * A.smem_per_warp;
     NbCtx &c = *(NbCtx *)my;
@@ -115,7 +118,7 @@ __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, Body
         if (lane == 0) i = (int)atomicAdd(A.counter, 1u);
         i = __shfl_sync(0xFFFFFFFFu, i, 0);
         if (i >= A.L.n_inst) break;
-        if (lane == 0) nb_fill_ctx(c, A, i);
+        if (lane == 0) nb_fill_ctx(c, A, i, &s_ctrl);
         if (LOAD) {
             nb_copy16(hdr_s, hdr_g + i, A.hdr_bytes16);
             nb_copy16(grid_s, grid_g + (size_t)i * grid_elems, A.grid_bytes16);
@@ -133,9 +136,8 @@ __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, Body
 __global__ void __launch_bounds__(NB_WPB * 32, NB_MIN_CTAS)
 nbiot_sim_kernel(NbKernelArgs A, const uint8_t *ext_actions, int until_time, int max_steps)
 {
-    const int ext_k = A.ctrl->ext_k;
     nb_for_each_instance<true>(A, [&](NbCtx &c, int i) {
-        nbc_controller_advance(c, A.ctrl, ext_actions ? ext_actions + (size_t)i * ext_k : nullptr, until_time, max_steps);
+        nbc_controller_advance(c, c.ctrl, ext_actions ? ext_actions + (size_t)i * c.ctrl->ext_k : nullptr, until_time, max_steps);
     });
 }
 
@@ -143,7 +145,7 @@ nbiot_sim_kernel(NbKernelArgs A, const uint8_t *ext_actions, int until_time, int
 __global__ void __launch_bounds__(NB_WPB * 32)
 nbiot_reset_kernel(NbKernelArgs A, int construct, const uint64_t *seeds)
 {
-    if (construct) nb_for_each_instance<false>(A, [&](NbCtx &c, int i) { nbc_construct(c, seeds[i], A.ctrl); nbc_reset(c); });
+    if (construct) nb_for_each_instance<false>(A, [&](NbCtx &c, int i) { nbc_construct(c, seeds[i], c.ctrl); nbc_reset(c); });
     else nb_for_each_instance<true>(A, [&](NbCtx &c, int) { nbc_reset(c); });
 }
 
@@ -242,7 +244,7 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     static_assert(sizeof(NbHdr) % 16 == 0, "NbHdr must be a multiple of 16 bytes for the staged copies");
     if (!conf || !state_dev || !seeds || !lut2 || !mcs || !ctrl || !out || n_inst <= 0) return set_err(NBIOT_E_INVALID, "nbiot_create: null or empty argument");
     if (conf->ue_cap < 1 || conf->ue_cap > 65535) return set_err(NBIOT_E_INVALID, "nbiot_create: ue_cap must be in 1..65535");
-    if (conf->grid_w < 256 || (conf->grid_w & (conf->grid_w - 1))) return set_err(NBIOT_E_INVALID, "nbiot_create: grid_w must be a power of two >= 256");
+    if (conf->grid_w < 256 || conf->grid_w > 32 * NB_BLK_MAX || (conf->grid_w & (conf->grid_w - 1))) return set_err(NBIOT_E_INVALID, "nbiot_create: grid_w must be a power of two in 256..4096");
     if (conf->hist_cap < 1 || conf->n_carriers < 1 || conf->n_carriers > 2) return set_err(NBIOT_E_INVALID, "nbiot_create: bad hist_cap / n_carriers");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_err(NBIOT_E_NOGPU, "no CUDA device: this library has no CPU path");

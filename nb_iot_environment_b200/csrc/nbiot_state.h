@@ -32,6 +32,7 @@
 #define NB_RAR_WIN 8         /* open RAR windows per CE level (300 sf window / 80 sf period) */
 #define NB_SCLOG 16          /* non-anchor NPRACH starts remembered (2-carrier cells)        */
 #define NB_RA_SLACK 64       /* tombstones tolerated in a random-access list                 */
+#define NB_BLK_MAX 128       /* 32-column block summaries per carrier: grid_w <= 4096        */
 
 /* event types kept in the generic pool */
 enum { NB_EV_NONE = 0, NB_EV_RAR_END = 1, NB_EV_MSG3 = 2, NB_EV_NPUSCH_END = 3 };
@@ -135,6 +136,7 @@ typedef struct __attribute__((aligned(16))) NbHdr {
     int32_t next_mac_idx, mac_valid;
     /* ---- carrier ---- */
     int32_t t_now, t_ahead;
+    uint16_t blk[2][NB_BLK_MAX];      /* OR of the column masks of each 32-column block of the ring (window tests) */
     int32_t max_lookahead, max_live;  /* high-water marks since reset: columns kept ahead, live UEs (capacity planning) */
     NbResource res[2][3];
     int32_t occ_head_start[3], occ_head_end[3], occ_tail[3];   /* ring cursors (monotone counters) */

@@ -86,8 +86,8 @@ def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256):
         raise NotImplementedError(f"sort_criterium '{sort}' is not supported")
     if n_carriers not in (1, 2):
         raise ValueError('n_carriers must be 1 or 2')
-    if grid_w & (grid_w - 1) or grid_w < 256:
-        raise ValueError('grid_w must be a power of two >= 256')
+    if grid_w & (grid_w - 1) or grid_w < 256 or grid_w > 4096:
+        raise ValueError('grid_w must be a power of two in 256..4096')
     M = int(conf['M'])
     c = NbiotConf()
     c.ratio = float(conf['ratio'])
