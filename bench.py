@@ -157,6 +157,9 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # anything a library prints on stdout (e.g. NCCL's version banner) goes to stderr: stdout carries ONE JSON line
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import __graft_entry__ as g
     g.build_cuda()
@@ -283,7 +286,10 @@ def main():
     if world == 1:
         r = cpu_reference_arm(40, 0, cells_per_step=16 * (os.cpu_count() or 1))
         line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if dist is not None:
         dist.destroy_process_group()
     return 0
