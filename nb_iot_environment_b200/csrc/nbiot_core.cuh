@@ -79,7 +79,7 @@ NB_DEV int nbc_rep_index(int N_rep) { int r = 0; NB_NOUNROLL while ((1 << r) < N
 NB_DEV int nbc_sf_per_ru(int N_sc) { return N_sc == 12 ? 1 : N_sc == 6 ? 2 : N_sc == 3 ? 4 : N_sc == 1 ? 8 : -1; }
 
 /* ------------------------------------------------------------------ event pool */
-NB_FN void nbc_pool_push(NbCtx &c, uint64_t key, int type, int ce, int aux)
+NB_FNM2 void nbc_pool_push(NbCtx &c, uint64_t key, int type, int ce, int aux)
 {
     NbHdr *h = nbc_hdr(c);
     if (!h->pool_free) { NB_FAULT(c, NBIOT_FAULT_EVENT_SLOTS); return; }
@@ -126,7 +126,7 @@ NB_DEV uint32_t nbc_scan_chunks(NbCtx &c, int carrier, int a, int n)
 #define NB_GRID_MODE 0     /* 0: one column per lane per step; 1: 8-column chunks; 2: chunks + 32-column block summaries */
 #endif
 #if NB_GRID_MODE == 0
-NB_FN uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
+NB_FN1S uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
 {
     return (uint32_t)nbw_run([&]() -> int {
         uint32_t v = 0;
@@ -135,7 +135,7 @@ NB_FN uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
         return (int)nbw_or_u32(v);
     });
 }
-NB_FN void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, int set)
+NB_FNM3 void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, int set)
 {
     nbw_run([&]() -> int {
         NB_NOUNROLL
@@ -147,7 +147,7 @@ NB_FN void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, i
 #else
 /* OR of the column masks of [a, a+n), n >= 1: whole 32-column blocks come from the block summaries,
  * the ragged head and tail are read chunk-wise, so the cost does not grow with the window length */
-NB_FN uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
+NB_FN1S uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
 {
     NbHdr *h = nbc_hdr(c);
     int nblk = c.W >> 5;
@@ -170,7 +170,7 @@ NB_FN uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
 }
 
 /* columns [a, a+n): OR `mask` in (set = 1) or start them empty (set = 0, only used for freshly generated columns) */
-NB_FN void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, int set)
+NB_FNM3 void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, int set)
 {
     if (n <= 0) return;
     NbHdr *h = nbc_hdr(c);
@@ -321,7 +321,7 @@ NB_DEV void nbc_erase_past_sf(NbCtx &c, int t)                   /* carrier.py:4
 }
 
 /* Carrier.allocate_resources (carrier.py:556-605): first fit over delays x carriers x offsets */
-NB_FN int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int N_sc, int N_sf)
+NB_FNM4 int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int N_sc, int N_sf)
 {
     NbHdr *h = nbc_hdr(c);
     nbc_erase_past_sf(c, t);
@@ -351,7 +351,7 @@ NB_FN int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int N
 }
 
 /* NodeB.allocate_resources (node_b.py:435-450): retry with other subcarrier counts */
-NB_FN int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc, int N_ru, int N_rep, int *out_sc, int *out_sf)
+NB_FNM3 int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc, int N_ru, int N_rep, int *out_sc, int *out_sf)
 {
     int spr = nbc_sf_per_ru(N_sc);
     if (spr < 0) { NB_FAULT(c, NBIOT_FAULT_ACTION); *out_sc = N_sc; *out_sf = 0; return 0; }
@@ -372,7 +372,7 @@ NB_FN int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc, 
 }
 
 /* compute_offsets (carrier.py:115-252): time/frequency packing of the three NPRACH resources */
-NB_FN int nbc_compute_offsets(const int periods[3], const int N_sfs[3], const int N_scs[3], int sc_off[3], int sf_off[3])
+NB_FN1 int nbc_compute_offsets(const int periods[3], const int N_sfs[3], const int N_scs[3], int sc_off[3], int sf_off[3])
 {
     NB_NOUNROLL
     for (int i = 0; i < 3; ++i) sc_off[i] = sf_off[i] = 0;
@@ -436,7 +436,7 @@ NB_FN int nbc_compute_offsets(const int periods[3], const int N_sfs[3], const in
 }
 
 /* Carrier.update_ra_parameters (carrier.py:610-650) + SFGenerator.update (:377-380) + NprachResource.update (:345-355) */
-NB_FN void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int th_C0)
+NB_FN1 void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int th_C0)
 {
     NbHdr *h = nbc_hdr(c);
     int periods[3], N_sfs[3], N_scs[3];
@@ -478,7 +478,7 @@ NB_FN void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int 
 /* ------------------------------------------------------------------ NodeB helpers */
 NB_DEV int nbc_rar_sum(NbCtx &c, int ce) { return nbc_hdr(c)->rar_tot[ce]; }   /* sum(RAR_UEs[ce]), kept incrementally */
 
-NB_FN void nbc_update_state(NbCtx &c)                           /* node_b.py:264-276 */
+NB_FNM void nbc_update_state(NbCtx &c)                           /* node_b.py:264-276 */
 {
     NbHdr *h = nbc_hdr(c);
     if (nbc_rar_sum(c, 0) + nbc_rar_sum(c, 1) + nbc_rar_sum(c, 2)) h->state = NB_ST_RAR_WINDOW;
@@ -486,7 +486,7 @@ NB_FN void nbc_update_state(NbCtx &c)                           /* node_b.py:264
     else h->state = NB_ST_IDLE;
 }
 
-NB_FN void nbc_schedule_NPDCCH(NbCtx &c, int elapsed_sfs)       /* node_b.py:420-432 */
+NB_FNM void nbc_schedule_NPDCCH(NbCtx &c, int elapsed_sfs)       /* node_b.py:420-432 */
 {
     NbHdr *h = nbc_hdr(c);
     int left = h->NPDCCH_sf_left - elapsed_sfs; if (left < 0) left = 0;
@@ -523,7 +523,7 @@ NB_FN void nbc_ra_compact(NbCtx &c, int ce)
     h->ra_n[ce] = out;
 }
 
-NB_FN void nbc_ra_append(NbCtx &c, int ce, int slot, int state, int ue_ce, int attempts, int rar_w_id)
+NB_FNM3 void nbc_ra_append(NbCtx &c, int ce, int slot, int state, int ue_ce, int attempts, int rar_w_id)
 {
     NbHdr *h = nbc_hdr(c);
     if (h->ra_n[ce] >= c.ra_cap) {
@@ -548,7 +548,7 @@ NB_DEV double nbc_find_y(double x1, double y1, double x2, double y2, double x)  
 #define NB_S32 0.8660254037844386
 
 /* Channel.set_xy_loss / generate_xy / location / antenna_pattern (channel.py:100-118, :134-151) */
-NB_FN double nbc_place_ue(NbCtx &c)
+NB_FN1S double nbc_place_ue(NbCtx &c)
 {
     double x, y;
     for (;;) {
@@ -572,7 +572,7 @@ NB_FN double nbc_place_ue(NbCtx &c)
 }
 
 /* UEGenerator.generate_arrivals (ue_generator.py:54-81) + Population.get_new_arrivals (population.py:103-132) */
-NB_FN void nbc_new_arrivals(NbCtx &c, int t)
+NB_FN1 void nbc_new_arrivals(NbCtx &c, int t)
 {
     NbHdr *h = nbc_hdr(c);
     if (c.conf->random_traffic) {                 /* update_counter (ue_generator.py:45-52) */
@@ -626,7 +626,7 @@ NB_FN void nbc_new_arrivals(NbCtx &c, int t)
 /* ------------------------------------------------------------------ NPRACH pass */
 /* AccessProcedure.NPRACH_start (access_procedure.py:37-91), Population.NPRACH_start (population.py:168-188),
  * Channel.preamble_detection (channel.py:156-176) */
-NB_FN void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
+NB_FN1 void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
 {
     NbHdr *h = nbc_hdr(c);
     int t = occ.t_start, N_sc = occ.N_sc, N_sf = occ.N_sf, N_pream = 4 * occ.N_sc;
@@ -740,7 +740,7 @@ NB_FN void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
 }
 
 /* AccessProcedure.NPRACH_end (access_procedure.py:93-116) + NodeB.start_RAR_window (node_b.py:524-554) */
-NB_FN void nbc_NPRACH_end(NbCtx &c, int ce, int t)
+NB_FN1S void nbc_NPRACH_end(NbCtx &c, int ce, int t)
 {
     NbHdr *h = nbc_hdr(c);
     int counter = h->RAR_counter[ce];
@@ -764,7 +764,7 @@ NB_FN void nbc_NPRACH_end(NbCtx &c, int ce, int t)
 }
 
 /* ------------------------------------------------------------------ contention set / MAC timers */
-NB_FN void nbc_mac_refresh(NbCtx &c)
+NB_FN1 void nbc_mac_refresh(NbCtx &c)
 {
     NbHdr *h = nbc_hdr(c);
     int n = h->cont_n;
@@ -791,7 +791,7 @@ NB_DEV void nbc_cont_remove(NbCtx &c, int idx)
 }
 
 /* Population.msg3_grant (population.py:201-256): the first UE of the list that is in RAR state */
-NB_FN void nbc_msg3_grant(NbCtx &c, int ce, int t, int t_msg3_end, int I_tbs, int N_rep)
+NB_FN1S void nbc_msg3_grant(NbCtx &c, int ce, int t, int t_msg3_end, int I_tbs, int N_rep)
 {
     NbHdr *h = nbc_hdr(c);
     NbRaEntry *L = c.ra[ce];
@@ -823,7 +823,7 @@ NB_FN void nbc_msg3_grant(NbCtx &c, int ce, int t, int t_msg3_end, int I_tbs, in
 }
 
 /* Population.MAC_timeout (population.py:151-163) */
-NB_FN void nbc_MAC_timeout(NbCtx &c, int idx)
+NB_FN1S void nbc_MAC_timeout(NbCtx &c, int idx)
 {
     NbContEntry e = c.cont[idx];
     nbc_cont_remove(c, idx);
@@ -833,7 +833,7 @@ NB_FN void nbc_MAC_timeout(NbCtx &c, int idx)
 }
 
 /* Population.RAR_window_end (population.py:258-306): unserved UEs of the window back off */
-NB_FN void nbc_population_RAR_window_end(NbCtx &c, int t, int ce, int backoff, int rar_w_id)
+NB_FN1 void nbc_population_RAR_window_end(NbCtx &c, int t, int ce, int backoff, int rar_w_id)
 {
     NbHdr *h = nbc_hdr(c);
     NbRaEntry *L = c.ra[ce];
@@ -881,7 +881,7 @@ NB_FN void nbc_population_RAR_window_end(NbCtx &c, int t, int ce, int backoff, i
 }
 
 /* ------------------------------------------------------------------ connected queue */
-NB_FN void nbc_conn_insert(NbCtx &c, int slot)
+NB_FNM4 void nbc_conn_insert(NbCtx &c, int slot)
 {
     NbHdr *h = nbc_hdr(c);
     NbUe *u = &c.ue[slot];
@@ -916,7 +916,7 @@ NB_FN void nbc_conn_insert(NbCtx &c, int slot)
     u->where = NB_IN_CONNECTED;
 }
 
-NB_FN void nbc_conn_remove(NbCtx &c, int slot)
+NB_FN1S void nbc_conn_remove(NbCtx &c, int slot)
 {
     NbHdr *h = nbc_hdr(c);
     int n = h->conn_n;
@@ -946,7 +946,7 @@ NB_FN void nbc_conn_remove(NbCtx &c, int slot)
 
 /* the first N_users UEs of the sorted queue whose CE level the remaining NPDCCH subframes allow
  * (NodeB.get_node_info, node_b.py:301-312) */
-NB_FN void nbc_conn_select(NbCtx &c)
+NB_FN1S void nbc_conn_select(NbCtx &c)
 {
     NbHdr *h = nbc_hdr(c);
     int max_CE = nb_ce_for_sf_left[h->NPDCCH_sf_left];
@@ -976,7 +976,7 @@ NB_FN void nbc_conn_select(NbCtx &c)
 }
 
 /* ------------------------------------------------------------------ receptions */
-NB_FN double nbc_get_bler(NbCtx &c, double snr, int itbs, int nr)   /* channel.py:76-79 */
+NB_FNM2 double nbc_get_bler(NbCtx &c, double snr, int itbs, int nr)   /* channel.py:76-79 */
 {
     if (!(snr > -30.0)) snr = -30.0;
     if (!(snr < 20.0)) snr = 20.0;
@@ -985,7 +985,7 @@ NB_FN double nbc_get_bler(NbCtx &c, double snr, int itbs, int nr)   /* channel.p
     return NB_DIV((double)NB_LDG(&c.lut2[(row * 8 + rep) * NB_LUT_SNR_PTS + idx]), NB_LUT_SCALE);
 }
 
-NB_FN void nbc_distribution_update(NbCtx &c, double sample)       /* node_b.py:207-225 */
+NB_FN1S void nbc_distribution_update(NbCtx &c, double sample)       /* node_b.py:207-225 */
 {
     NbHdr *h = nbc_hdr(c);
     if (h->k_dist > 1000) return;
@@ -1008,7 +1008,7 @@ NB_FN void nbc_distribution_update(NbCtx &c, double sample)       /* node_b.py:2
 
 /* RxProcedure.msg3_event (rx_procedure.py:29-51), Channel.msg3_detection / sinr_estimation
  * (channel.py:178-198, :221-234), NodeB.msg3_outcome (node_b.py:770-799) */
-NB_FN void nbc_msg3_event(NbCtx &c, int slot, int t)
+NB_FN1 void nbc_msg3_event(NbCtx &c, int slot, int t)
 {
     NbHdr *h = nbc_hdr(c);
     NbUe *u = &c.ue[slot];
@@ -1055,7 +1055,7 @@ NB_FN void nbc_msg3_event(NbCtx &c, int slot, int t)
 
 /* RxProcedure.NPUSCH_end (rx_procedure.py:54-61), Channel.NPUSCH_detection (channel.py:236-256),
  * NodeB.NPUSCH_end (node_b.py:801-830), PerfMonitor.account_rx/account_error/unregister_ue */
-NB_FN void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
+NB_FN1 void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
 {
     NbHdr *h = nbc_hdr(c);
     NbUe *u = &c.ue[slot];
@@ -1133,7 +1133,7 @@ NB_DEV int nbc_rar_list_cmp(NbCtx &c, int a, int b)              /* Python list 
     return na == nb ? 0 : (na < nb ? -1 : 1);
 }
 
-NB_FN void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:453-521 */
+NB_FN1 void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:453-521 */
 {
     NbHdr *h = nbc_hdr(c);
     NbSched P;
@@ -1182,7 +1182,7 @@ NB_FN void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:453
     nbc_update_state(c);
 }
 
-NB_FN void nbc_step_RAR_end(NbCtx &c, const uint8_t *a)         /* node_b.py:558-581 */
+NB_FN1S void nbc_step_RAR_end(NbCtx &c, const uint8_t *a)         /* node_b.py:558-581 */
 {
     NbHdr *h = nbc_hdr(c);
     int ce = h->cur_ce;
@@ -1207,7 +1207,7 @@ NB_DEV void nbc_clear_info(NbCtx &c)                             /* perf_monitor
     h->rx_sum = 0.0; h->rx_inv_sum = 0.0; h->rx_log_sum = 0.0;
 }
 
-NB_FN void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:584-693 */
+NB_FN1 void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:584-693 */
 {
     NbHdr *h = nbc_hdr(c);
     nbc_clear_info(c);
@@ -1266,7 +1266,7 @@ NB_FN void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:584
     nbc_update_state(c);
 }
 
-NB_FN void nbc_step_update(NbCtx &c, const uint8_t *a)          /* node_b.py:695-768 */
+NB_FN1 void nbc_step_update(NbCtx &c, const uint8_t *a)          /* node_b.py:695-768 */
 {
     NbHdr *h = nbc_hdr(c);
     h->thr_count = 0;
@@ -1302,7 +1302,7 @@ NB_FN void nbc_step_update(NbCtx &c, const uint8_t *a)          /* node_b.py:695
 /* ------------------------------------------------------------------ event selection */
 /* candidate codes: 0 NPDCCH_arrival, 1 NPRACH_update, 2+ce NPRACH_start, 5+ce NPRACH_end, 8 MAC_timer, 16+i pool[i].
  * The minimum (time, insertion count) key over the fixed slots and the pool = the reference's heap pop. */
-NB_FN uint64_t nbc_next_event(NbCtx &c, int *code)
+NB_FN1S uint64_t nbc_next_event(NbCtx &c, int *code)
 {
     NbHdr *h = nbc_hdr(c);
     if (!h->mac_valid) nbc_mac_refresh(c);
@@ -1400,7 +1400,7 @@ NB_DEV double nbc_reward(NbCtx &c)                               /* perf_monitor
 
 /* materialise the decision record (reward + info dict of NodeB.get_node_info, node_b.py:278-418) in HBM;
  * only called when an external agent or the host will look at it (cold path) */
-NB_FN void nbc_write_record(NbCtx &c, double reward, double occ_nprach, double occ_ra, double occ_npusch)
+NB_FN1 void nbc_write_record(NbCtx &c, double reward, double occ_nprach, double occ_ra, double occ_npusch)
 {
     NbHdr *h = nbc_hdr(c);
     nbiot_record_t *r = c.rec;
@@ -1476,7 +1476,7 @@ NB_FN void nbc_write_record(NbCtx &c, double reward, double occ_nprach, double o
 
 /* NodeB.get_node_info (node_b.py:278-418): its side effects always happen, the record is only materialised
  * when somebody will read it */
-NB_FN void nbc_node_info(NbCtx &c, int write_record, double reward)
+NB_FNM4 void nbc_node_info(NbCtx &c, int write_record, double reward)
 {
     NbHdr *h = nbc_hdr(c);
     double occ_nprach = 0.0, occ_ra = 0.0, occ_npusch = 0.0;
@@ -1612,7 +1612,7 @@ NB_DEV void nbc_node_step(NbCtx &c, const uint8_t *a)
 }
 
 /* fixed actions of internal agents: one value per set bit of the table's mask */
-NB_FN void nbc_apply_writes(NbCtx &c, const NbWrites *w)
+NB_FNM void nbc_apply_writes(NbCtx &c, const NbWrites *w)
 {
     uint32_t m = w->mask;                                      /* tables live in shared memory: plain loads */
     NbHdr *h = nbc_hdr(c);

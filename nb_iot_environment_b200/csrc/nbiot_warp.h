@@ -24,6 +24,44 @@
 #define NB_LANES 32
 #define NB_DEV __device__ __forceinline__
 #define NB_FN __device__ __noinline__
+/* functions with a single call site: NB_INLINE_SINGLE = 0 keeps them out of line, 1 inlines the small ones, 2 all */
+#ifndef NB_INLINE_SINGLE
+#define NB_INLINE_SINGLE 1
+#endif
+/* small functions with several call sites: NB_INLINE_MULTI = 1 inlines the tiny ones, 2 also the mid-size ones */
+#ifndef NB_INLINE_MULTI
+#define NB_INLINE_MULTI 3
+#endif
+#if NB_INLINE_MULTI >= 3
+#define NB_FNM3 __device__ __forceinline__
+#else
+#define NB_FNM3 __device__ __noinline__
+#endif
+#if NB_INLINE_MULTI >= 4
+#define NB_FNM4 __device__ __forceinline__
+#else
+#define NB_FNM4 __device__ __noinline__
+#endif
+#if NB_INLINE_MULTI >= 1
+#define NB_FNM __device__ __forceinline__
+#else
+#define NB_FNM __device__ __noinline__
+#endif
+#if NB_INLINE_MULTI >= 2
+#define NB_FNM2 __device__ __forceinline__
+#else
+#define NB_FNM2 __device__ __noinline__
+#endif
+#if NB_INLINE_SINGLE >= 1
+#define NB_FN1S __device__ __forceinline__
+#else
+#define NB_FN1S __device__ __noinline__
+#endif
+#if NB_INLINE_SINGLE >= 2
+#define NB_FN1 __device__ __forceinline__
+#else
+#define NB_FN1 __device__ __noinline__
+#endif
 #define NB_FULL 0xFFFFFFFFu
 #define NB_NOUNROLL _Pragma("unroll 1")
 NB_DEV int nbw_lane() { return (int)(threadIdx.x & 31u); }
@@ -46,6 +84,12 @@ NB_DEV int nbw_ffsll(uint64_t v) { return __ffsll((long long)v); }
 #define NB_LANES NBIOT_EMU_LANES
 #define NB_DEV static inline
 #define NB_FN static
+#define NB_FN1 static
+#define NB_FN1S static
+#define NB_FNM static
+#define NB_FNM2 static
+#define NB_FNM3 static
+#define NB_FNM4 static
 #define NB_LDG(p) (*(p))
 #define NB_NOUNROLL
 static inline int nbw_popc(uint32_t v) { return __builtin_popcount(v); }
