@@ -25,6 +25,9 @@
 #ifndef NBIOT_CORE_CUH
 #define NBIOT_CORE_CUH
 
+#ifndef NB_GRID_MODE
+#define NB_GRID_MODE 0     /* 0: one column per lane per step; 1: 8-column chunks; 2: chunks + 32-column block summaries */
+#endif
 #include "nbiot_params.h"
 #include "nbiot_rng.h"
 #include "nbiot_state.h"
@@ -122,9 +125,6 @@ NB_DEV uint32_t nbc_scan_chunks(NbCtx &c, int carrier, int a, int n)
     return acc;
 }
 
-#ifndef NB_GRID_MODE
-#define NB_GRID_MODE 0     /* 0: one column per lane per step; 1: 8-column chunks; 2: chunks + 32-column block summaries */
-#endif
 #if NB_GRID_MODE == 0
 NB_FN1S uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
 {
@@ -1312,9 +1312,9 @@ NB_FN1S uint64_t nbc_next_event(NbCtx &c, int *code)
         nbw_sync();
         uint64_t k = NB_KEY_NONE; int cd = -1;
         NB_NOUNROLL
-        for (int j = nbw_lane(); j < 16 + NB_EV_POOL; j += NB_LANES) {
-            uint64_t kj = j < 16 ? h->keys[j] : h->pool[j - 16].key;
-            if (kj < k) { k = kj; cd = j; }
+        for (int j = nbw_lane(); j < NB_FIXED_KEYS + NB_EV_POOL; j += NB_LANES) {
+            uint64_t kj = j < NB_FIXED_KEYS ? h->keys[j] : h->pool[j - NB_FIXED_KEYS].key;
+            if (kj < k) { k = kj; cd = j < NB_FIXED_KEYS ? j : j + (16 - NB_FIXED_KEYS); }
         }
         uint64_t m = nbw_min_u64(k);
         uint32_t who = nbw_ballot(k == m && cd >= 0);
@@ -1540,9 +1540,9 @@ NB_FN void nbc_reset(NbCtx &c)
 {
     NbHdr *h = nbc_hdr(c);
     h->fault = 0; h->draws = 0; h->events = 0; h->subframes_done = 0;
-    h->seq = 0; h->pool_free = ~0ULL;
+    h->seq = 0; h->pool_free = (1ULL << NB_EV_POOL) - 1ULL;
     NB_NOUNROLL
-    for (int i = 0; i < 16; ++i) h->keys[i] = NB_KEY_NONE;
+    for (int i = 0; i < NB_FIXED_KEYS; ++i) h->keys[i] = NB_KEY_NONE;
     NB_NOUNROLL
     for (int i = 0; i < NB_EV_POOL; ++i) { h->pool[i].type = NB_EV_NONE; h->pool[i].key = NB_KEY_NONE; }
     /* population.reset */

@@ -27,11 +27,12 @@
 #include "nbiot_ctrl.h"
 #include "nbiot_record.h"
 
-#define NB_EV_POOL 64        /* pending RAR_window_end / Msg3 / NPUSCH_end events            */
-#define NB_OCC_RING 32       /* pending NPRACH occasions per CE level (look-ahead / 80 sf)   */
+#define NB_EV_POOL 48        /* pending RAR_window_end / Msg3 / NPUSCH_end events            */
+#define NB_OCC_RING 24       /* pending NPRACH occasions per CE level (look-ahead / 80 sf)   */
 #define NB_RAR_WIN 8         /* open RAR windows per CE level (300 sf window / 80 sf period) */
 #define NB_SCLOG 16          /* non-anchor NPRACH starts remembered (2-carrier cells)        */
 #define NB_RA_SLACK 64       /* tombstones tolerated in a random-access list                 */
+#define NB_FIXED_KEYS 10      /* fixed event slots (9 used)                                   */
 #define NB_BLK_MAX 128       /* 32-column block summaries per carrier: grid_w <= 4096        */
 
 /* event types kept in the generic pool */
@@ -111,7 +112,7 @@ typedef struct __attribute__((aligned(16))) NbHdr {
     int32_t action3[3];
     /* keys of the fixed event slots, NB_KEY_NONE when nothing is pending:
      * 0 NPDCCH_arrival, 1 NPRACH_update, 2+ce next NPRACH_start, 5+ce next NPRACH_end, 8 next MAC_timer */
-    uint64_t keys[16];
+    uint64_t keys[NB_FIXED_KEYS];
     int32_t cur_ce, cur_wid, cur_t;   /* payload of the RAR_window_end being decided */
     uint8_t ctrl_action[24];          /* the controller's shared action vector (controller.py:33) */
     /* ---- NPRACH configuration ---- */
@@ -136,7 +137,9 @@ typedef struct __attribute__((aligned(16))) NbHdr {
     int32_t next_mac_idx, mac_valid;
     /* ---- carrier ---- */
     int32_t t_now, t_ahead;
+#if defined(NB_GRID_MODE) && NB_GRID_MODE == 2
     uint16_t blk[2][NB_BLK_MAX];      /* OR of the column masks of each 32-column block of the ring (window tests) */
+#endif
     int32_t max_lookahead, max_live;  /* high-water marks since reset: columns kept ahead, live UEs (capacity planning) */
     NbResource res[2][3];
     int32_t occ_head_start[3], occ_head_end[3], occ_tail[3];   /* ring cursors (monotone counters) */
