@@ -1539,7 +1539,8 @@ NB_FN void nbc_construct(NbCtx &c, uint64_t seed, const NbCtrlDev *ctrl)
 NB_FN void nbc_reset(NbCtx &c)
 {
     NbHdr *h = nbc_hdr(c);
-    h->fault = 0; h->draws = 0; h->events = 0; h->subframes_done = 0;
+    /* the random generator is an object outside the cell (system_creator.py:22): a reset does not rewind it */
+    h->fault = 0; h->events = 0; h->subframes_done = 0;
     h->seq = 0; h->pool_free = (1ULL << NB_EV_POOL) - 1ULL;
     NB_NOUNROLL
     for (int i = 0; i < NB_FIXED_KEYS; ++i) h->keys[i] = NB_KEY_NONE;

@@ -258,6 +258,20 @@ class BatchedNBIoTEnv:
         sv = self.state[os_:os_ + N * cap * 4].cpu().numpy().view(np.int32).reshape(N, cap)
         return inc, dl, sv
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save_state(self):
+        """Snapshot of the complete simulation state (every instance: clock, event slots, lists, UE records, random
+        counters). The reference has no checkpointing; here it is one tensor copy."""
+        torch.cuda.synchronize(self.device)
+        return self.state.clone()
+
+    def load_state(self, snapshot):
+        """Restore a snapshot taken from an environment created with the same conf, capacities and num_envs."""
+        if snapshot.numel() != self.state.numel():
+            raise ValueError('snapshot size does not match this environment (conf / capacities / num_envs differ)')
+        self.state.copy_(snapshot.to(self.device))
+        torch.cuda.synchronize(self.device)
+
     def stats_tensor(self):
         """int64[N_STATS] on the device: episode statistics summed over this handle's instances."""
         with torch.cuda.device(self.device):

@@ -201,3 +201,74 @@ def test_faults_are_never_silent():
     recs = env.records()
     assert recs['fault'][0] == 0 and recs['fault'][1] & 4
     env.close()
+
+
+def test_checkpoint_resume_and_ragged_batch():
+    """state snapshot -> restore in a fresh environment continues bit-identically; batch sizes that do not fill a CTA"""
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from oracle_controller import OracleController
+    for N in (1, 5):
+        seeds = list(range(200, 200 + N))
+        env = BatchedNBIoTEnv(CFG3, agents_conf=NPUSCH_AGENTS, ext_agent=0, num_envs=N, seeds=seeds, ue_cap=1024, grid_w=2048)
+        env.reset()
+        rng = np.random.default_rng(3)
+        acts = [_random_ext_actions(rng, env.action_nvec, N) for _ in range(60)]
+        for a in acts[:30]:
+            env.step(a)
+        snap = env.save_state()
+        for a in acts[30:]:
+            obs_a, rew_a, _, _, _ = env.step(a)
+        rec_a, obs_a, rew_a = env.records(), obs_a.cpu().numpy().copy(), rew_a.cpu().numpy().copy()
+        env.close()
+        env2 = BatchedNBIoTEnv(CFG3, agents_conf=NPUSCH_AGENTS, ext_agent=0, num_envs=N, seeds=[0] * N, ue_cap=1024, grid_w=2048)
+        env2.load_state(snap)
+        for a in acts[30:]:
+            obs_b, rew_b, _, _, _ = env2.step(a)
+        assert env2.records().tobytes() == rec_a.tobytes()
+        assert np.array_equal(obs_b.cpu().numpy(), obs_a) and np.array_equal(rew_b.cpu().numpy(), rew_a)
+        env2.close()
+        c = OracleController(CFG3, seeds[-1], agents_conf=NPUSCH_AGENTS, ext_agent=0)
+        c.reset()
+        for a in acts:
+            c.step(a[-1])
+        assert not record_diff(c.rec, rec_a[-1], rtol=0.0)
+
+
+def test_reset_after_run_and_agent_reconfiguration():
+    """the scripts' sequence Controller(...).reset(); set_ext_agent(k); env.reset() (evaluate_RL.py:128-131), a second
+    reset after running (NodeB.reset keeps total_departures / NPDCCH_sf_left), and
+    DummyAgent.set_action on an internal agent"""
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from oracle_controller import OracleController
+    N = 6
+    seeds = list(range(300, 300 + N))
+    conf = dict(CFG1, ratio=0.5)
+    env = BatchedNBIoTEnv(conf, agents_conf=NPRACH_AGENTS, ext_agent=-1, num_envs=N, seeds=seeds, ue_cap=1000, grid_w=2048)
+    ctrls = [OracleController(conf, s, agents_conf=NPRACH_AGENTS, ext_agent=-1) for s in seeds]
+    env.reset()
+    env.set_ext_agent(3)
+    env.set_internal_action(2, {'backoff': 5, 'mac_timer': 4})
+    obs, _ = env.reset()
+    for c in ctrls:
+        c.reset()
+        c.t.set_ext_agent(3)
+        c.t.agents[2].set_action({'backoff': 5, 'mac_timer': 4})
+        o = c.reset()
+    rng = np.random.default_rng(9)
+    for rnd in range(2):
+        for _ in range(4):
+            a = _random_ext_actions(rng, env.action_nvec, N)
+            a[:, 0] = np.minimum(a[:, 0], a[:, 1])
+            obs, rew, _, _, _ = env.step(a)
+            recs = env.records()
+            for i, c in enumerate(ctrls):
+                o, r = c.step(a[i])
+                assert np.array_equal(o, obs[i].cpu().numpy()) and r == rew[i].item()
+                assert not record_diff(c.rec, recs[i], rtol=0.0)
+        obs, _ = env.reset()            # reset in the middle of an episode
+        recs = env.records()
+        for i, c in enumerate(ctrls):
+            o = c.reset()
+            assert np.array_equal(o, obs[i].cpu().numpy())
+            assert not record_diff(c.rec, recs[i], rtol=0.0)
+    env.close()
