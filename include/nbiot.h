@@ -92,6 +92,10 @@ int nbiot_reset(nbiot_handle_t *h, void *stream);
 /* replaces Controller.step + to_next_step (controller.py:234-288), or Controller.run_until (:185-195)
  * when ext_actions is NULL. ext_actions: device uint8[n_inst][ext_k]. until_time < 0: no time bound. */
 int nbiot_advance(nbiot_handle_t *h, const uint8_t *ext_actions_dev, int until_time, int max_steps, void *stream);
+/* the same for a subset: instances with active_dev[i] == 0 are left untouched (their record, clock and random
+ * stream do not move) -- what a per-instance wrapper does when it answers without calling env.step
+ * (wrappers.py:94-103). active_dev: device uint8[n_inst], NULL = all. */
+int nbiot_advance_masked(nbiot_handle_t *h, const uint8_t *ext_actions_dev, const uint8_t *active_dev, int until_time, int max_steps, void *stream);
 
 /* device pointer to nbiot_record_t[n_inst] (reward + info dict of NodeB.get_node_info, node_b.py:278-418)
  * and to the per-period lists incoming (double) / delays / service_times (int32), hist_cap entries each */

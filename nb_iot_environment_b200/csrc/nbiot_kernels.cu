@@ -100,7 +100,7 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
 /* Claim instances from the work counter; stage [ctx | header | grid] in this warp's shared-memory slice;
  * run `body`; write header and grid back. */
 template <bool LOAD, class Body>
-__device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, Body body)
+__device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, const uint8_t *active, Body body)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ NbCtrlDev s_ctrl;                       /* the controller tables, once per CTA */
@@ -118,6 +118,7 @@ __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, Body
         if (lane == 0) i = (int)atomicAdd(A.counter, 1u);
         i = __shfl_sync(0xFFFFFFFFu, i, 0);
         if (i >= A.L.n_inst) break;
+        if (active && !active[i]) continue;
         if (lane == 0) nb_fill_ctx(c, A, i, &s_ctrl);
         if (LOAD) {
             nb_copy16(hdr_s, hdr_g + i, A.hdr_bytes16);
@@ -134,9 +135,9 @@ __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, Body
 
 /* the hot kernel: Controller.step / run_until for every instance */
 __global__ void __launch_bounds__(NB_WPB * 32, NB_MIN_CTAS)
-nbiot_sim_kernel(NbKernelArgs A, const uint8_t *ext_actions, int until_time, int max_steps)
+nbiot_sim_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps)
 {
-    nb_for_each_instance<true>(A, [&](NbCtx &c, int i) {
+    nb_for_each_instance<true>(A, active, [&](NbCtx &c, int i) {
         nbc_controller_advance(c, c.ctrl, ext_actions ? ext_actions + (size_t)i * c.ctrl->ext_k : nullptr, until_time, max_steps);
     });
 }
@@ -145,8 +146,8 @@ nbiot_sim_kernel(NbKernelArgs A, const uint8_t *ext_actions, int until_time, int
 __global__ void __launch_bounds__(NB_WPB * 32)
 nbiot_reset_kernel(NbKernelArgs A, int construct, const uint64_t *seeds)
 {
-    if (construct) nb_for_each_instance<false>(A, [&](NbCtx &c, int i) { nbc_construct(c, seeds[i], c.ctrl); nbc_reset(c); });
-    else nb_for_each_instance<true>(A, [&](NbCtx &c, int) { nbc_reset(c); });
+    if (construct) nb_for_each_instance<false>(A, nullptr, [&](NbCtx &c, int i) { nbc_construct(c, seeds[i], c.ctrl); nbc_reset(c); });
+    else nb_for_each_instance<true>(A, nullptr, [&](NbCtx &c, int) { nbc_reset(c); });
 }
 
 /* Controller.get_obs (controller.py:105-120) for the whole batch: one thread per (instance, obs element) */
@@ -213,12 +214,12 @@ static NbKernelArgs make_args(nbiot_handle_t *h)
     return A;
 }
 
-static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, int until_time, int max_steps, cudaStream_t st)
+static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, int until_time, int max_steps, cudaStream_t st, const uint8_t *active = nullptr)
 {
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->counter_dev, 0, sizeof(unsigned int), st));
     NbKernelArgs A = make_args(h);
-    if (mode == 2) nbiot_sim_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, ext_actions, until_time, max_steps);
+    if (mode == 2) nbiot_sim_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, ext_actions, active, until_time, max_steps);
     else nbiot_reset_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, mode == 0 ? 1 : 0, h->seeds_dev);
     CK(cudaGetLastError());
     h->launches += 1;
@@ -322,6 +323,13 @@ int nbiot_advance(nbiot_handle_t *h, const uint8_t *ext_actions_dev, int until_t
     if (!h) return set_err(NBIOT_E_INVALID, "nbiot_advance: null handle");
     if (max_steps < 1) return set_err(NBIOT_E_INVALID, "nbiot_advance: max_steps must be >= 1");
     return launch_sim(h, 2, ext_actions_dev, until_time, max_steps, (cudaStream_t)stream);
+}
+
+int nbiot_advance_masked(nbiot_handle_t *h, const uint8_t *ext_actions_dev, const uint8_t *active_dev, int until_time, int max_steps, void *stream)
+{
+    if (!h) return set_err(NBIOT_E_INVALID, "nbiot_advance_masked: null handle");
+    if (max_steps < 1) return set_err(NBIOT_E_INVALID, "nbiot_advance_masked: max_steps must be >= 1");
+    return launch_sim(h, 2, ext_actions_dev, until_time, max_steps, (cudaStream_t)stream, active_dev);
 }
 
 int nbiot_records_ptr(nbiot_handle_t *h, void **records_dev)

@@ -196,16 +196,23 @@ class BatchedNBIoTEnv:
             obs = self._gather()
         return obs, LazyInfos(self)
 
-    def step(self, actions):
+    def step(self, actions, active=None):
         """actions: int[N, k] (k = number of action items of the external agent) as a CUDA tensor (stays on
-        the device) or a host array (copied). Returns (obs, reward, terminated, truncated, infos)."""
+        the device) or a host array (copied). Returns (obs, reward, terminated, truncated, infos).
+        active: optional bool[N]; instances with False are not stepped at all (their observation, reward and
+        record stay as they were) -- used by wrappers that answer without calling the environment."""
         k = self.ctrl.ext_k
         with torch.cuda.device(self.device):
             if isinstance(actions, torch.Tensor):
                 a = actions.to(device=self.device, dtype=torch.uint8).reshape(self.num_envs, k).contiguous()
             else:
                 a = torch.from_numpy(np.ascontiguousarray(np.asarray(actions).reshape(self.num_envs, k), dtype=np.uint8)).to(self.device)
-            _cabi.check(self.L.nbiot_advance(self._h, a.data_ptr(), -1, 1 << 30, self._stream()))
+            if active is None:
+                _cabi.check(self.L.nbiot_advance(self._h, a.data_ptr(), -1, 1 << 30, self._stream()))
+            else:
+                m = torch.as_tensor(active).to(device=self.device, dtype=torch.uint8).reshape(self.num_envs).contiguous()
+                _cabi.check(self.L.nbiot_advance_masked(self._h, a.data_ptr(), m.data_ptr(), -1, 1 << 30, self._stream()))
+                self._last_mask = m
             self._last_actions = a          # keep alive until the kernel has consumed it
             obs = self._gather()
         return obs, self._reward, self._false, self._false, LazyInfos(self)
@@ -242,6 +249,19 @@ class BatchedNBIoTEnv:
             self._last_actions = a
 
     # ------------------------------------------------------------------ results
+    def record_field(self, name):
+        """one field of the decision records as a torch tensor ON THE DEVICE (a strided view of the state buffer;
+        int32 / float64 fields only) -- lets wrappers read info values without a host round trip."""
+        dt, off = RECORD_DTYPE.fields[name][0], RECORD_DTYPE.fields[name][1]
+        base, shape = dt.base, dt.shape
+        tdt = {np.dtype('<i4'): torch.int32, np.dtype('<f8'): torch.float64}[base]
+        esz = base.itemsize
+        n_el = int(np.prod(shape)) if shape else 1
+        flat = self.state[self._rec_off:self._rec_off + self.num_envs * RECORD_DTYPE.itemsize].view(tdt)
+        stride = RECORD_DTYPE.itemsize // esz
+        v = torch.as_strided(flat, (self.num_envs, n_el), (stride, 1), flat.storage_offset() + off // esz)
+        return v if shape else v[:, 0]
+
     def records(self):
         """decision records of all instances as a numpy structured array (device -> host copy)."""
         n = self.num_envs * RECORD_DTYPE.itemsize
