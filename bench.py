@@ -114,7 +114,7 @@ def cpu_reference_arm(steps, warmup, cells_per_step=None):
     from nb_iot_environment_b200.record import make_conf
     oracle_py.build()
     cores = os.cpu_count() or 1
-    cells = cells_per_step or 16 * cores
+    cells = cells_per_step or 64 * cores
     ctrl = ControllerTables(AGENTS, EXT_AGENT).build()
     conf = make_conf(CONF, **CAPS)
     acts = ext_actions(warmup + steps, cells, seed=999)
@@ -284,7 +284,7 @@ def main():
         'wall_s_timed_region': wall1,
     }
     if world == 1:
-        r = cpu_reference_arm(40, 0, cells_per_step=16 * (os.cpu_count() or 1))
+        r = cpu_reference_arm(40, 0, cells_per_step=64 * (os.cpu_count() or 1))     # ~15 CPU-seconds of work
         line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
