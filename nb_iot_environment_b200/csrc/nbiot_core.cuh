@@ -50,7 +50,7 @@ struct __attribute__((aligned(16))) NbCtx {
     nbiot_record_t *rec;
     const uint16_t *lut2;
     const uint8_t *mcs;
-    const nbiot_conf_t *conf;
+    nbiot_conf_t conf;        /* by value: one shared-memory load per use instead of a pointer chase into HBM */
     const NbCtrlDev *ctrl;    /* controller tables (shared memory in the kernels) */
     int32_t *evlog;           /* optional (t, type) pop log for debugging */
     int W, ue_cap, ra_cap, hist_cap, C, evlog_cap;
@@ -357,7 +357,7 @@ NB_FNM3 int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc
     if (spr < 0) { NB_FAULT(c, NBIOT_FAULT_ACTION); *out_sc = N_sc; *out_sf = 0; return 0; }
     int n_sc = N_sc, N_sf = spr * N_ru * N_rep;
     int t_ul_end = nbc_carrier_allocate(c, c_id, ref_t, delay, N_sc, N_sf);
-    if (!t_ul_end && c.conf->sc_adjustment && !NB_FATAL(c)) {
+    if (!t_ul_end && c.conf.sc_adjustment && !NB_FATAL(c)) {
         int row = N_sc == 1 ? 0 : N_sc == 3 ? 1 : N_sc == 6 ? 2 : 3;
         NB_NOUNROLL
         for (int i = 0; i < 3; ++i) {
@@ -561,7 +561,7 @@ NB_FN1S double nbc_place_ue(NbCtx &c)
     double distance = NB_SQRT(NB_ADD(NB_MUL(x_t, x_t), NB_MUL(y, y)));
     double cos_theta = NB_DIV(x_t, distance);
     double theta = NB_SUB(NB_MUL(nb_acos(cos_theta), NB_RAD2DEG), 60.0);
-    double range = c.conf->max_d > 0 ? c.conf->max_d : NB_MAX_RANGE;
+    double range = c.conf.max_d > 0 ? c.conf.max_d : NB_MAX_RANGE;
     double R = NB_MUL(distance, range); if (!(R > 0.1)) R = 0.1;
     double q = NB_DIV(theta, 65.0);
     double ap = NB_MUL(12.0, NB_MUL(q, q)); if (!(ap < 20.0)) ap = 20.0;
@@ -575,7 +575,7 @@ NB_FN1S double nbc_place_ue(NbCtx &c)
 NB_FN1 void nbc_new_arrivals(NbCtx &c, int t)
 {
     NbHdr *h = nbc_hdr(c);
-    if (c.conf->random_traffic) {                 /* update_counter (ue_generator.py:45-52) */
+    if (c.conf.random_traffic) {                 /* update_counter (ue_generator.py:45-52) */
         int new_count = t / NB_T_UNIFORM;
         if (new_count > h->gen_counter) { h->gen_counter = new_count; h->gen_p = NB_ADD(0.0, NB_MUL(0.8, nbc_u01(c))); }
     }
@@ -600,7 +600,7 @@ NB_FN1 void nbc_new_arrivals(NbCtx &c, int t)
     NB_NOUNROLL
     for (int n = 0; n < total; ++n) {
         h->ue_count += 1;
-        int buffer = c.conf->buffer_hi > c.conf->buffer_lo ? nbc_integers(c, c.conf->buffer_lo, c.conf->buffer_hi + 1) : c.conf->buffer_lo;
+        int buffer = c.conf.buffer_hi > c.conf.buffer_lo ? nbc_integers(c, c.conf.buffer_lo, c.conf.buffer_hi + 1) : c.conf.buffer_lo;
         double loss = nbc_place_ue(c);
         int beta = 0;
         if (beta_arrivals > 0) { beta = 1; beta_arrivals -= 1; }
@@ -886,7 +886,7 @@ NB_FNM4 void nbc_conn_insert(NbCtx &c, int slot)
     NbHdr *h = nbc_hdr(c);
     NbUe *u = &c.ue[slot];
     uint64_t k1;
-    if (c.conf->sort_by_loss) k1 = nb_d2u(u->loss);           /* loss > 0: the bit pattern orders like the value */
+    if (c.conf.sort_by_loss) k1 = nb_d2u(u->loss);           /* loss > 0: the bit pattern orders like the value */
     else k1 = (uint64_t)(uint32_t)u->t_connection;
     int n = h->conn_n;
     NbConnEntry *Q = c.conn;
@@ -1074,8 +1074,8 @@ NB_FN1 void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
         if (h->n_rx < NBIOT_STEP_LIST) { h->rx_id[h->n_rx] = u->id; h->rx_delay[h->n_rx] = d; }
         h->n_rx += 1;
         h->rx_sum = NB_ADD(h->rx_sum, (double)d);
-        if (c.conf->reward_criteria == NB_RW_INVD_USERS) h->rx_inv_sum = NB_ADD(h->rx_inv_sum, NB_DIV(1.0, NB_DIV((double)d, 1000.0)));
-        if (c.conf->reward_criteria == NB_RW_LOG_INVD_USERS) h->rx_log_sum = NB_ADD(h->rx_log_sum, nb_log(NB_DIV((double)d, 1000.0)));
+        if (c.conf.reward_criteria == NB_RW_INVD_USERS) h->rx_inv_sum = NB_ADD(h->rx_inv_sum, NB_DIV(1.0, NB_DIV((double)d, 1000.0)));
+        if (c.conf.reward_criteria == NB_RW_LOG_INVD_USERS) h->rx_log_sum = NB_ADD(h->rx_log_sum, nb_log(NB_DIV((double)d, 1000.0)));
         u->timestamp = t; h->attempts_count += 1;
         if (!u->buffer) {
             u->state = NB_UE_DONE;
@@ -1083,7 +1083,7 @@ NB_FN1 void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
             h->ue_departures[u->CE_level] += 1; h->thr_count += 1; h->total_bits += u->acked_data;
             int deps = h->ue_departures[0] + h->ue_departures[1] + h->ue_departures[2];
             h->av_delay = NB_ADD(h->av_delay, NB_DIV(NB_SUB((double)delay, h->av_delay), (double)deps));
-            if (c.conf->random_traffic) { if (nbc_bernoulli(c, h->gen_p) > 0) h->M_beta += 1; else h->M_uniform += 1; }   /* ue_generator.departure */
+            if (c.conf.random_traffic) { if (nbc_bernoulli(c, h->gen_p) > 0) h->M_beta += 1; else h->M_uniform += 1; }   /* ue_generator.departure */
             else if (u->beta && h->M_beta < h->M_beta_max) h->M_beta += 1;
             else h->M_uniform += 1;
             if (h->n_departures < c.hist_cap) { c.delays[h->n_departures] = delay; c.service[h->n_departures] = service_time; }
@@ -1145,7 +1145,7 @@ NB_FN1 void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:45
     h->valid_CE_control = 1;
     int valid_control = 1;
     int NPDCCH_sf = nb_npdcch_sf_per_ce[CE_level];
-    if (!(RAR_ues[CE_level] > 0) || NPDCCH_sf > h->NPDCCH_sf_left || c.conf->ce_mcs_automatic) {
+    if (!(RAR_ues[CE_level] > 0) || NPDCCH_sf > h->NPDCCH_sf_left || c.conf.ce_mcs_automatic) {
         int order[3] = { 0, 1, 2 };                            /* stable descending sort by list value */
         NB_NOUNROLL
         for (int x = 1; x < 3; ++x)
@@ -1165,7 +1165,7 @@ NB_FN1 void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:45
     }
     if (!valid_control) { nbc_schedule_NPDCCH(c, h->NPDCCH_sf_left); return; }
     int N_sc = P.N_sc;
-    if (c.conf->ce_mcs_automatic) { I_tbs = 2; N_ru = 1; N_rep = h->msg3_nrep[CE_level]; }
+    if (c.conf.ce_mcs_automatic) { I_tbs = 2; N_ru = 1; N_rep = h->msg3_nrep[CE_level]; }
     int reference_time = h->time + NPDCCH_sf;
     int n_sf = 0;
     int t_ul_end = nbc_node_allocate(c, P.carrier, reference_time, P.delay, N_sc, N_ru, N_rep, &N_sc, &n_sf);
@@ -1220,7 +1220,7 @@ NB_FN1 void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:58
     int CE_level = u->CE_level, new_data = u->new_data;
     int I_tbs, N_rep, N_ru, tbs;
     if (!new_data) { I_tbs = u->I_tbs; N_rep = u->N_rep; N_ru = u->N_ru; tbs = u->tbs; }
-    else if (c.conf->mcs_automatic) {
+    else if (c.conf.mcs_automatic) {
         int li = (int)NB_RINT(NB_MUL(u->loss, 10.0));
         if (li < 1214) li = 1214;
         if (li > 1713) { NB_FAULT(c, NBIOT_FAULT_MCS_KEY); return; }
@@ -1234,7 +1234,7 @@ NB_FN1 void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:58
         N_rep = P.N_rep; I_tbs = P.I_tbs;
         int row = nb_itbs_to_row[I_tbs];
         int p = 7; for (int i = 0; i < 8; ++i) if (nb_tbs_table[row][i] >= u->buffer) { p = i; break; }
-        if (c.conf->tx_all_buffer) { tbs = nb_tbs_table[row][p]; N_ru = nb_n_ru_list[p]; }
+        if (c.conf.tx_all_buffer) { tbs = nb_tbs_table[row][p]; N_ru = nb_n_ru_list[p]; }
         else {
             int I_N_ru = P.N_ru & 7;
             if (p < I_N_ru) { N_ru = nb_n_ru_list[p]; tbs = nb_tbs_table[row][p]; }
@@ -1387,7 +1387,7 @@ NB_DEV double nbc_reward(NbCtx &c)                               /* perf_monitor
 {
     NbHdr *h = nbc_hdr(c);
     int n = h->n_rx;
-    switch (c.conf->reward_criteria) {
+    switch (c.conf.reward_criteria) {
     case NB_RW_THROUGHPUT: return (double)h->thr_count;
     case NB_RW_AVERAGE_DELAY: return NB_DIV(NB_MUL(-1.0, h->rx_sum), (double)(n > 1 ? n : 1));
     case NB_RW_ACCUMULATED_DELAY: return NB_MUL(-1.0, h->rx_sum);
@@ -1574,9 +1574,9 @@ NB_FN void nbc_reset(NbCtx &c)
     h->ue_connections = 0; h->av_delay = 0.0; h->msg3_resources = 0; h->NPUSCH_resources = 0; h->NPRACH_resources = 0;
     nbc_clear_info(c);
     /* ue_generator.reset (ue_generator.py:38-42) */
-    double ratio = c.conf->ratio < 1.0 ? c.conf->ratio : 1.0;
-    h->M_uniform = (int)NB_RINT(NB_MUL((double)c.conf->M, ratio));
-    h->M_beta = c.conf->M - h->M_uniform; h->M_beta_max = h->M_beta; h->gen_t = 0;
+    double ratio = c.conf.ratio < 1.0 ? c.conf.ratio : 1.0;
+    h->M_uniform = (int)NB_RINT(NB_MUL((double)c.conf.M, ratio));
+    h->M_beta = c.conf.M - h->M_uniform; h->M_beta_max = h->M_beta; h->gen_t = 0;
     /* access_procedure.reset (access_procedure.py:28-35) */
     h->probability_anchor = 0.0;
     NB_NOUNROLL

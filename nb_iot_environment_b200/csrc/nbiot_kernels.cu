@@ -92,7 +92,7 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
     c.service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
     c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
     c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
-    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = A.conf; c.ctrl = s_ctrl;
+    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = *A.conf; c.ctrl = s_ctrl;
     c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
     c.evlog = i == 0 ? A.evlog : nullptr; c.evlog_cap = A.evlog_cap;
 }
