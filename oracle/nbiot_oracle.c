@@ -1327,6 +1327,7 @@ typedef struct {
     const uint64_t *seeds; const uint8_t *actions;   /* [steps][n_inst][ext_k] or NULL */
     int n_inst, steps, until_time, first, stride;
     long long subframes, node_steps; double seconds;
+    nbiot_record_t *records;      /* optional [n_inst]: the last decision record of every cell */
 } BenchJob;
 
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
@@ -1356,6 +1357,7 @@ static void *bench_worker(void *arg)
                 ns += orc_ctrl_advance(cells[k], j->ctrl, acts[k], j->actions + ((size_t)s * j->n_inst + i) * j->ctrl->ext_k, -1, 1 << 30, &rec);
         else ns += orc_ctrl_advance(cells[k], j->ctrl, acts[k], NULL, j->until_time, 1 << 30, &rec);
         sf += cells[k]->time - t_before;
+        if (j->records) j->records[i] = rec;
     }
     j->seconds = now_s() - t0;
     j->subframes = sf; j->node_steps = ns;
@@ -1366,14 +1368,15 @@ static void *bench_worker(void *arg)
 
 /* simulate n_inst cells on n_threads host threads (instances are dealt round-robin); returns the slowest
  * thread's wall-clock seconds inside the step loop and the total simulated subframes */
-double orc_bench(const nbiot_conf_t *conf, const nbiot_ctrl_t *ctrl, const uint16_t *lut2, const uint8_t *mcs, const uint64_t *seeds,
-                 int n_inst, const uint8_t *actions, int steps, int until_time, int n_threads, long long *subframes, long long *node_steps)
+double orc_bench_records(const nbiot_conf_t *conf, const nbiot_ctrl_t *ctrl, const uint16_t *lut2, const uint8_t *mcs, const uint64_t *seeds,
+                         int n_inst, const uint8_t *actions, int steps, int until_time, int n_threads, long long *subframes, long long *node_steps,
+                         nbiot_record_t *records)
 {
     if (n_threads < 1) n_threads = 1;
     BenchJob *jobs = calloc((size_t)n_threads, sizeof(BenchJob));
     pthread_t *th = malloc(sizeof(pthread_t) * (size_t)n_threads);
     for (int t = 0; t < n_threads; ++t) {
-        BenchJob j = { conf, ctrl, lut2, mcs, seeds, actions, n_inst, steps, until_time, t, n_threads, 0, 0, 0.0 };
+        BenchJob j = { conf, ctrl, lut2, mcs, seeds, actions, n_inst, steps, until_time, t, n_threads, 0, 0, 0.0, records };
         jobs[t] = j;
         pthread_create(&th[t], NULL, bench_worker, &jobs[t]);
     }
@@ -1387,6 +1390,10 @@ double orc_bench(const nbiot_conf_t *conf, const nbiot_ctrl_t *ctrl, const uint1
     free(jobs); free(th);
     return worst;
 }
+
+double orc_bench(const nbiot_conf_t *conf, const nbiot_ctrl_t *ctrl, const uint16_t *lut2, const uint8_t *mcs, const uint64_t *seeds,
+                 int n_inst, const uint8_t *actions, int steps, int until_time, int n_threads, long long *subframes, long long *node_steps)
+{ return orc_bench_records(conf, ctrl, lut2, mcs, seeds, n_inst, actions, steps, until_time, n_threads, subframes, node_steps, NULL); }
 
 /* host twins of the random stream, for the Python shim that drives the reference */
 double orc_rng_u01(uint64_t seed, uint64_t ctr, uint32_t stream) { return nb_rng_u01(seed, ctr, stream); }

@@ -44,6 +44,8 @@ def lib():
         L.orc_rng_pair.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p]
         L.orc_bench.restype = ctypes.c_double
         L.orc_bench.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_bench_records.restype = ctypes.c_double
+        L.orc_bench_records.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         assert L.orc_record_size() == RECORD_DTYPE.itemsize
         assert L.orc_conf_size() == ctypes.sizeof(NbiotConf)
         _LIB = L
@@ -132,3 +134,21 @@ def bench(conf, ctrl, seeds, actions=None, steps=0, until_time=-1, n_threads=1):
     sec = L.orc_bench(ctypes.byref(conf), ctypes.byref(ctrl), lut.ctypes.data, mcs.ctypes.data, seeds.ctypes.data, len(seeds), ap,
                       int(steps), int(until_time), int(n_threads), ctypes.byref(sf), ctypes.byref(ns))
     return sec, sf.value, ns.value
+
+
+def run_batch(conf, ctrl, seeds, actions=None, steps=0, until_time=-1, n_threads=None):
+    """Simulate a batch on host threads and return the last decision record of every cell (RECORD_DTYPE[n])."""
+    import os
+    L = lib()
+    lut, mcs = tables()
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    recs = np.zeros(len(seeds), dtype=RECORD_DTYPE)
+    sf, ns = ctypes.c_longlong(), ctypes.c_longlong()
+    ap = None
+    if actions is not None:
+        actions = np.ascontiguousarray(actions, dtype=np.uint8)
+        assert actions.shape == (steps, len(seeds), ctrl.ext_k)
+        ap = actions.ctypes.data
+    L.orc_bench_records(ctypes.byref(conf), ctypes.byref(ctrl), lut.ctypes.data, mcs.ctypes.data, seeds.ctypes.data, len(seeds), ap,
+                        int(steps), int(until_time), int(n_threads or os.cpu_count() or 1), ctypes.byref(sf), ctypes.byref(ns), recs.ctypes.data)
+    return recs

@@ -9,7 +9,7 @@ import numpy as np
 from nb_iot_environment_b200.record import RECORD_DTYPE, FLOAT_FIELDS, INT_FIELDS, NON_PARITY_FIELDS
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))) if not n.startswith('wrappers_'))
+CASES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))) if not n.startswith(('wrappers_', 'long_')))
 
 # float fields are compared to the reference's numpy/libm/scipy arithmetic: nbiot_math.h agrees to ~1e-15,
 # the contract (BASELINE.json north_star) is 1e-5 relative

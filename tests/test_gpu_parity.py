@@ -172,6 +172,14 @@ def test_batch_independence_and_determinism_at_scale():
     recs, st = out[0][2], out[0][3]
     assert not (recs['fault'] & 0x1F).any() and (recs['time'] == 9000).all()
     assert st['subframes'] == 9000 * N
+    # every one of the 4096 cells against the CPU oracle (threaded C driver), bit for bit
+    from oracle import oracle_py
+    from nb_iot_environment_b200.controller import ControllerTables
+    from nb_iot_environment_b200.record import make_conf
+    orecs = oracle_py.run_batch(make_conf(conf, ue_cap=512, grid_w=2048), ControllerTables(NPRACH_AGENTS, 3).build(), np.arange(N),
+                                actions=np.stack(acts), steps=len(acts))
+    bad = [i for i in range(N) if record_diff(orecs[i], recs[i], rtol=0.0)]
+    assert not bad, f'{len(bad)} of {N} cells differ from the oracle, first: {bad[:5]}'
     for i in (0, 1, 777, 4095):
         c = OracleController(conf, i, agents_conf=NPRACH_AGENTS, ext_agent=3)
         c.reset()
