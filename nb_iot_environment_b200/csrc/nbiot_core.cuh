@@ -316,8 +316,9 @@ NB_FN void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
 
 NB_DEV void nbc_erase_past_sf(NbCtx &c, int t)                   /* carrier.py:481-489 */
 {
-    if (t > nbc_hdr(c)->t_now) nbc_hdr(c)->t_now = t;
-    nbc_extend_lookahead(c, t + NB_HORIZON);
+    NbHdr *h = nbc_hdr(c);
+    if (t > h->t_now) h->t_now = t;
+    if (t + NB_HORIZON > h->t_ahead) nbc_extend_lookahead(c, t + NB_HORIZON);   /* the usual case needs no call */
 }
 
 /* Carrier.allocate_resources (carrier.py:556-605): first fit over delays x carriers x offsets */
@@ -329,21 +330,26 @@ NB_FNM4 int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int
     NB_NOUNROLL
     for (int d = delay; d <= 64; d *= 2) {
         int new_t_ahead = t + d + N_sf;
-        nbc_extend_lookahead(c, new_t_ahead);
-        if (NB_FATAL(c)) return 0;
+        if (new_t_ahead > h->t_ahead) {
+            nbc_extend_lookahead(c, new_t_ahead);
+            if (NB_FATAL(c)) return 0;
+        }
         int from = h->t_now + d;
         NB_NOUNROLL
         for (int ci = 0; ci < c.C; ++ci) {
             int cc = ci == 0 ? carrier_id : (carrier_id == 0 ? 1 : 0);
             uint32_t busy = nbc_grid_busy(c, cc, from, N_sf);
-            uint32_t m0 = (1u << N_sc) - 1u;
-            NB_NOUNROLL
-            for (int off = 0; off < 12; off += N_sc) {
-                uint32_t m = m0 << off;
-                if (!(busy & m)) {
-                    nbc_grid_or(c, cc, from, N_sf, m);
-                    return new_t_ahead;
-                }
+            /* first free aligned group of N_sc subcarriers (offsets_per_sc, carrier.py:29-34): fold the
+             * group's bits onto its lowest one, then take the lowest clear group bit */
+            uint32_t fold = busy;
+            if (N_sc >= 3) fold |= (busy >> 1) | (busy >> 2);
+            if (N_sc >= 6) fold |= fold >> 3;
+            if (N_sc == 12) fold |= fold >> 6;
+            uint32_t heads = N_sc == 1 ? 0xFFFu : N_sc == 3 ? 0x249u : N_sc == 6 ? 0x041u : 0x001u;
+            uint32_t pick = ~fold & heads;
+            if (pick) {
+                nbc_grid_or(c, cc, from, N_sf, ((1u << N_sc) - 1u) << (nbw_ffs(pick) - 1));
+                return new_t_ahead;
             }
         }
     }
@@ -895,10 +901,13 @@ NB_FNM4 void nbc_conn_insert(NbCtx &c, int slot)
     h->conn_order += 1;
     nbw_run([&]() -> int {
         /* stable sort position: after every entry whose key is <= k1 (the new stamp is the largest) */
-        int cnt = 0;
-        NB_NOUNROLL
-        for (int i = nbw_lane(); i < n; i += NB_LANES) cnt += Q[i].k1 <= k1;
-        int pos = nbw_add_i32(cnt);
+        int pos = n;
+        if (n > 0 && Q[n - 1].k1 > k1) {                       /* not the usual append: count the keys <= k1 */
+            int cnt = 0;
+            NB_NOUNROLL
+            for (int i = nbw_lane(); i < n; i += NB_LANES) cnt += Q[i].k1 <= k1;
+            pos = nbw_add_i32(cnt);
+        }
         NB_NOUNROLL
         for (int hi = n; hi > pos; hi -= NB_LANES) {
             int i = hi - 1 - nbw_lane();

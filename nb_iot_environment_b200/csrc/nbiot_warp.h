@@ -145,24 +145,39 @@ NB_DEV uint64_t nbw_shfl64(uint64_t v, int src)
 
 NB_DEV uint64_t nbw_min_u64(uint64_t v)
 {
+#if defined(__CUDA_ARCH__)
+    /* two redux.sync steps: the smallest high word, then the smallest low word among its holders */
+    uint32_t hi = (uint32_t)(v >> 32), mh = __reduce_min_sync(NB_FULL, hi);
+    uint32_t ml = __reduce_min_sync(NB_FULL, hi == mh ? (uint32_t)v : 0xFFFFFFFFu);
+    return ((uint64_t)mh << 32) | ml;
+#else
     for (int m = NB_LANES / 2; m > 0; m >>= 1) {
         uint32_t lo = nbw_shfl_xor((uint32_t)v, m), hi = nbw_shfl_xor((uint32_t)(v >> 32), m);
         uint64_t o = ((uint64_t)hi << 32) | lo;
         v = o < v ? o : v;
     }
     return v;
+#endif
 }
 
 NB_DEV uint32_t nbw_or_u32(uint32_t v)
 {
+#if defined(__CUDA_ARCH__)
+    return __reduce_or_sync(NB_FULL, v);
+#else
     for (int m = NB_LANES / 2; m > 0; m >>= 1) v |= nbw_shfl_xor(v, m);
     return v;
+#endif
 }
 
 NB_DEV int32_t nbw_add_i32(int32_t v)
 {
+#if defined(__CUDA_ARCH__)
+    return __reduce_add_sync(NB_FULL, v);
+#else
     for (int m = NB_LANES / 2; m > 0; m >>= 1) v += (int32_t)nbw_shfl_xor((uint32_t)v, m);
     return v;
+#endif
 }
 
 #endif /* NBIOT_WARP_H */
