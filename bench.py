@@ -176,9 +176,13 @@ def main():
     N = args.instances
     from nb_iot_environment_b200.sharding import shard_seeds, allreduce_stats
     seeds = shard_seeds(N * world, rank, world)              # instance g of the job has Philox key g on any number of GPUs
+    if os.environ.get('NBIOT_BENCH_SAME'):                    # measurement knob: identical cells (upper bound of code sharing between warps)
+        seeds = np.zeros_like(np.asarray(seeds))
     env = BatchedNBIoTEnv(CONF, agents_conf=AGENTS, ext_agent=EXT_AGENT, num_envs=N, seeds=seeds, device=local_rank, **CAPS)
     total_steps = W + 2 * K
     acts_host = ext_actions(total_steps, N, seed=1234 + rank)
+    if os.environ.get('NBIOT_BENCH_SAME'):
+        acts_host[:] = acts_host[:, :1]
     acts_pinned = torch.from_numpy(acts_host).pin_memory()
     acts_dev = acts_pinned.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
@@ -283,7 +287,7 @@ def main():
                      'note': 'algorithmic bytes of SURVEY 8(d) (a per-subframe UE scan); the kernel skips idle subframes, so its DRAM traffic is far below this'},
         'wall_s_timed_region': wall1,
     }
-    if world == 1:
+    if world == 1 and not os.environ.get('NBIOT_BENCH_NO_CPU'):          # (measurement sweeps skip the CPU leg)
         r = cpu_reference_arm(40, 0, cells_per_step=64 * (os.cpu_count() or 1))     # ~15 CPU-seconds of work
         line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
     sys.stdout.flush()

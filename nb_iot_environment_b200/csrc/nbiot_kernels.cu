@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "nbiot.h"
@@ -281,6 +282,7 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nbiot_sim_kernel, NB_WPB * 32, h->smem_bytes));
     if (per_sm < 1) per_sm = 1;
+    if (const char *e = getenv("NBIOT_MAX_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   /* measurement knob */
     int need = (n_inst + NB_WPB - 1) / NB_WPB;
     int cap = prop.multiProcessorCount * per_sm;
     h->blocks = need < cap ? need : cap;
