@@ -13,7 +13,9 @@ LIB_PATH = os.environ.get('NBIOT_LIB') or os.path.join(_HERE, 'libnbiot_b200.so'
 SYMBOLS = ['nbiot_abi_version', 'nbiot_last_error', 'nbiot_state_bytes', 'nbiot_hdr_bytes', 'nbiot_create', 'nbiot_destroy',
            'nbiot_set_controller', 'nbiot_reset', 'nbiot_advance', 'nbiot_advance_masked', 'nbiot_records_ptr', 'nbiot_hist_ptrs', 'nbiot_gather_obs',
            'nbiot_reduce_stats', 'nbiot_step_host', 'nbiot_set_event_log', 'nbiot_launch_count', 'nbiot_launch_geometry',
-           'nbiot_rng_u01', 'nbiot_rng_pair', 'nbiot_rng_normal', 'nbiot_rng_bounded']
+           'nbiot_rng_u01', 'nbiot_rng_pair', 'nbiot_rng_normal', 'nbiot_rng_bounded',
+           # include/nbiot_agent.h
+           'nbiot_mb_agent_create', 'nbiot_mb_agent_destroy', 'nbiot_mb_agent_act', 'nbiot_mb_agent_faults']
 
 N_STATS = 24
 STAT_NAMES = {0: 'ue_arrivals', 3: 'ue_departures', 6: 'backoffs', 9: 'ue_connections', 10: 'error_count', 11: 'attempts_count',
@@ -25,6 +27,17 @@ N_SUM_STATS = 20      # entries [0, 20) are sums, the rest maxima
 class ObsItem(ctypes.Structure):
     _fields_ = [('offset', ctypes.c_int32), ('kind', ctypes.c_int32), ('length', ctypes.c_int32),
                 ('state_mask', ctypes.c_uint32), ('norm', ctypes.c_double)]
+
+
+class MbTables(ctypes.Structure):
+    """nbiot_mb_tables_t (include/nbiot_agent.h)"""
+    _fields_ = [('ml_est', ctypes.c_void_p), ('cfg_rate', ctypes.c_void_p), ('cfg_conf', ctypes.c_void_p), ('cfg_n', ctypes.c_int32 * 3),
+                ('m3_det', ctypes.c_double * 15), ('m3_ce', ctypes.c_uint8 * 15), ('pad0', ctypes.c_uint8), ('rate_conf', ctypes.c_void_p),
+                ('min_value', ctypes.c_double), ('max_value', ctypes.c_double), ('step', ctypes.c_double),
+                ('period_list', ctypes.c_int32 * 6), ('th_default', ctypes.c_uint8 * 2), ('pad1', ctypes.c_uint8 * 6)]
+
+
+MB_STATE_BYTES = 56       # sizeof(nbiot_mb_state_t)
 
 
 class NbiotError(RuntimeError):
@@ -70,6 +83,10 @@ def load():
     L.nbiot_rng_bounded.restype = u64
     L.nbiot_rng_bounded.argtypes = [u64, u64, u32, u64]
     L.nbiot_rng_pair.argtypes = [u64, u64, u32, vp]
+    L.nbiot_mb_agent_create.argtypes = [vp, ctypes.POINTER(MbTables), i32, i32, ctypes.c_double, vp, vp, ctypes.POINTER(vp)]
+    L.nbiot_mb_agent_destroy.argtypes = [vp]
+    L.nbiot_mb_agent_act.argtypes = [vp, vp, vp, vp, vp]
+    L.nbiot_mb_agent_faults.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
     if L.nbiot_abi_version() != 1:
         raise NbiotError('libnbiot_b200.so ABI version mismatch: rebuild')
     _lib = L

@@ -461,3 +461,5 @@ double nbiot_rng_normal(uint64_t seed, uint64_t ctr, uint32_t stream) { return n
 uint64_t nbiot_rng_bounded(uint64_t seed, uint64_t ctr, uint32_t stream, uint64_t n) { return nb_rng_bounded(seed, ctr, stream, n); }
 
 }   /* extern "C" */
+
+#include "nbiot_agent_impl.cuh"

@@ -109,6 +109,10 @@ class _Wrapper:
     def reset(self, seed=None, options=None):
         return self.env.reset()
 
+    def _div(self, x, d):
+        """x / d as IEEE division (a CUDA tensor divided by a Python scalar is multiplied by the rounded reciprocal)"""
+        return x / torch.full_like(x, float(d))
+
     def _actions(self, a, k):
         return torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(self.device).long().reshape(self.num_envs, k)
 
@@ -141,7 +145,7 @@ class NPRACHWrapper(_Wrapper):
         transformed = torch.cat([self._pair_idx[a[:, 0]], a[:, 1:]], dim=1)
         applied = torch.where(valid[:, None], transformed, self.action)
         obs, reward, terminated, truncated, infos = self.env.step(applied)
-        reward = torch.where(valid, reward / self.norm, torch.full_like(reward, -1.0))
+        reward = torch.where(valid, self._div(reward, self.norm), torch.full_like(reward, -1.0))
         if not self.default_action:
             self.action = applied
         self.last_valid = valid
@@ -217,3 +221,51 @@ class RARWrapper(_Wrapper):
         reward = torch.where(f('valid_CE_control') == 0, torch.full_like(reward, -1.0), reward)
         self.n_steps += 1
         return obs, reward, terminated, truncated, infos
+
+
+class NPRACHAgentWrapper(_Wrapper):
+    """reference NPRACH_agent_wrapper (wrappers.py:257-318): the learner only picks the margin (beta) of the model-based
+    configurator; the agent (mb_agent.BatchedNPRACHAgent) turns it into the 8 NPRACH action items on the device.
+    Observation = the selected items of the environment's observation followed by the last `obs_window` arrival-rate
+    estimates of the agent; reward = environment reward / norm."""
+
+    def __init__(self, env, agent, bounds=(1.4, 3.4), reduced_observation=True, discrete=True, n_actions=30, obs_items=(11, 12), obs_window=1, norm=100):
+        super().__init__(env)
+        self.agent = agent
+        self.samples = agent.samples
+        self.discrete = discrete
+        self.bounds = bounds
+        if discrete:
+            self.action_values = torch.from_numpy(np.linspace(bounds[0], bounds[1], n_actions)).to(self.device)   # wrappers.py:266
+        self.reduced_observation = reduced_observation
+        self.obs_items = torch.as_tensor(list(obs_items), device=self.device, dtype=torch.long)
+        self.obs_window = obs_window
+        self.arrival_history = torch.zeros((self.num_envs, obs_window), dtype=torch.float64, device=self.device)   # deque([0] * obs_window)
+        self.norm = norm
+        self.n = 0
+
+    def _reduce(self, obs):
+        if not self.reduced_observation:
+            return obs
+        return torch.cat([obs[:, self.obs_items], self.arrival_history], dim=1)
+
+    def reset(self, seed=None, options=None):
+        obs, infos = self.env.reset()
+        self.obs = self._reduce(obs)
+        return self.obs, infos
+
+    def step(self, action):
+        self.n += 1
+        if self.discrete:
+            margin = self.action_values[self._actions(action, 1)[:, 0]]
+        else:
+            margin = torch.as_tensor(action, dtype=torch.float64, device=self.device).reshape(self.num_envs, -1)[:, 0]
+        self.agent.set_parameter(margin)
+        conf = self.agent.get_action()
+        obs, reward, terminated, truncated, infos = self.env.step(conf)
+        self.conf = conf
+        self.r = self._div(reward, self.norm)
+        if self.reduced_observation:
+            self.arrival_history = torch.cat([self.arrival_history[:, 1:], self.agent.lambda_estimate[:, None].clone()], dim=1)
+        self.obs = self._reduce(obs)
+        return self.obs, self.r, terminated, truncated, infos

@@ -21,8 +21,8 @@ def cuda_lib():
 
 def test_every_declared_symbol_is_exported(cuda_lib):
     from nb_iot_environment_b200 import _cabi
-    text = open(os.path.join(ROOT, 'include', 'nbiot.h')).read()
-    declared = sorted(set(re.findall(r'\b(nbiot_[a-z0-9_]+)\s*\(', text)))
+    text = open(os.path.join(ROOT, 'include', 'nbiot.h')).read() + open(os.path.join(ROOT, 'include', 'nbiot_agent.h')).read()
+    declared = sorted(set(re.findall(r'^(?:int|size_t|double|void|uint64_t|long long|const char \*)\s*\*?(nbiot_[a-z0-9_]+)\s*\(', text, flags=re.M)))
     assert declared == sorted(_cabi.SYMBOLS)
     for name in declared:
         assert hasattr(cuda_lib, name), name
@@ -36,6 +36,8 @@ def test_struct_sizes_match(cuda_lib, oracle_lib):
     assert oracle_lib.orc_conf_size() == ctypes.sizeof(NbiotConf)
     assert ctypes.sizeof(NbiotCtrl) == 8 + 24 + 24 + 96 + 24
     assert ctypes.sizeof(ObsItem) == 24
+    from nb_iot_environment_b200._cabi import MbTables, MB_STATE_BYTES
+    assert ctypes.sizeof(MbTables) == 240 and MB_STATE_BYTES == 56          # nbiot_mb_tables_t / nbiot_mb_state_t (include/nbiot_agent.h)
     assert cuda_lib.nbiot_hdr_bytes() % 16 == 0
 
 

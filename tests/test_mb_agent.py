@@ -60,3 +60,82 @@ def test_agent_tables_are_consistent():
     for ce in range(3):
         n = int(t['cfg_n'][ce])
         assert (np.diff(t['cfg_rate'][ce, :n]) >= 0).all() and np.isinf(t['cfg_rate'][ce, n:]).all()
+
+
+# ------------------------------------------------------------------ GPU: the CUDA agent through the C ABI
+def _write_records(env, rows):
+    """overwrite the decision records of the batch with the given structured rows (the state buffer is caller-owned)"""
+    import torch
+    from nb_iot_environment_b200.record import RECORD_DTYPE
+    raw = torch.from_numpy(np.frombuffer(rows.tobytes(), dtype=np.uint8).copy())
+    env.state[env._rec_off:env._rec_off + rows.size * RECORD_DTYPE.itemsize] = raw.to(env.state.device)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('no_th', [False, True])
+def test_agent_kernel_matches_reference_traces_and_oracle(no_th):
+    """every get_action of the golden traces, replayed through nbiot_mb_agent_act: actions, arrival estimate, sample
+    counter and msg3 detection estimate bit-identical to the reference agent"""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from nb_iot_environment_b200.mb_agent import BatchedNPRACHAgent
+    from nb_iot_environment_b200.record import RECORD_DTYPE
+    z, meta = _golden()
+    pref = [p for p, f in _prefixes(meta) if f == no_th]
+    N = len(pref)
+    env = BatchedNBIoTEnv({'ratio': 1.0, 'M': 1000, 'buffer_range': [100, 600], 'reward_criteria': 'throughput'}, num_envs=N, seeds=list(range(N)),
+                          ue_cap=64, grid_w=256, hist_cap=64)
+    env.reset()
+    agent = BatchedNPRACHAgent(env, no_th=no_th)
+    for s in range(40):
+        rows = np.zeros(N, dtype=RECORD_DTYPE)
+        for i, p in enumerate(pref):
+            rows[i]['state'] = 1
+            rows[i]['det_hist'] = z[f'{p}_det'][s]; rows[i]['col_hist'] = z[f'{p}_col'][s]; rows[i]['n_occ'] = z[f'{p}_nocc'][s]
+            rows[i]['distribution'] = z[f'{p}_dist'][s]; rows[i]['n_incoming'] = z[f'{p}_ninc'][s]
+        _write_records(env, rows)
+        agent.set_parameter(np.asarray([z[f'{p}_margin'][s] for p in pref]))
+        act = agent.get_action().cpu().numpy()
+        lam, k, m3 = agent.lambda_estimate.cpu().numpy(), agent.k.cpu().numpy(), agent.msg3_detection.cpu().numpy()
+        for i, p in enumerate(pref):
+            assert act[i].tolist() == z[f'{p}_out'][s].tolist(), (p, s)
+            assert lam[i] == z[f'{p}_lam'][s] and k[i] == z[f'{p}_k'][s] and m3[i].tolist() == z[f'{p}_m3'][s].tolist(), (p, s)
+    # a cell that is not at an NPRACH_update decision is left alone
+    rows['state'] = 0
+    _write_records(env, rows)
+    before = agent.state.clone()
+    agent.get_action()
+    assert torch.equal(before, agent.state) and agent.faults() == 0
+    agent.close(); env.close()
+
+
+@pytest.mark.gpu
+def test_agent_closed_loop_on_device_matches_reference():
+    """evaluate_MBRL.py set-up entirely on the device (environment -> records -> agent -> actions -> environment) against the
+    reference environment + agent + NPRACH_agent_wrapper: same configurations, estimates, observations, rewards, samples"""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from test_gpu_parity import NPRACH_AGENTS
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from nb_iot_environment_b200.mb_agent import BatchedNPRACHAgent
+    from nb_iot_environment_b200.wrappers import NPRACHAgentWrapper
+    z, meta = _golden()
+    for ci, m in enumerate(meta['loops']):
+        p = f'loop_{ci}'
+        env = BatchedNBIoTEnv(m['conf'], agents_conf=NPRACH_AGENTS, ext_agent=3, num_envs=2, seeds=[m['seed'], m['seed']], ue_cap=1000, grid_w=2048, hist_cap=1024)
+        agent = BatchedNPRACHAgent(env, no_th=m['no_th'])
+        w = NPRACHAgentWrapper(env, agent, n_actions=26, obs_items=[0, 1, 2, 3, 4, 5, 9, 10, 11, 12], obs_window=1, bounds=[0.3, 2.0], discrete=True, norm=100)
+        obs, _ = w.reset()
+        np.testing.assert_allclose(obs.cpu().numpy()[0], z[f'{p}_obs0'], rtol=1e-9, atol=1e-12)
+        for s in range(m['steps']):
+            a = int(z[f'{p}_act'][s])
+            obs, r, _, _, _ = w.step(np.asarray([a, a]))
+            conf = w.conf.cpu().numpy()
+            assert conf[0].tolist() == z[f'{p}_out'][s].tolist() and conf[1].tolist() == conf[0].tolist(), (p, s)
+            assert agent.lambda_estimate.cpu().numpy()[0] == z[f'{p}_lam'][s], (p, s)
+            assert r.cpu().numpy()[0] == z[f'{p}_rew'][s], (p, s)
+            np.testing.assert_allclose(obs.cpu().numpy()[0], z[f'{p}_obs'][s], rtol=1e-9, atol=1e-12, err_msg=f'{p} step {s}')
+        for name, key in (('departures', 's_departures'), ('NPRACH_occupation', 's_occupation'), ('service_times', 's_service'), ('beta', 's_beta')):
+            got = np.asarray([x.cpu().numpy()[0] for x in agent.samples[name]])
+            np.testing.assert_allclose(got, z[f'{p}_{key}'], rtol=1e-9, atol=1e-12, err_msg=f'{p} samples {name}')
+        assert agent.faults() == 0
+        agent.close(); env.close()
