@@ -102,6 +102,16 @@ int nbiot_advance_masked(nbiot_handle_t *h, const uint8_t *ext_actions_dev, cons
 int nbiot_records_ptr(nbiot_handle_t *h, void **records_dev);
 int nbiot_hist_ptrs(nbiot_handle_t *h, void **incoming_dev, void **delays_dev, void **service_dev, int *hist_cap);
 
+/* conf.stat_cap > 0 (conf['statistics']): the per-departure histories of PerfMonitor (perf_monitor.py:61-84, :161-171; the arrays
+ * experiments_RL.py:139-140 / experiments_MAMBRL.py:121-122 save) as rings in HBM.
+ * stat_dev = int32[n_inst][4][stat_cap]: 0 delay_history, 1 connection_history, 2 access_history, 3 acked bits (th_history = bits / delay);
+ * entry k of an instance is departure number (k + m * stat_cap) since reset -- nbiot_stat_counts gives the number recorded. */
+int nbiot_stat_ptrs(nbiot_handle_t *h, void **stat_dev, int *stat_cap);
+int nbiot_stat_counts(nbiot_handle_t *h, int32_t *counts_dev, void *stream);
+/* histogram of one history over ALL instances, on the device: hist_dev = int64[n_bins], bin b counts values in
+ * [b * bin_width, (b + 1) * bin_width), the last bin is open-ended (delay CDFs of a batch without a host round trip) */
+int nbiot_stat_histogram(nbiot_handle_t *h, int which, int bin_width, int n_bins, int64_t *hist_dev, void *stream);
+
 /* replaces Controller.get_obs (controller.py:105-120): obs_dev = double[n_inst][sum(length)],
  * reward_dev = double[n_inst] (either may be NULL) */
 int nbiot_gather_obs(nbiot_handle_t *h, const nbiot_obs_item_t *items, int n_items, double *obs_dev, double *reward_dev, void *stream);

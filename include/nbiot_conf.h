@@ -10,24 +10,38 @@
 
 #include <stdint.h>
 
-typedef struct nbiot_conf {
-    double ratio;             /* conf['ratio']: share of uniform (vs beta-burst) devices       */
-    double max_d;             /* conf['max_d'] cell range in km; <= 0 means default (10 km)    */
-    int32_t M;                /* conf['M']: devices per cell                                    */
-    int32_t buffer_lo;        /* conf['buffer_range'][0]                                        */
-    int32_t buffer_hi;        /* conf['buffer_range'][1]                                        */
-    int32_t reward_criteria;  /* NB_RW_* (conf['reward_criteria'])                             */
-    int32_t sort_by_loss;     /* conf['sort_criterium'] == 'loss' (default 't_connection')      */
-    int32_t sc_adjustment;    /* default 1 */
-    int32_t mcs_automatic;    /* default 1 */
-    int32_t ce_mcs_automatic; /* default 1 */
-    int32_t tx_all_buffer;    /* default 1 */
-    int32_t random_traffic;   /* conf['random'] */
-    int32_t n_carriers;       /* 1 or 2 (parameters.N_carriers) */
-    /* capacities (CUDA path only; the oracle grows its containers) */
-    int32_t ue_cap;           /* live-UE slots per instance (<= M suffices: closed population)  */
-    int32_t grid_w;           /* carrier look-ahead ring, columns, power of two                 */
+/* the fields every event handler may read: the simulation kernels keep a by-value copy of this prefix in shared memory */
+#define NBIOT_CONF_HOT_FIELDS \
+    double ratio;             /* conf['ratio']: share of uniform (vs beta-burst) devices       */ \
+    double max_d;             /* conf['max_d'] cell range in km; <= 0 means default (10 km)    */ \
+    int32_t M;                /* conf['M']: devices per cell                                    */ \
+    int32_t buffer_lo;        /* conf['buffer_range'][0]                                        */ \
+    int32_t buffer_hi;        /* conf['buffer_range'][1]                                        */ \
+    int32_t reward_criteria;  /* NB_RW_* (conf['reward_criteria'])                             */ \
+    int32_t sort_by_loss;     /* conf['sort_criterium'] == 'loss' (default 't_connection')      */ \
+    int32_t sc_adjustment;    /* default 1 */ \
+    int32_t mcs_automatic;    /* default 1 */ \
+    int32_t ce_mcs_automatic; /* default 1 */ \
+    int32_t tx_all_buffer;    /* default 1 */ \
+    int32_t random_traffic;   /* conf['random'] */ \
+    int32_t n_carriers;       /* 1 or 2 (parameters.N_carriers) */ \
+    /* capacities (CUDA path only; the oracle grows its containers) */ \
+    int32_t ue_cap;           /* live-UE slots per instance (<= M suffices: closed population)  */ \
+    int32_t grid_w;           /* carrier look-ahead ring, columns, power of two                 */ \
     int32_t hist_cap;         /* entries of incoming/delays/service_times kept per period       */
+
+typedef struct nbiot_conf_hot { NBIOT_CONF_HOT_FIELDS } nbiot_conf_hot_t;
+
+typedef struct nbiot_conf {
+    NBIOT_CONF_HOT_FIELDS
+    /* ---- read on rare paths only (arrivals, departures) ---- */
+    int32_t stat_cap;         /* conf['statistics']: entries of the per-departure histories kept per instance
+                                 (PerfMonitor.delay/connection/access/th_history, perf_monitor.py:61-84); 0 = off */
+    int32_t clustered;        /* conf['clustered'] (population.py:57-63, :75-101)               */
+    int32_t cluster_lo;       /* conf['cluster_ues'][0]                                         */
+    int32_t cluster_hi;       /* conf['cluster_ues'][1]                                         */
+    double cluster_prob;      /* conf['cluster_prob']                                           */
+    double cluster_range;     /* conf['cluster_range'] in km (divided by the cell range when used) */
 } nbiot_conf_t;
 
 #endif /* NBIOT_CONF_H */

@@ -205,6 +205,27 @@ NB_HD_CALL double nb_cos2pi(double u)
     }
 }
 
+/* sin(2 pi u), u in [0,1): the same reduction (clustered placement, population.py:90-96) */
+NB_HD_CALL double nb_sin2pi(double u)
+{
+    double t = NB_MUL(u, 4.0);
+    double qf = NB_FLOOR(t);
+    int q = (int)qf;
+    double f = NB_SUB(t, qf);
+    int swap = f > 0.5;
+    double g = swap ? NB_SUB(1.0, f) : f;
+    double y = NB_MUL(g, NB_PI_2);
+    double sn = nb_sin_k(y), cs = nb_cos_k(y);
+    double c = swap ? sn : cs;
+    double s = swap ? cs : sn;
+    switch (q & 3) {
+    case 0: return s;
+    case 1: return c;
+    case 2: return -s;
+    default: return -c;
+    }
+}
+
 /* atan(t), t >= 0 */
 NB_HD_CALL double nb_atan_pos(double t)
 {

@@ -50,8 +50,8 @@ struct __attribute__((aligned(16))) NbCtx {
     nbiot_record_t *rec;
     const uint16_t *lut2;
     const uint8_t *mcs;
-    nbiot_conf_t conf;        /* by value: one shared-memory load per use instead of a pointer chase into HBM */
-    const NbCtrlDev *ctrl;    /* controller tables (shared memory in the kernels) */
+    nbiot_conf_hot_t conf;    /* by value: one shared-memory load per use instead of a pointer chase into HBM */
+    const NbCtrlDev *ctrl;    /* controller tables: the first member of an NbCtaConst (shared memory in the kernels) */
     int32_t *evlog;           /* optional (t, type) pop log for debugging */
     int W, ue_cap, ra_cap, hist_cap, C, evlog_cap;
 };
@@ -62,6 +62,7 @@ struct __attribute__((aligned(16))) NbCtx {
 #define NB_ASSUME_SHARED(p) ((void)0)
 #endif
 NB_DEV NbHdr *nbc_hdr(NbCtx &c) { NbHdr *h = (NbHdr *)((char *)&c + sizeof(NbCtx)); NB_ASSUME_SHARED(h); return h; }
+NB_DEV const NbColdConf *nbc_cold(NbCtx &c) { return &((const NbCtaConst *)c.ctrl)->cold; }
 NB_DEV uint16_t *nbc_grid(NbCtx &c) { return (uint16_t *)((char *)nbc_hdr(c) + sizeof(NbHdr)); }
 #define NB_WARP_BYTES(C, W) (sizeof(NbCtx) + sizeof(NbHdr) + (size_t)(C) * (size_t)(W) * 2u)
 
@@ -554,15 +555,15 @@ NB_DEV double nbc_find_y(double x1, double y1, double x2, double y2, double x)  
 #define NB_S32 0.8660254037844386
 
 /* Channel.set_xy_loss / generate_xy / location / antenna_pattern (channel.py:100-118, :134-151) */
-NB_FN1S double nbc_place_ue(NbCtx &c)
+NB_FNM4 double nbc_place_ue(NbCtx &c, double x, double y, double *xy_out)
 {
-    double x, y;
-    for (;;) {
+    if (x < 0) for (;;) {                        /* generate_xy; also when a clustered x falls left of the cell (channel.py:143-144) */
         nb_rng_pair(nbc_hdr(c)->seed, nbc_hdr(c)->draws++, NBIOT_STREAM_ENV, &x, &y);
         int in_cell = (y > nbc_find_y(0, NB_S34, 0.25, 0, x)) && (y > nbc_find_y(0.75, 0, 1, NB_S34, x)) &&
                       (y < nbc_find_y(0, NB_S34, 0.25, NB_S32, x)) && (y < nbc_find_y(0.75, NB_S32, 1, NB_S34, x)) && (y < NB_S32);
         if (in_cell) break;
     }
+    if (xy_out) { xy_out[0] = x; xy_out[1] = y; }
     double x_t = NB_SUB(x, 0.25);
     double distance = NB_SQRT(NB_ADD(NB_MUL(x_t, x_t), NB_MUL(y, y)));
     double cos_theta = NB_DIV(x_t, distance);
@@ -575,6 +576,25 @@ NB_FN1S double nbc_place_ue(NbCtx &c)
     double L = NB_ADD(128.1, NB_MUL(37.6, nb_log10(R)));
     if (!(L > 0.0)) L = 0.0;
     return NB_ADD(NB_SUB(L, G), 0.0);
+}
+
+/* Population.clustered_ue_generation (population.py:75-101): out of line, only clustered cells come here */
+NB_FN double nbc_place_clustered(NbCtx &c)
+{
+    const NbColdConf *cold = nbc_cold(c);
+    double p = nbc_u01(c), xy[2];
+    if (!(p < cold->cluster_prob)) return nbc_place_ue(c, -1.0, -1.0, nullptr);
+    if (!c.occ->cluster_count) {                 /* a new cluster: its first UE is placed anywhere and becomes the centre */
+        double loss = nbc_place_ue(c, -1.0, -1.0, xy);
+        c.occ->cluster_cx = xy[0]; c.occ->cluster_cy = xy[1];
+        c.occ->cluster_count = nbc_integers(c, cold->cluster_lo, cold->cluster_hi);
+        return loss;
+    }
+    double ua = nbc_u01(c);                      /* angle = uniform(0, 2 pi); cos / sin taken at 2 pi u */
+    double radius = NB_MUL(cold->cluster_range, NB_SQRT(NB_ADD(0.0, NB_MUL(1.0, nbc_u01(c)))));
+    double x = NB_ADD(NB_MUL(radius, nb_cos2pi(ua)), c.occ->cluster_cx), y = NB_ADD(NB_MUL(radius, nb_sin2pi(ua)), c.occ->cluster_cy);
+    c.occ->cluster_count -= 1;
+    return nbc_place_ue(c, x, y, nullptr);
 }
 
 /* UEGenerator.generate_arrivals (ue_generator.py:54-81) + Population.get_new_arrivals (population.py:103-132) */
@@ -607,7 +627,7 @@ NB_FN1 void nbc_new_arrivals(NbCtx &c, int t)
     for (int n = 0; n < total; ++n) {
         h->ue_count += 1;
         int buffer = c.conf.buffer_hi > c.conf.buffer_lo ? nbc_integers(c, c.conf.buffer_lo, c.conf.buffer_hi + 1) : c.conf.buffer_lo;
-        double loss = nbc_place_ue(c);
+        double loss = nbc_cold(c)->clustered ? nbc_place_clustered(c) : nbc_place_ue(c, -1.0, -1.0, nullptr);
         int beta = 0;
         if (beta_arrivals > 0) { beta = 1; beta_arrivals -= 1; }
         double P_RSRP = NB_SUB(NB_SRP, loss);
@@ -1092,6 +1112,14 @@ NB_FN1 void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
             h->ue_departures[u->CE_level] += 1; h->thr_count += 1; h->total_bits += u->acked_data;
             int deps = h->ue_departures[0] + h->ue_departures[1] + h->ue_departures[2];
             h->av_delay = NB_ADD(h->av_delay, NB_DIV(NB_SUB((double)delay, h->av_delay), (double)deps));
+            const NbColdConf *cold = nbc_cold(c);
+            if (cold->stat_cap > 0) {                          /* statistics histories (perf_monitor.py:161-171): rings of stat_cap entries */
+                int32_t *st = cold->stat_base + (size_t)(c.occ - cold->occ_base) * 4u * (size_t)cold->stat_cap;
+                int j = c.occ->stat_n % cold->stat_cap;
+                st[j] = delay; st[cold->stat_cap + j] = service_time; st[2 * cold->stat_cap + j] = u->t_connection - u->t_arrival;
+                st[3 * cold->stat_cap + j] = u->acked_data;
+                c.occ->stat_n += 1;
+            }
             if (c.conf.random_traffic) { if (nbc_bernoulli(c, h->gen_p) > 0) h->M_beta += 1; else h->M_uniform += 1; }   /* ue_generator.departure */
             else if (u->beta && h->M_beta < h->M_beta_max) h->M_beta += 1;
             else h->M_uniform += 1;
@@ -1530,6 +1558,7 @@ NB_FN void nbc_construct(NbCtx &c, uint64_t seed, const NbCtrlDev *ctrl)
         return 0;
     });
     h->seed = seed;
+    c.occ->cluster_count = 0; c.occ->stat_n = 0; c.occ->cluster_cx = 0.0; c.occ->cluster_cy = 0.0;   /* Population.__init__ (:57-63): not reset() */
     h->NPDCCH_sf_left = NB_NPDCCH_SF;
     NB_NOUNROLL
     for (int i = 0; i < 16; ++i) h->nprach_conf[i] = nb_nprach_default_conf[i];
@@ -1581,6 +1610,7 @@ NB_FN void nbc_reset(NbCtx &c)
     NB_NOUNROLL
     for (int i = 0; i < 3; ++i) { h->ue_arrivals[i] = 0; h->ue_departures[i] = 0; h->backoffs[i] = 0; }
     h->ue_connections = 0; h->av_delay = 0.0; h->msg3_resources = 0; h->NPUSCH_resources = 0; h->NPRACH_resources = 0;
+    c.occ->stat_n = 0;                                         /* the histories restart (perf_monitor.py:61-84) */
     nbc_clear_info(c);
     /* ue_generator.reset (ue_generator.py:38-42) */
     double ratio = c.conf.ratio < 1.0 ? c.conf.ratio : 1.0;

@@ -37,7 +37,7 @@ struct NbKernelArgs {
     uint8_t *state;
     NbLayout L;
     const nbiot_conf_t *conf;
-    const NbCtrlDev *ctrl;
+    const NbCtaConst *ctrl;      /* controller tables + cold configuration */
     const uint16_t *lut2;
     const uint8_t *mcs;
     unsigned int *counter;
@@ -52,7 +52,7 @@ struct nbiot_handle {
     int device, n_inst;
     uint8_t *state;
     nbiot_conf_t *conf_dev;
-    NbCtrlDev *ctrl_dev;
+    NbCtaConst *ctrl_dev;
     uint16_t *lut2_dev;
     uint8_t *mcs_dev;
     uint64_t *seeds_dev;
@@ -78,7 +78,7 @@ __device__ __forceinline__ void nb_copy16(void *dst, const void *src, int n16)
     for (int i = threadIdx.x & 31; i < n16; i += 32) d[i] = s[i];
 }
 
-__device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int i, const NbCtrlDev *s_ctrl)
+__device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int i, const NbCtaConst *s_cc)
 {
     const NbLayout &L = A.L;
     uint8_t *s = A.state;
@@ -93,7 +93,7 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
     c.service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
     c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
     c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
-    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = *A.conf; c.ctrl = s_ctrl;
+    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = *(const nbiot_conf_hot_t *)A.conf; c.ctrl = &s_cc->ctrl;
     c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
     c.evlog = i == 0 ? A.evlog : nullptr; c.evlog_cap = A.evlog_cap;
 }
@@ -104,8 +104,8 @@ template <bool LOAD, class Body>
 __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, const uint8_t *active, Body body)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ NbCtrlDev s_ctrl;                       /* the controller tables, once per CTA */
-    for (int k = threadIdx.x; k < (int)(sizeof(NbCtrlDev) / 4); k += blockDim.x) ((uint32_t *)&s_ctrl)[k] = ((const uint32_t *)A.ctrl)[k];
+    __shared__ NbCtaConst s_ctrl;                      /* the controller tables + cold configuration, once per CTA */
+    for (int k = threadIdx.x; k < (int)(sizeof(NbCtaConst) / 4); k += blockDim.x) ((uint32_t *)&s_ctrl)[k] = ((const uint32_t *)A.ctrl)[k];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *my = smem + (size_t)warp * A.smem_per_warp;
@@ -203,6 +203,29 @@ __global__ void nbiot_stats_kernel(const NbHdr *hdr, int n_inst, unsigned long l
         if (acc[k]) { if (k < NBIOT_STAT_MAX_LOOKAHEAD) atomicAdd(&out[k], acc[k]); else atomicMax(&out[k], acc[k]); }
 }
 
+/* statistics histories (perf_monitor.py:61-84): entries recorded per instance */
+__global__ void nbiot_stat_count_kernel(const NbOccHist *occ, int n_inst, int32_t *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_inst) out[i] = occ[i].stat_n;
+}
+
+/* histogram over the whole batch of one history (0 delay, 1 connection, 2 access, 3 acked bits): one warp per instance
+ * streams its ring (coalesced int32 reads), bins of `bin_width` with the last bin open-ended; HBM-bound, one pass */
+__global__ void nbiot_stat_hist_kernel(const NbOccHist *occ, const int32_t *stat, int cap, int n_inst, int which, int bin_width, int n_bins,
+                                       unsigned long long *hist)
+{
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n_inst; i += n_warps) {
+        int n = occ[i].stat_n; if (n > cap) n = cap;
+        const int32_t *v = stat + ((size_t)i * 4u + (size_t)which) * (size_t)cap;
+        for (int k = lane; k < n; k += 32) {
+            int b = v[k] / bin_width; if (b < 0) b = 0; if (b >= n_bins) b = n_bins - 1;
+            atomicAdd(&hist[b], 1ull);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ host side */
 static NbKernelArgs make_args(nbiot_handle_t *h)
 {
@@ -259,14 +282,16 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     memset(h, 0, sizeof *h);
     h->conf = *conf; h->ctrl = *ctrl; h->L = L; h->device = device; h->n_inst = n_inst; h->state = (uint8_t *)state_dev;
     CK(cudaMalloc(&h->conf_dev, sizeof(nbiot_conf_t)));
-    CK(cudaMalloc(&h->ctrl_dev, sizeof(NbCtrlDev)));
+    CK(cudaMalloc(&h->ctrl_dev, sizeof(NbCtaConst)));
     CK(cudaMalloc(&h->lut2_dev, NB_LUT_CURVES * NB_LUT_SNR_PTS * sizeof(uint16_t)));
     CK(cudaMalloc(&h->mcs_dev, NB_MCS_LOSS_ROWS * NB_N_TBS * 3));
     CK(cudaMalloc(&h->seeds_dev, sizeof(uint64_t) * (size_t)n_inst));
     CK(cudaMalloc(&h->counter_dev, sizeof(unsigned int)));
     CK(cudaMemcpyAsync(h->conf_dev, conf, sizeof(nbiot_conf_t), cudaMemcpyHostToDevice, st));
-    NbCtrlDev cd = nb_make_ctrl_dev(ctrl);
-    CK(cudaMemcpyAsync(h->ctrl_dev, &cd, sizeof(NbCtrlDev), cudaMemcpyHostToDevice, st));
+    static_assert(sizeof(NbCtaConst) % 4 == 0, "NbCtaConst is staged word by word");
+    NbCtaConst cd; memset(&cd, 0, sizeof cd);
+    cd.ctrl = nb_make_ctrl_dev(ctrl); cd.cold = nb_make_cold(conf, h->state, L.off_occ, L.off_stat);
+    CK(cudaMemcpyAsync(h->ctrl_dev, &cd, sizeof(NbCtaConst), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->lut2_dev, lut2, NB_LUT_CURVES * NB_LUT_SNR_PTS * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->mcs_dev, mcs, NB_MCS_LOSS_ROWS * NB_N_TBS * 3, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->seeds_dev, seeds, sizeof(uint64_t) * (size_t)n_inst, cudaMemcpyHostToDevice, st));
@@ -309,7 +334,7 @@ int nbiot_set_controller(nbiot_handle_t *h, const struct nbiot_ctrl *ctrl, void 
     CK(cudaSetDevice(h->device));
     h->ctrl = *ctrl;
     NbCtrlDev cd = nb_make_ctrl_dev(&h->ctrl);
-    CK(cudaMemcpyAsync(h->ctrl_dev, &cd, sizeof(NbCtrlDev), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CK(cudaMemcpyAsync(&h->ctrl_dev->ctrl, &cd, sizeof(NbCtrlDev), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }
@@ -434,6 +459,39 @@ int nbiot_step_host(nbiot_handle_t *h, const uint8_t *actions_host, int until_ti
     CK(cudaStreamSynchronize(st));
     if (obs_host && obs_dim > 0) memcpy(obs_host, h->obs_pin, (size_t)h->n_inst * obs_dim * sizeof(double));
     if (reward_host) memcpy(reward_host, h->rew_pin, (size_t)h->n_inst * sizeof(double));
+    return 0;
+}
+
+int nbiot_stat_ptrs(nbiot_handle_t *h, void **stat_dev, int *stat_cap)
+{
+    if (!h) return set_err(NBIOT_E_INVALID, "nbiot_stat_ptrs: null handle");
+    if (stat_dev) *stat_dev = h->L.stat_cap > 0 ? (void *)(h->state + h->L.off_stat) : nullptr;
+    if (stat_cap) *stat_cap = h->L.stat_cap;
+    return 0;
+}
+
+int nbiot_stat_counts(nbiot_handle_t *h, int32_t *counts_dev, void *stream)
+{
+    if (!h || !counts_dev) return set_err(NBIOT_E_INVALID, "nbiot_stat_counts: null argument");
+    CK(cudaSetDevice(h->device));
+    nbiot_stat_count_kernel<<<(h->n_inst + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const NbOccHist *)(h->state + h->L.off_occ), h->n_inst, counts_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+int nbiot_stat_histogram(nbiot_handle_t *h, int which, int bin_width, int n_bins, int64_t *hist_dev, void *stream)
+{
+    if (!h || !hist_dev || which < 0 || which > 3 || bin_width < 1 || n_bins < 1) return set_err(NBIOT_E_INVALID, "nbiot_stat_histogram: bad argument");
+    if (h->L.stat_cap <= 0) return set_err(NBIOT_E_INVALID, "nbiot_stat_histogram: the batch was created without statistics (stat_cap = 0)");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(hist_dev, 0, sizeof(int64_t) * (size_t)n_bins, st));
+    int blocks = (h->n_inst + 3) / 4; if (blocks > 148 * 8) blocks = 148 * 8;
+    nbiot_stat_hist_kernel<<<blocks, 128, 0, st>>>((const NbOccHist *)(h->state + h->L.off_occ), (const int32_t *)(h->state + h->L.off_stat), h->L.stat_cap,
+                                                    h->n_inst, which, bin_width, n_bins, (unsigned long long *)hist_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
     return 0;
 }
 

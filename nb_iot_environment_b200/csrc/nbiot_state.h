@@ -26,6 +26,7 @@
 #include "nbiot_conf.h"
 #include "nbiot_ctrl.h"
 #include "nbiot_record.h"
+#include "nbiot_params.h"
 
 #define NB_EV_POOL 48        /* pending RAR_window_end / Msg3 / NPUSCH_end events            */
 #define NB_OCC_RING 24       /* pending NPRACH occasions per CE level (look-ahead / 80 sf)   */
@@ -96,9 +97,13 @@ typedef struct {            /* 64 B: reference system/user.py:35-70 minus never-
     uint8_t where, pad[7];
 } NbUe;
 
-typedef struct {            /* per-occasion NPRACH histories of the current update period (cold) */
+typedef struct {            /* cold per-instance block in HBM: per-occasion NPRACH histories of the current update period,
+                               clustered-placement memory (population.py:57-63), statistics cursor */
     int16_t det[3][NBIOT_MAX_OCC];
     int16_t col[3][NBIOT_MAX_OCC];
+    int32_t cluster_count;  /* UEs still to be placed around the current cluster centre */
+    int32_t stat_n;         /* departures recorded in the statistics histories since reset */
+    double cluster_cx, cluster_cy;
 } NbOccHist;
 
 typedef struct __attribute__((aligned(16))) NbHdr {
@@ -182,6 +187,17 @@ typedef struct {
     uint8_t init_action[24];
 } NbCtrlDev;
 
+/* configuration read on rare paths only (arrivals, departures): kept out of the per-warp context */
+typedef struct {
+    int32_t stat_cap, clustered, cluster_lo, cluster_hi;
+    double cluster_prob, cluster_range;   /* cluster_range already divided by the cell range (population.py:62) */
+    NbOccHist *occ_base;                  /* instance index = c.occ - occ_base */
+    int32_t *stat_base;                   /* int32[n_inst][4][stat_cap]: delay, connection, access, acked bits */
+} NbColdConf;
+
+/* per-CTA constants in shared memory: NbCtx.ctrl points at the first member */
+typedef struct { NbCtrlDev ctrl; NbColdConf cold; } NbCtaConst;
+
 static inline NbCtrlDev nb_make_ctrl_dev(const nbiot_ctrl_t *c)
 {
     NbCtrlDev d;
@@ -198,18 +214,28 @@ static inline NbCtrlDev nb_make_ctrl_dev(const nbiot_ctrl_t *c)
 
 /* byte offsets of the per-instance arrays inside the caller-owned state buffer */
 typedef struct {
-    int32_t n_inst, ue_cap, grid_w, hist_cap, n_carriers, ra_cap, pad0, pad1;
+    int32_t n_inst, ue_cap, grid_w, hist_cap, n_carriers, ra_cap, stat_cap, pad1;
     uint64_t off_hdr, off_grid, off_ra, off_conn, off_cont, off_ue, off_free, off_occ;
-    uint64_t off_incoming, off_delays, off_service, off_rec, off_scratch, total;
+    uint64_t off_incoming, off_delays, off_service, off_rec, off_scratch, off_stat, total;
 } NbLayout;
 
 static inline uint64_t nb_align256(uint64_t x) { return (x + 255u) & ~(uint64_t)255u; }
+
+static inline NbColdConf nb_make_cold(const nbiot_conf_t *c, uint8_t *state, uint64_t off_occ, uint64_t off_stat)
+{
+    NbColdConf k;
+    double range = c->max_d > 0 ? c->max_d : NB_MAX_RANGE;      /* channel.py:128-131 */
+    k.stat_cap = c->stat_cap > 0 ? c->stat_cap : 0; k.clustered = c->clustered; k.cluster_lo = c->cluster_lo; k.cluster_hi = c->cluster_hi;
+    k.cluster_prob = c->cluster_prob; k.cluster_range = c->cluster_range / range;
+    k.occ_base = (NbOccHist *)(state + off_occ); k.stat_base = (int32_t *)(state + off_stat);
+    return k;
+}
 
 static inline NbLayout nb_make_layout(const nbiot_conf_t *c, int n)
 {
     NbLayout L;
     L.n_inst = n; L.ue_cap = c->ue_cap; L.grid_w = c->grid_w; L.hist_cap = c->hist_cap;
-    L.n_carriers = c->n_carriers >= 2 ? 2 : 1; L.ra_cap = c->ue_cap + NB_RA_SLACK; L.pad0 = L.pad1 = 0;
+    L.n_carriers = c->n_carriers >= 2 ? 2 : 1; L.ra_cap = c->ue_cap + NB_RA_SLACK; L.stat_cap = c->stat_cap > 0 ? c->stat_cap : 0; L.pad1 = 0;
     uint64_t o = 0, N = (uint64_t)n;
     L.off_hdr = o;      o = nb_align256(o + N * sizeof(NbHdr));
     L.off_grid = o;     o = nb_align256(o + N * (uint64_t)L.n_carriers * (uint64_t)L.grid_w * 2u);
@@ -224,6 +250,7 @@ static inline NbLayout nb_make_layout(const nbiot_conf_t *c, int n)
     L.off_service = o;  o = nb_align256(o + N * (uint64_t)L.hist_cap * 4u);
     L.off_rec = o;      o = nb_align256(o + N * sizeof(nbiot_record_t));
     L.off_scratch = o;  o = nb_align256(o + N * (uint64_t)L.ra_cap * 2u);
+    L.off_stat = o;     o = nb_align256(o + N * 4u * (uint64_t)L.stat_cap * 4u);
     L.total = o;
     return L;
 }

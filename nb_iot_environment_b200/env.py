@@ -100,7 +100,7 @@ class BatchedNBIoTEnv:
     that is driven from outside (-1: none, the cells run on their internal agents)."""
 
     def __init__(self, conf, agents_conf=None, ext_agent=-1, num_envs=1, seeds=None, n_carriers=1, device=0,
-                 ue_cap=None, grid_w=1024, hist_cap=256, all_states_external=False):
+                 ue_cap=None, grid_w=1024, hist_cap=256, all_states_external=False, stat_cap=None):
         if not torch.cuda.is_available():
             raise _cabi.NbiotError('BatchedNBIoTEnv needs a CUDA device: there is no CPU fallback')
         self.L = _cabi.load()
@@ -108,7 +108,7 @@ class BatchedNBIoTEnv:
         self.device = torch.device('cuda', device)
         self.conf = dict(conf)
         self.n_carriers = n_carriers
-        self.cconf = make_conf(conf, n_carriers=n_carriers, ue_cap=ue_cap, grid_w=grid_w, hist_cap=hist_cap)
+        self.cconf = make_conf(conf, n_carriers=n_carriers, ue_cap=ue_cap, grid_w=grid_w, hist_cap=hist_cap, stat_cap=stat_cap)
         self.tables = ControllerTables(agents_conf, ext_agent, n_carriers)
         self.all_states_external = bool(all_states_external)
         self.ctrl = self.tables.build(all_states_external=self.all_states_external)
@@ -139,6 +139,10 @@ class BatchedNBIoTEnv:
         _cabi.check(self.L.nbiot_hist_ptrs(self._h, ctypes.byref(ip), ctypes.byref(dp), ctypes.byref(sp), ctypes.byref(cap)))
         base = self.state.data_ptr()
         self._hist_off = (ip.value - base, dp.value - base, sp.value - base, cap.value)
+        stp, scap = ctypes.c_void_p(), ctypes.c_int()
+        _cabi.check(self.L.nbiot_stat_ptrs(self._h, ctypes.byref(stp), ctypes.byref(scap)))
+        self.stat_cap = scap.value
+        self._stat_off = (stp.value - base) if stp.value else None
 
     # ------------------------------------------------------------------ spaces (controller.py:77-103)
     def _set_obs_items(self):
@@ -267,6 +271,47 @@ class BatchedNBIoTEnv:
         n = self.num_envs * RECORD_DTYPE.itemsize
         raw = self.state[self._rec_off:self._rec_off + n].cpu().numpy()
         return raw.view(RECORD_DTYPE).copy()
+
+    # ------------------------------------------------------------------ statistics histories (conf['statistics'])
+    def stat_counts(self):
+        """int32[N] on the device: departures recorded in the histories since reset"""
+        out = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.L.nbiot_stat_counts(self._h, out.data_ptr(), self._stream()))
+        return out
+
+    def histories(self):
+        """PerfMonitor.delay_history / connection_history / access_history / th_history (perf_monitor.py:61-84, :161-171) of every cell:
+        a list of dicts of numpy arrays, in departure order (what experiments_RL.py:139-140 saves as `delay` and `connection`).
+        A cell with more departures than stat_cap keeps the last stat_cap of them ('truncated': True)."""
+        if not self.stat_cap:
+            raise _cabi.NbiotError("the batch was created without statistics: pass conf['statistics']=True or stat_cap")
+        N, cap = self.num_envs, self.stat_cap
+        cnt = self.stat_counts().cpu().numpy()
+        raw = self.state[self._stat_off:self._stat_off + N * 4 * cap * 4].cpu().numpy().view(np.int32).reshape(N, 4, cap)
+        out = []
+        for i in range(N):
+            n = int(cnt[i])
+            if n <= cap:
+                v = raw[i, :, :n]
+            else:                                    # ring: the oldest kept entry sits at n % cap
+                v = np.roll(raw[i], -(n % cap), axis=1)
+            out.append({'delay': v[0].copy(), 'connection': v[1].copy(), 'access': v[2].copy(),
+                        'th': v[3].astype(np.float64) / v[0].astype(np.float64), 'served_users': n, 'truncated': n > cap})
+        return out
+
+    def save_results(self, path, i=0):
+        """np.savez with the reference's keys (experiments_RL.py:139-140, experiments_MAMBRL.py:121-122) for cell i"""
+        h = self.histories()[i]
+        np.savez(path, delay=h['delay'], connection=h['connection'], served_users=h['served_users'])
+
+    def stat_histogram(self, which='delay', bin_width=100, n_bins=64):
+        """int64[n_bins] on the device: histogram of one history over the whole batch (last bin open-ended)"""
+        idx = {'delay': 0, 'connection': 1, 'access': 2, 'bits': 3}[which]
+        out = torch.zeros(n_bins, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.L.nbiot_stat_histogram(self._h, idx, int(bin_width), int(n_bins), out.data_ptr(), self._stream()))
+        return out
 
     def period_lists(self):
         """(incoming float64[N, cap], delays int32[N, cap], service_times int32[N, cap]) of the update period

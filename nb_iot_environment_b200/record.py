@@ -61,16 +61,21 @@ class NbiotConf(ctypes.Structure):
                 ('sc_adjustment', ctypes.c_int32), ('mcs_automatic', ctypes.c_int32),
                 ('ce_mcs_automatic', ctypes.c_int32), ('tx_all_buffer', ctypes.c_int32),
                 ('random_traffic', ctypes.c_int32), ('n_carriers', ctypes.c_int32),
-                ('ue_cap', ctypes.c_int32), ('grid_w', ctypes.c_int32), ('hist_cap', ctypes.c_int32)]
+                ('ue_cap', ctypes.c_int32), ('grid_w', ctypes.c_int32), ('hist_cap', ctypes.c_int32),
+                ('stat_cap', ctypes.c_int32), ('clustered', ctypes.c_int32), ('cluster_lo', ctypes.c_int32), ('cluster_hi', ctypes.c_int32),
+                ('cluster_prob', ctypes.c_double), ('cluster_range', ctypes.c_double)]
 
 
-_UNSUPPORTED_TRUE = ('animate_carrier', 'animate_stats', 'traces', 'resource_monitor', 'clustered')
+_UNSUPPORTED_TRUE = ('animate_carrier', 'animate_stats', 'traces', 'resource_monitor')
 _KNOWN = {'ratio', 'M', 'buffer_range', 'reward_criteria', 'sort_criterium', 'levels', 'max_d', 'sc_adjustment',
           'mcs_automatic', 'ce_mcs_automatic', 'tx_all_buffer', 'animate_carrier', 'statistics', 'animate_stats',
           'traces', 'resource_monitor', 'random', 'clustered', 'cluster_ues', 'cluster_prob', 'cluster_range'}
 
 
-def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256):
+DEFAULT_STAT_CAP = 2048
+
+
+def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_cap=None):
     """conf dict with the reference's keys and defaults (system_creator.py:24-44) -> NbiotConf."""
     unknown = set(conf) - _KNOWN
     if unknown:
@@ -105,6 +110,18 @@ def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256):
     c.ue_cap = int(ue_cap if ue_cap is not None else M)
     c.grid_w = int(grid_w)
     c.hist_cap = int(hist_cap)
+    # conf['statistics'] keeps the per-departure histories (perf_monitor.py:61-84): stat_cap entries per cell
+    c.stat_cap = int(stat_cap) if stat_cap is not None else (DEFAULT_STAT_CAP if conf.get('statistics', False) else 0)
+    if c.stat_cap < 0:
+        raise ValueError('stat_cap must be >= 0')
+    # clustered placement (system_creator.py:41-44, population.py:57-63)
+    c.clustered = int(bool(conf.get('clustered', False)))
+    lo, hi = conf.get('cluster_ues', [10, 30])
+    c.cluster_lo, c.cluster_hi = int(lo), int(hi)
+    if c.clustered and not c.cluster_hi > c.cluster_lo:
+        raise ValueError('cluster_ues must be [MIN, MAX] with MAX > MIN (rng.integers(MIN, MAX))')
+    c.cluster_prob = float(conf.get('cluster_prob', 0.5))
+    c.cluster_range = float(conf.get('cluster_range', 0.5))
     return c
 
 

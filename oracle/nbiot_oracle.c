@@ -129,6 +129,9 @@ typedef struct Oracle {
     int detected_preambles_per_CE[3], collided_preambles_per_CE[3], contenders_per_CE[3], RAR_counter[3];
     ivec detection_history[3], collision_history[3];
 
+    /* clustered placement (population.py:57-63): survives reset() */
+    int cluster_count; double cluster_center[2], cluster_range;
+
     /* ue generator (ue_generator.py:23-42) */
     int M_uniform, M_beta, M_beta_max, gen_t, gen_counter; double gen_p;
 
@@ -138,6 +141,7 @@ typedef struct Oracle {
     double av_delay;
     long long msg3_resources, NPUSCH_resources, NPRACH_resources;
     ivec rx_id, rx_delay, err_id, unfit_id, acc_id, acc_delay;
+    ivec access_history, connection_history, delay_history, bits_history;   /* statistics (perf_monitor.py:61-84); th = bits / delay */
 
     int fault;
     /* last NPRACH_update info lists (copied out on request) */
@@ -196,6 +200,7 @@ static void perf_reset(Oracle *o)
     VCLEAR(o->rx_id); VCLEAR(o->rx_delay); VCLEAR(o->err_id); VCLEAR(o->unfit_id); VCLEAR(o->acc_id); VCLEAR(o->acc_delay);
     for (int i = 0; i < 3; ++i) o->ue_arrivals[i] = o->ue_departures[i] = o->backoffs[i] = 0;
     o->ue_connections = 0; o->av_delay = 0; o->msg3_resources = o->NPUSCH_resources = o->NPRACH_resources = 0;
+    VCLEAR(o->access_history); VCLEAR(o->connection_history); VCLEAR(o->delay_history); VCLEAR(o->bits_history);
 }
 static void perf_clear_info(Oracle *o)
 { VCLEAR(o->rx_id); VCLEAR(o->rx_delay); VCLEAR(o->err_id); VCLEAR(o->unfit_id); VCLEAR(o->acc_id); VCLEAR(o->acc_delay); }
@@ -278,10 +283,9 @@ static double find_y_value(double x1, double y1, double x2, double y2, double x)
 #define S34 0.4330127018922193   /* np.sqrt(3)/4 */
 #define S32 0.8660254037844386   /* np.sqrt(3)/2 */
 
-static void channel_set_xy_loss(Oracle *o, UE *ue)
+static void channel_set_xy_loss_at(Oracle *o, UE *ue, double x, double y)
 {
-    double x, y;
-    for (;;) {                                               /* generate_xy :108-114 */
+    if (x < 0) for (;;) {                                    /* generate_xy :108-114 (also when a clustered x falls left of the cell, :143-144) */
         nb_rng_pair(o->seed, o->draws++, NBIOT_STREAM_ENV, &x, &y);
         int in_cell = (y > find_y_value(0, S34, 0.25, 0, x)) && (y > find_y_value(0.75, 0, 1, S34, x)) &&
                       (y < find_y_value(0, S34, 0.25, S32, x)) && (y < find_y_value(0.75, S32, 1, S34, x)) && (y < S32);
@@ -298,6 +302,27 @@ static void channel_set_xy_loss(Oracle *o, UE *ue)
     if (!(L > 0)) L = 0;
     L = L - G + 0;
     ue->loss = L; ue->x = x; ue->y = y;
+}
+static void channel_set_xy_loss(Oracle *o, UE *ue) { channel_set_xy_loss_at(o, ue, -1, -1); }
+
+/* Population.clustered_ue_generation (population.py:75-101) */
+static void clustered_ue_generation(Oracle *o, UE *ue)
+{
+    double p = rng_u01(o);
+    if (p < o->conf.cluster_prob) {
+        if (!o->cluster_count) {
+            channel_set_xy_loss(o, ue);
+            o->cluster_center[0] = ue->x; o->cluster_center[1] = ue->y;
+            o->cluster_count = rng_integers(o, o->conf.cluster_lo, o->conf.cluster_hi);
+        } else {
+            double ua = rng_u01(o);                          /* angle = uniform(0, 2 pi): cos / sin taken at 2 pi u */
+            double radius = o->cluster_range * NB_SQRT(rng_uniform(o, 0, 1));
+            double x = radius * nb_cos2pi(ua), y = radius * nb_sin2pi(ua);
+            x = x + o->cluster_center[0]; y = y + o->cluster_center[1];
+            channel_set_xy_loss_at(o, ue, x, y);
+            o->cluster_count -= 1;
+        }
+    } else channel_set_xy_loss(o, ue);
 }
 
 static double get_bler(Oracle *o, double snr, int itbs, int nr)
@@ -634,7 +659,8 @@ static void get_new_arrivals(Oracle *o, int t)                        /* populat
         UE *ue = calloc(1, sizeof(UE));
         ue->id = o->ue_count; ue->t_arrival = t; ue->buffer = buffer; ue->new_data = 1; ue->loss = 70;
         if (beta_arrivals > 0) { ue->beta = 1; beta_arrivals -= 1; }
-        channel_set_xy_loss(o, ue);
+        if (o->conf.clustered) clustered_ue_generation(o, ue);
+        else channel_set_xy_loss(o, ue);
         double P_RSRP = NB_SRP - ue->loss;
         int CE_level;
         if (P_RSRP < o->CE_thresholds[0]) CE_level = 2;
@@ -851,6 +877,10 @@ static void rx_NPUSCH_end(Oracle *o, Event *ev)                       /* rx_proc
             int delay = t - ue->t_connection, service_time = t - ue->t_arrival;   /* perf.unregister_ue :142-171 */
             o->ue_departures[ue->CE_level] += 1; o->thr_count += 1; o->total_bits += ue->acked_data;
             o->av_delay += ((double)delay - o->av_delay) / (double)(o->ue_departures[0] + o->ue_departures[1] + o->ue_departures[2]);
+            if (o->conf.stat_cap > 0) {                                          /* statistics (perf_monitor.py:161-171) */
+                VPUSH(o->access_history, ue->t_connection - ue->t_arrival); VPUSH(o->connection_history, service_time);
+                VPUSH(o->delay_history, delay); VPUSH(o->bits_history, ue->acked_data);
+            }
             gen_departure(o, ue);
             VPUSH(o->departures, delay);
             o->total_departures += 1;
@@ -1250,6 +1280,8 @@ Oracle *orc_create(const nbiot_conf_t *conf, uint64_t seed, const uint16_t *lut2
     o->CE_thresholds[0] = -102; o->CE_thresholds[1] = -85;   /* [-102.5,-85.0]: overwritten by the t=0 update before any arrival */
     o->preamble_trans_max = 2; o->MAC_timer = 64;
     o->gen_p = 0.5; o->gen_counter = 0;
+    o->cluster_count = 0; o->cluster_center[0] = o->cluster_center[1] = 0;
+    o->cluster_range = conf->cluster_range / o->range;       /* population.py:62 */
     return o;
 }
 
@@ -1266,7 +1298,17 @@ void orc_destroy(Oracle *o)
     VFREE(o->connected); VFREE(o->contention); VFREE(o->incoming); VFREE(o->departures); VFREE(o->service_times);
     VFREE(o->sc_log); VFREE(o->rx_id); VFREE(o->rx_delay); VFREE(o->err_id); VFREE(o->unfit_id); VFREE(o->acc_id); VFREE(o->acc_delay);
     VFREE(o->info_incoming); VFREE(o->info_delays); VFREE(o->info_service);
+    VFREE(o->access_history); VFREE(o->connection_history); VFREE(o->delay_history); VFREE(o->bits_history);
     free(o);
+}
+
+/* statistics histories since the last reset: which = 0 delay, 1 connection (service time), 2 access, 3 acked bits;
+ * returns the true length, copies at most cap entries */
+int orc_get_stats(Oracle *o, int which, int32_t *out, int cap)
+{
+    ivec *v = which == 0 ? &o->delay_history : which == 1 ? &o->connection_history : which == 2 ? &o->access_history : &o->bits_history;
+    for (int i = 0; i < v->n && i < cap; ++i) out[i] = v->d[i];
+    return v->n;
 }
 
 /* lists of the last NPRACH_update info: returns the true lengths, copies at most cap entries */

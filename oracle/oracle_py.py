@@ -29,6 +29,8 @@ def lib():
         L.orc_destroy.argtypes = [ctypes.c_void_p]
         L.orc_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.orc_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_get_stats.restype = ctypes.c_int
+        L.orc_get_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.orc_get_hist.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 2
         L.orc_get_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_set_event_log.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
@@ -101,6 +103,17 @@ class OracleCell:
         ni = ctypes.c_int32(); nd = ctypes.c_int32()
         self.L.orc_get_hist(self.h, inc.ctypes.data, d.ctypes.data, s.ctypes.data, cap, ctypes.byref(ni), ctypes.byref(nd))
         return inc[:ni.value].copy(), d[:nd.value].copy(), s[:nd.value].copy()
+
+    def stats(self, cap=1 << 16):
+        """statistics histories since reset (perf_monitor.py:61-84): delay, connection, access (int32) and th = bits / delay"""
+        out = {}
+        buf = np.zeros(cap, dtype=np.int32)
+        for which, name in enumerate(('delay', 'connection', 'access', 'bits')):
+            n = self.L.orc_get_stats(self.h, which, buf.ctypes.data, cap)
+            assert n <= cap
+            out[name] = buf[:n].copy()
+        out['th'] = out['bits'].astype(np.float64) / out['delay'].astype(np.float64)      # acked_data / delay (perf_monitor.py:169)
+        return out
 
     def counters(self):
         out = np.zeros(16, dtype=np.int64); av = ctypes.c_double()

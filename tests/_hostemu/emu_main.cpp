@@ -9,7 +9,7 @@
 
 struct Emu {
     nbiot_conf_t conf;
-    NbCtrlDev ctrl;
+    NbCtaConst cc;
     NbLayout L;
     uint8_t *state;
     const uint16_t *lut2;
@@ -38,7 +38,7 @@ struct Staged {
         c->service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
         c->scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
         c->rec = (nbiot_record_t *)(s + L.off_rec) + i;
-        c->lut2 = e->lut2; c->mcs = e->mcs; c->conf = e->conf; c->ctrl = &e->ctrl;
+        c->lut2 = e->lut2; c->mcs = e->mcs; c->conf = *(const nbiot_conf_hot_t *)&e->conf; c->ctrl = &e->cc.ctrl;
         c->W = L.grid_w; c->ue_cap = L.ue_cap; c->ra_cap = L.ra_cap; c->hist_cap = L.hist_cap; c->C = L.n_carriers;
         c->evlog = (e->evlog && i == 0) ? e->evlog : NULL; c->evlog_cap = e->evlog_cap;
         if (load) {
@@ -64,15 +64,16 @@ int emu_hdr_size(void) { return (int)sizeof(NbHdr); }
 void *emu_create(const nbiot_conf_t *conf, int n_inst, const uint64_t *seeds, const uint16_t *lut2, const uint8_t *mcs, const nbiot_ctrl_t *ctrl)
 {
     Emu *e = (Emu *)calloc(1, sizeof(Emu));
-    e->conf = *conf; e->ctrl = nb_make_ctrl_dev(ctrl); e->lut2 = lut2; e->mcs = mcs;
+    e->conf = *conf; e->cc.ctrl = nb_make_ctrl_dev(ctrl); e->lut2 = lut2; e->mcs = mcs;
     e->L = nb_make_layout(conf, n_inst);
     e->state = (uint8_t *)calloc(1, e->L.total);
-    for (int i = 0; i < n_inst; ++i) { Staged st(e, i, false); nbc_construct(*st.c, seeds[i], &e->ctrl); }
+    e->cc.cold = nb_make_cold(conf, e->state, e->L.off_occ, e->L.off_stat);
+    for (int i = 0; i < n_inst; ++i) { Staged st(e, i, false); nbc_construct(*st.c, seeds[i], &e->cc.ctrl); }
     return e;
 }
 
 void emu_destroy(void *p) { Emu *e = (Emu *)p; free(e->state); free(e); }
-void emu_set_ctrl(void *p, const nbiot_ctrl_t *ctrl) { ((Emu *)p)->ctrl = nb_make_ctrl_dev(ctrl); }
+void emu_set_ctrl(void *p, const nbiot_ctrl_t *ctrl) { ((Emu *)p)->cc.ctrl = nb_make_ctrl_dev(ctrl); }
 void emu_set_evlog(void *p, int32_t *buf, int cap) { Emu *e = (Emu *)p; e->evlog = buf; e->evlog_cap = cap; }
 
 void emu_reset(void *p)
@@ -87,9 +88,19 @@ void emu_advance(void *p, const uint8_t *ext_actions, int until_time, int max_st
     Emu *e = (Emu *)p;
     for (int i = 0; i < e->L.n_inst; ++i) {
         Staged st(e, i, true);
-        int s = nbc_controller_advance(*st.c, &e->ctrl, ext_actions ? ext_actions + (size_t)i * e->ctrl.ext_k : NULL, until_time, max_steps);
+        int s = nbc_controller_advance(*st.c, &e->cc.ctrl, ext_actions ? ext_actions + (size_t)i * e->cc.ctrl.ext_k : NULL, until_time, max_steps);
         if (steps_out) steps_out[i] = s;
     }
+}
+
+// statistics histories of instance i: which = 0 delay, 1 connection, 2 access, 3 bits; returns the number recorded
+int emu_stats(void *p, int i, int which, int32_t *out, int cap)
+{
+    Emu *e = (Emu *)p;
+    int n = ((NbOccHist *)(e->state + e->L.off_occ))[i].stat_n, sc = e->L.stat_cap;
+    const int32_t *v = (const int32_t *)(e->state + e->L.off_stat) + ((size_t)i * 4 + which) * sc;
+    for (int k = 0; k < n && k < cap && k < sc; ++k) out[k] = v[k];
+    return n;
 }
 
 const void *emu_records(void *p) { Emu *e = (Emu *)p; return e->state + e->L.off_rec; }

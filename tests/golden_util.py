@@ -9,7 +9,7 @@ import numpy as np
 from nb_iot_environment_b200.record import RECORD_DTYPE, FLOAT_FIELDS, INT_FIELDS, NON_PARITY_FIELDS
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))) if not n.startswith(('wrappers_', 'long_')))
+CASES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))) if not n.startswith(('wrappers_', 'long_', 'mb_agent')))
 
 # float fields are compared to the reference's numpy/libm/scipy arithmetic: nbiot_math.h agrees to ~1e-15,
 # the contract (BASELINE.json north_star) is 1e-5 relative
@@ -45,6 +45,12 @@ class Golden:
 
     def events(self, si):
         return self.z[f'events_{si}']
+
+    def stats(self, si):
+        """PerfMonitor histories of a statistics=True case (delay, connection, access int32; th float64), or None"""
+        if f'stat_delay_{si}' not in self.z.files:
+            return None
+        return {'delay': self.z[f'stat_delay_{si}'], 'connection': self.z[f'stat_conn_{si}'], 'access': self.z[f'stat_access_{si}'], 'th': self.z[f'stat_th_{si}']}
 
 
 def record_diff(a, b, rtol=0.0, skip=NON_PARITY_FIELDS):

@@ -25,6 +25,8 @@ def lib(lanes):
         L.emu_reset.argtypes = [ctypes.c_void_p]
         L.emu_advance.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.emu_records.restype = ctypes.c_void_p
+        L.emu_stats.restype = ctypes.c_int
+        L.emu_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.emu_records.argtypes = [ctypes.c_void_p]
         L.emu_counters.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         assert L.emu_lanes() == lanes
@@ -71,6 +73,15 @@ class EmuBatch:
         else:
             self.L.emu_advance(self.h, None, until_time, max_steps, steps.ctypes.data)
         return self.records(), steps
+
+    def stats(self, i, cap=1 << 16):
+        out = {}
+        buf = np.zeros(cap, dtype=np.int32)
+        for which, name in enumerate(('delay', 'connection', 'access', 'bits')):
+            n = self.L.emu_stats(self.h, i, which, buf.ctypes.data, cap)
+            out[name] = buf[:min(n, cap, self.cconf.stat_cap)].copy()
+            out['n'] = n
+        return out
 
     def counters(self, i):
         out = np.zeros(16, dtype=np.int64); av = ctypes.c_double()

@@ -88,8 +88,13 @@ def test_conf_validation():
     from nb_iot_environment_b200.record import make_conf
     base = {'ratio': 1.0, 'M': 100, 'buffer_range': [100, 600], 'reward_criteria': 'throughput'}
     make_conf(base)
+    c = make_conf(dict(base, clustered=True, cluster_ues=[3, 8], cluster_prob=0.9, cluster_range=2.0, statistics=True))
+    assert (c.clustered, c.cluster_lo, c.cluster_hi, c.cluster_prob, c.cluster_range, c.stat_cap) == (1, 3, 8, 0.9, 2.0, 2048)
+    assert make_conf(base).stat_cap == 0 and make_conf(base, stat_cap=64).stat_cap == 64
+    with pytest.raises(ValueError):
+        make_conf(dict(base, clustered=True, cluster_ues=[5, 5]))
     with pytest.raises(NotImplementedError):
-        make_conf(dict(base, clustered=True))
+        make_conf(dict(base, traces=True))
     with pytest.raises(NotImplementedError):
         make_conf(dict(base, reward_criteria='average_total_delay'))
     with pytest.raises(KeyError):

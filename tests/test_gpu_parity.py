@@ -73,7 +73,45 @@ def test_golden_traces_and_oracle(case):
                 assert np.array_equal(lists[1][si, :len(gdl)], gdl) and np.array_equal(lists[2][si, :len(gsv)], gsv)
                 assert np.allclose(lists[0][si, :len(ginc)], ginc, rtol=REF_RTOL, atol=0)
     assert not (recs['fault'] & 0x1F).any()
+    if g.stats(0) is not None:
+        # conf['statistics']: the per-departure histories (perf_monitor.py:61-84) and the batch histogram computed on the device
+        hs = env.histories()
+        all_delays = []
+        for si in range(len(g.seeds)):
+            gs = g.stats(si)
+            assert hs[si]['served_users'] == len(gs['delay']) and not hs[si]['truncated']
+            for k in ('delay', 'connection', 'access'):
+                assert np.array_equal(hs[si][k], gs[k]), k
+            assert np.array_equal(hs[si]['th'], gs['th'])
+            all_delays.append(gs['delay'])
+        d = np.concatenate(all_delays)
+        want = np.bincount(np.minimum(d // 250, 31), minlength=32)
+        assert np.array_equal(env.stat_histogram('delay', bin_width=250, n_bins=32).cpu().numpy(), want)
     env.close()
+
+
+@pytest.mark.gpu
+def test_statistics_ring_keeps_the_latest_departures():
+    """more departures than stat_cap: the ring holds the last stat_cap of them, in order, and says so"""
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    conf = dict(CFG1, statistics=True)
+    full = BatchedNBIoTEnv(conf, num_envs=3, seeds=[5, 6, 7], ue_cap=512, grid_w=1024)
+    small = BatchedNBIoTEnv(conf, num_envs=3, seeds=[5, 6, 7], ue_cap=512, grid_w=1024, stat_cap=16)
+    for e in (full, small):
+        e.reset(); e.run_until(20000)
+    hf, hs = full.histories(), small.histories()
+    for i in range(3):
+        n = hf[i]['served_users']
+        assert n > 16 and hs[i]['served_users'] == n and hs[i]['truncated'] and not hf[i]['truncated']
+        for k in ('delay', 'connection', 'access', 'th'):
+            assert np.array_equal(hs[i][k], hf[i][k][-16:]), k
+    small.reset()
+    assert small.stat_counts().cpu().numpy().tolist() == [0, 0, 0]          # perf_monitor.reset() restarts the histories
+    no = BatchedNBIoTEnv(CFG1, num_envs=1, ue_cap=64, grid_w=256)
+    with pytest.raises(Exception):
+        no.histories()
+    for e in (full, small, no):
+        e.close()
 
 
 def _random_ext_actions(rng, nvec, n):

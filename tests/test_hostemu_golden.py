@@ -35,6 +35,13 @@ def _replay(case, lanes, decisions):
                     assert c[k] == pytest.approx(v, rel=REF_RTOL)
                 else:
                     assert c[k] == v, k
+            gs = g.stats(si)
+            if gs is not None:                                   # statistics histories (perf_monitor.py:161-171)
+                st = b.stats(si)
+                assert st['n'] == len(gs['delay'])
+                for k in ('delay', 'connection', 'access'):
+                    assert np.array_equal(st[k], gs[k]), k
+                assert np.array_equal(st['bits'].astype(np.float64) / st['delay'].astype(np.float64), gs['th'])
 
 
 @pytest.mark.parametrize('case', CASES)

@@ -33,5 +33,12 @@ def test_oracle_replays_reference_trace(case, oracle_lib):
                 assert c[k] == pytest.approx(v, rel=REF_RTOL)
             else:
                 assert c[k] == v, k
+        gs = g.stats(si)
+        if gs is not None:                                       # statistics=True: the per-departure histories (perf_monitor.py:161-171)
+            st = cell.stats()
+            for k in ('delay', 'connection', 'access'):
+                assert np.array_equal(st[k], gs[k]), k
+            assert np.array_equal(st['th'], gs['th'])           # acked bits / delay: one IEEE division of the same integers
+            assert len(gs['delay']) == sum(gc['ue_departures'])
         ev = g.events(si)
         assert np.array_equal(cell.event_log()[:len(ev)], ev)   # same pops in the same (time, seq) order

@@ -50,6 +50,10 @@ CASES = {
     # RA congestion: thousands of contenders per NPRACH, backoff draws dominate
     'overload': dict(conf={'M': 20000, 'ratio': 0.2, 'buffer_range': [256, 256], 'reward_criteria': 'accumulated_delay'},
                      nc=1, policy='fixed', seeds=[60], decisions=700),
+    # clustered placement (population.py:75-101) and the statistics histories (perf_monitor.py:61-84, :161-171)
+    'clustered_statistics': dict(conf=dict(CFG1, ratio=0.5, clustered=True, statistics=True), nc=1, policy='fixed', seeds=[80, 81], decisions=1400),
+    'clustered_tight_small_cell': dict(conf=dict(CFG1, clustered=True, cluster_ues=[3, 8], cluster_prob=0.9, cluster_range=2.0, max_d=5.0, statistics=True),
+                                       nc=1, policy='random', seeds=[85], decisions=1400),
     'invd_reward_small_cell': dict(conf=dict(CFG1, reward_criteria='invd_users', max_d=3.0, M=600), nc=1, policy='random', seeds=[70], decisions=800),
 }
 
@@ -76,7 +80,7 @@ def run_case(name):
     S, D = len(case['seeds']), case['decisions']
     records = np.zeros((S, D + 1), dtype=RECORD_DTYPE)
     actions = np.zeros((S, D, 23), dtype=np.int8)
-    counters, hists, events = [], [], []
+    counters, hists, events, stats = [], [], [], []
     for si, seed in enumerate(case['seeds']):
         cell = RefCell(case['conf'], seed, n_carriers=case['nc'], log_events=True)
         prng = np.random.default_rng(1000 + seed)
@@ -88,6 +92,10 @@ def run_case(name):
             rec = cell.step(a)
             records[si, d + 1] = rec
         counters.append(cell.counters())
+        if case['conf'].get('statistics'):
+            pm = cell.perf
+            stats.append((np.asarray(pm.delay_history, np.int32), np.asarray(pm.connection_history, np.int32),
+                          np.asarray(pm.access_history, np.int32), np.asarray(pm.th_history, np.float64)))
         hists.append(cell.hists)
         events.append(np.asarray(cell.events, dtype=np.int32))
         cell.close()
@@ -104,6 +112,8 @@ def run_case(name):
         flat[f'service_{si}'] = np.concatenate(sv) if sv else np.zeros(0, dtype=np.int32)
         flat[f'delays_len_{si}'] = np.asarray([len(x) for x in dl], dtype=np.int32)
         flat[f'events_{si}'] = events[si][:20000]
+        if stats:
+            flat[f'stat_delay_{si}'], flat[f'stat_conn_{si}'], flat[f'stat_access_{si}'], flat[f'stat_th_{si}'] = stats[si]
     meta = {'name': name, 'conf': case['conf'], 'n_carriers': case['nc'], 'seeds': case['seeds'], 'policy': case['policy'],
             'decisions': D, 'counters': counters, 'record_itemsize': RECORD_DTYPE.itemsize,
             'record_descr': str(RECORD_DTYPE.descr)}
