@@ -555,7 +555,7 @@ NB_DEV double nbc_find_y(double x1, double y1, double x2, double y2, double x)  
 #define NB_S32 0.8660254037844386
 
 /* Channel.set_xy_loss / generate_xy / location / antenna_pattern (channel.py:100-118, :134-151) */
-NB_FNM4 double nbc_place_ue(NbCtx &c, double x, double y, double *xy_out)
+NB_DEV double nbc_place_ue(NbCtx &c, double x, double y, double *xy_out)
 {
     if (x < 0) for (;;) {                        /* generate_xy; also when a clustered x falls left of the cell (channel.py:143-144) */
         nb_rng_pair(nbc_hdr(c)->seed, nbc_hdr(c)->draws++, NBIOT_STREAM_ENV, &x, &y);
@@ -578,14 +578,16 @@ NB_FNM4 double nbc_place_ue(NbCtx &c, double x, double y, double *xy_out)
     return NB_ADD(NB_SUB(L, G), 0.0);
 }
 
+NB_FN double nbc_place_ue_cold(NbCtx &c, double x, double y, double *xy_out) { return nbc_place_ue(c, x, y, xy_out); }
+
 /* Population.clustered_ue_generation (population.py:75-101): out of line, only clustered cells come here */
 NB_FN double nbc_place_clustered(NbCtx &c)
 {
     const NbColdConf *cold = nbc_cold(c);
     double p = nbc_u01(c), xy[2];
-    if (!(p < cold->cluster_prob)) return nbc_place_ue(c, -1.0, -1.0, nullptr);
+    if (!(p < cold->cluster_prob)) return nbc_place_ue_cold(c, -1.0, -1.0, nullptr);
     if (!c.occ->cluster_count) {                 /* a new cluster: its first UE is placed anywhere and becomes the centre */
-        double loss = nbc_place_ue(c, -1.0, -1.0, xy);
+        double loss = nbc_place_ue_cold(c, -1.0, -1.0, xy);
         c.occ->cluster_cx = xy[0]; c.occ->cluster_cy = xy[1];
         c.occ->cluster_count = nbc_integers(c, cold->cluster_lo, cold->cluster_hi);
         return loss;
@@ -594,7 +596,7 @@ NB_FN double nbc_place_clustered(NbCtx &c)
     double radius = NB_MUL(cold->cluster_range, NB_SQRT(NB_ADD(0.0, NB_MUL(1.0, nbc_u01(c)))));
     double x = NB_ADD(NB_MUL(radius, nb_cos2pi(ua)), c.occ->cluster_cx), y = NB_ADD(NB_MUL(radius, nb_sin2pi(ua)), c.occ->cluster_cy);
     c.occ->cluster_count -= 1;
-    return nbc_place_ue(c, x, y, nullptr);
+    return nbc_place_ue_cold(c, x, y, nullptr);
 }
 
 /* UEGenerator.generate_arrivals (ue_generator.py:54-81) + Population.get_new_arrivals (population.py:103-132) */
@@ -1082,6 +1084,16 @@ NB_FN1 void nbc_msg3_event(NbCtx &c, int slot, int t)
     nbc_update_state(c);
 }
 
+/* statistics histories (perf_monitor.py:161-171): rings of stat_cap entries per cell, out of line (off unless conf['statistics']) */
+NB_FN void nbc_stat_append(NbCtx &c, int delay, int service_time, int access, int bits)
+{
+    const NbColdConf *cold = nbc_cold(c);
+    int32_t *st = cold->stat_base + (size_t)(c.occ - cold->occ_base) * 4u * (size_t)cold->stat_cap;
+    int j = c.occ->stat_n % cold->stat_cap;
+    st[j] = delay; st[cold->stat_cap + j] = service_time; st[2 * cold->stat_cap + j] = access; st[3 * cold->stat_cap + j] = bits;
+    c.occ->stat_n += 1;
+}
+
 /* RxProcedure.NPUSCH_end (rx_procedure.py:54-61), Channel.NPUSCH_detection (channel.py:236-256),
  * NodeB.NPUSCH_end (node_b.py:801-830), PerfMonitor.account_rx/account_error/unregister_ue */
 NB_FN1 void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
@@ -1112,14 +1124,7 @@ NB_FN1 void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
             h->ue_departures[u->CE_level] += 1; h->thr_count += 1; h->total_bits += u->acked_data;
             int deps = h->ue_departures[0] + h->ue_departures[1] + h->ue_departures[2];
             h->av_delay = NB_ADD(h->av_delay, NB_DIV(NB_SUB((double)delay, h->av_delay), (double)deps));
-            const NbColdConf *cold = nbc_cold(c);
-            if (cold->stat_cap > 0) {                          /* statistics histories (perf_monitor.py:161-171): rings of stat_cap entries */
-                int32_t *st = cold->stat_base + (size_t)(c.occ - cold->occ_base) * 4u * (size_t)cold->stat_cap;
-                int j = c.occ->stat_n % cold->stat_cap;
-                st[j] = delay; st[cold->stat_cap + j] = service_time; st[2 * cold->stat_cap + j] = u->t_connection - u->t_arrival;
-                st[3 * cold->stat_cap + j] = u->acked_data;
-                c.occ->stat_n += 1;
-            }
+            if (nbc_cold(c)->stat_cap > 0) nbc_stat_append(c, delay, service_time, u->t_connection - u->t_arrival, u->acked_data);
             if (c.conf.random_traffic) { if (nbc_bernoulli(c, h->gen_p) > 0) h->M_beta += 1; else h->M_uniform += 1; }   /* ue_generator.departure */
             else if (u->beta && h->M_beta < h->M_beta_max) h->M_beta += 1;
             else h->M_uniform += 1;
