@@ -29,8 +29,15 @@
 #ifndef NB_WPB
 #define NB_WPB 4   /* warps (instances in flight) per CTA */
 #endif
-#ifndef NB_MIN_CTAS
-#define NB_MIN_CTAS 7   /* __launch_bounds__ second argument: resident CTAs per SM the register budget must allow */
+/* The hot kernel is built twice: MINB = 7 (72 registers: the budget that lets 7 CTAs = 28 warps live on an SM, which is what the
+ * shared-memory slice of a grid_w = 2048 instance allows) and MINB = 9 (56 registers, 36 warps: what a grid_w = 1024 slice allows).
+ * Instruction supply, not registers, bounds this kernel (profiles/r01_icache.txt), so the extra warps win wherever shared memory
+ * lets them be resident: +11 % on the config-5 sweep. nbiot_create picks the build with the most resident warps for the batch. */
+#ifndef NB_MIN_CTAS_LO
+#define NB_MIN_CTAS_LO 7
+#endif
+#ifndef NB_MIN_CTAS_HI
+#define NB_MIN_CTAS_HI 9
 #endif
 
 struct NbKernelArgs {
@@ -57,7 +64,7 @@ struct nbiot_handle {
     uint8_t *mcs_dev;
     uint64_t *seeds_dev;
     unsigned int *counter_dev;
-    int blocks, smem_bytes;
+    int blocks, smem_bytes, sim_hi;
     long long launches;
     int32_t *evlog; int evlog_cap;
     /* staging for nbiot_step_host */
@@ -135,7 +142,8 @@ __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, cons
 }
 
 /* the hot kernel: Controller.step / run_until for every instance */
-__global__ void __launch_bounds__(NB_WPB * 32, NB_MIN_CTAS)
+template <int MINB>
+__global__ void __launch_bounds__(NB_WPB * 32, MINB)
 nbiot_sim_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps)
 {
     nb_for_each_instance<true>(A, active, [&](NbCtx &c, int i) {
@@ -243,7 +251,8 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->counter_dev, 0, sizeof(unsigned int), st));
     NbKernelArgs A = make_args(h);
-    if (mode == 2) nbiot_sim_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, ext_actions, active, until_time, max_steps);
+    if (mode == 2 && h->sim_hi) nbiot_sim_kernel<NB_MIN_CTAS_HI><<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, ext_actions, active, until_time, max_steps);
+    else if (mode == 2) nbiot_sim_kernel<NB_MIN_CTAS_LO><<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, ext_actions, active, until_time, max_steps);
     else nbiot_reset_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, mode == 0 ? 1 : 0, h->seeds_dev);
     CK(cudaGetLastError());
     h->launches += 1;
@@ -302,10 +311,17 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if ((size_t)h->smem_bytes > prop.sharedMemPerBlockOptin) return set_err(NBIOT_E_INVALID, "grid_w too large for the shared memory of one CTA");
-    CK(cudaFuncSetAttribute(nbiot_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CK(cudaFuncSetAttribute(nbiot_sim_kernel<NB_MIN_CTAS_LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    CK(cudaFuncSetAttribute(nbiot_sim_kernel<NB_MIN_CTAS_HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     CK(cudaFuncSetAttribute(nbiot_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nbiot_sim_kernel, NB_WPB * 32, h->smem_bytes));
+    int per_sm_hi = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nbiot_sim_kernel<NB_MIN_CTAS_LO>, NB_WPB * 32, h->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_hi, nbiot_sim_kernel<NB_MIN_CTAS_HI>, NB_WPB * 32, h->smem_bytes));
+    /* the leaner-register build only when it really puts more CTAs on an SM AND the batch has the instances to fill them */
+    h->sim_hi = per_sm_hi > per_sm && (long long)n_inst > (long long)prop.multiProcessorCount * per_sm * NB_WPB;
+    if (const char *e = getenv("NBIOT_SIM_BUILD")) h->sim_hi = !strcmp(e, "hi");      /* measurement knob: "lo" / "hi" */
+    if (h->sim_hi) per_sm = per_sm_hi;
     if (per_sm < 1) per_sm = 1;
     if (const char *e = getenv("NBIOT_MAX_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   /* measurement knob */
     int need = (n_inst + NB_WPB - 1) / NB_WPB;
