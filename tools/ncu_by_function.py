@@ -6,6 +6,7 @@ executed instructions, stall samples and the share of samples that are instructi
 import csv, os, re, subprocess, sys, tempfile, bisect
 src = sys.argv[1]
 lib = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'nb_iot_environment_b200', 'libnbiot_b200.so')
+KERNEL = os.environ.get('NBIOT_PROFILE_KERNEL', 'nbiot_sim_kernelILi7')   # the 72-register build (bench workload)
 d = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=d, capture_output=True)
 cub = [f for f in os.listdir(d) if f.endswith('.cubin')][-1]
@@ -14,7 +15,7 @@ txt = subprocess.run(['nvdisasm', '-c', os.path.join(d, cub)], capture_output=Tr
 starts, names, insec, cur = [], [], False, None
 for line in txt.splitlines():
     if line.startswith('//') and '.text.' in line:
-        insec = 'nbiot_sim_kernel' in line
+        insec = KERNEL in line
     m = re.match(r'^(\$?[\w\$\.]+):\s*$', line.strip())
     if m and not m.group(1).startswith('.L'):
         cur = m.group(1) if insec else None
