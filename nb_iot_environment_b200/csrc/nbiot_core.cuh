@@ -34,7 +34,7 @@
 #include "nbiot_warp.h"
 
 /* Per-warp working context. It sits in shared memory directly in front of the staged header and grid
- *   [ NbCtx | NbHdr | grid[C][W] ]
+ *   [ NbCtx | NbHdr | grid[C][W] (when staged) ]
  * so the hot state is reached from the one register holding &ctx with constant offsets (no pointer chase),
  * and the compiler is told it is shared memory. The HBM-resident arrays are reached through the pointers. */
 struct __attribute__((aligned(16))) NbCtx {
@@ -54,6 +54,7 @@ struct __attribute__((aligned(16))) NbCtx {
     const NbCtrlDev *ctrl;    /* controller tables: the first member of an NbCtaConst (shared memory in the kernels) */
     int32_t *evlog;           /* optional (t, type) pop log for debugging */
     int W, ue_cap, ra_cap, hist_cap, C, evlog_cap;
+    uint16_t *grid;           /* the look-ahead ring: staged in shared memory behind the header, or in place in HBM (short launches) */
 };
 
 #if defined(__CUDA_ARCH__)
@@ -63,7 +64,7 @@ struct __attribute__((aligned(16))) NbCtx {
 #endif
 NB_DEV NbHdr *nbc_hdr(NbCtx &c) { NbHdr *h = (NbHdr *)((char *)&c + sizeof(NbCtx)); NB_ASSUME_SHARED(h); return h; }
 NB_DEV const NbColdConf *nbc_cold(NbCtx &c) { return &((const NbCtaConst *)c.ctrl)->cold; }
-NB_DEV uint16_t *nbc_grid(NbCtx &c) { return (uint16_t *)((char *)nbc_hdr(c) + sizeof(NbHdr)); }
+NB_DEV uint16_t *nbc_grid(NbCtx &c) { return c.grid; }
 #define NB_WARP_BYTES(C, W) (sizeof(NbCtx) + sizeof(NbHdr) + (size_t)(C) * (size_t)(W) * 2u)
 
 #define NB_FAULT(c, bit) (nbc_hdr(c)->fault |= (int32_t)(bit))

@@ -50,6 +50,7 @@ struct NbKernelArgs {
     unsigned int *counter;
     int32_t *evlog; int evlog_cap;
     int smem_per_warp, hdr_bytes16, grid_bytes16;
+    int stage_grid;              /* 1: the look-ahead ring is staged in shared memory; 0: used in place in HBM (short launches) */
 };
 
 struct nbiot_handle {
@@ -65,6 +66,7 @@ struct nbiot_handle {
     uint64_t *seeds_dev;
     unsigned int *counter_dev;
     int blocks, smem_bytes, sim_hi;
+    int blocks_short, smem_short, sim_hi_short, stage_policy;     /* geometry of launches that leave the grid in HBM */
     long long launches;
     int32_t *evlog; int evlog_cap;
     /* staging for nbiot_step_host */
@@ -103,6 +105,8 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
     c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = *(const nbiot_conf_hot_t *)A.conf; c.ctrl = &s_cc->ctrl;
     c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
     c.evlog = i == 0 ? A.evlog : nullptr; c.evlog_cap = A.evlog_cap;
+    c.grid = A.stage_grid ? (uint16_t *)((unsigned char *)&c + sizeof(NbCtx) + sizeof(NbHdr))
+                          : (uint16_t *)(A.state + A.L.off_grid) + (size_t)i * A.L.n_carriers * A.L.grid_w;
 }
 
 /* Claim instances from the work counter; stage [ctx | header | grid] in this warp's shared-memory slice;
@@ -130,13 +134,13 @@ __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, cons
         if (lane == 0) nb_fill_ctx(c, A, i, &s_ctrl);
         if (LOAD) {
             nb_copy16(hdr_s, hdr_g + i, A.hdr_bytes16);
-            nb_copy16(grid_s, grid_g + (size_t)i * grid_elems, A.grid_bytes16);
+            if (A.stage_grid) nb_copy16(grid_s, grid_g + (size_t)i * grid_elems, A.grid_bytes16);
         }
         __syncwarp();
         body(c, i);
         __syncwarp();
         nb_copy16(hdr_g + i, hdr_s, A.hdr_bytes16);
-        nb_copy16(grid_g + (size_t)i * grid_elems, grid_s, A.grid_bytes16);
+        if (A.stage_grid) nb_copy16(grid_g + (size_t)i * grid_elems, grid_s, A.grid_bytes16);
         __syncwarp();
     }
 }
@@ -235,14 +239,15 @@ __global__ void nbiot_stat_hist_kernel(const NbOccHist *occ, const int32_t *stat
 }
 
 /* ------------------------------------------------------------------ host side */
-static NbKernelArgs make_args(nbiot_handle_t *h)
+static NbKernelArgs make_args(nbiot_handle_t *h, int stage_grid = 1)
 {
     NbKernelArgs A;
     A.state = h->state; A.L = h->L; A.conf = h->conf_dev; A.ctrl = h->ctrl_dev; A.lut2 = h->lut2_dev; A.mcs = h->mcs_dev;
     A.counter = h->counter_dev; A.evlog = h->evlog; A.evlog_cap = h->evlog_cap;
     A.hdr_bytes16 = (int)(sizeof(NbHdr) / 16);
     A.grid_bytes16 = (int)((size_t)h->L.n_carriers * h->L.grid_w * 2 / 16);
-    A.smem_per_warp = (int)sizeof(NbCtx) + A.hdr_bytes16 * 16 + A.grid_bytes16 * 16;
+    A.stage_grid = stage_grid;
+    A.smem_per_warp = (int)sizeof(NbCtx) + A.hdr_bytes16 * 16 + (stage_grid ? A.grid_bytes16 * 16 : 0);
     return A;
 }
 
@@ -250,9 +255,15 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
 {
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->counter_dev, 0, sizeof(unsigned int), st));
-    NbKernelArgs A = make_args(h);
-    if (mode == 2 && h->sim_hi) nbiot_sim_kernel<NB_MIN_CTAS_HI><<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, ext_actions, active, until_time, max_steps);
-    else if (mode == 2) nbiot_sim_kernel<NB_MIN_CTAS_LO><<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, ext_actions, active, until_time, max_steps);
+    /* Short launches -- an external agent that acts at Scheduling / RAR decisions gets control back after one or two NodeB steps
+     * (configs 3 and 4) -- touch a few dozen columns of the look-ahead ring: it stays in HBM (read through L1), which saves staging
+     * 2 x C x W x 2 bytes per instance per launch and leaves room for more CTAs per SM. Long launches stage it. */
+    const unsigned frequent = (1u << NB_ST_SCHEDULING) | (1u << NB_ST_RAR_WINDOW) | (1u << NB_ST_RAR_WINDOW_END);
+    int stage = h->stage_policy >= 0 ? h->stage_policy : !(mode == 2 && ext_actions && (h->ctrl.ext_state_mask & frequent));
+    NbKernelArgs A = make_args(h, stage);
+    int blocks = stage ? h->blocks : h->blocks_short, smem = stage ? h->smem_bytes : h->smem_short, hi = stage ? h->sim_hi : h->sim_hi_short;
+    if (mode == 2 && hi) nbiot_sim_kernel<NB_MIN_CTAS_HI><<<blocks, NB_WPB * 32, smem, st>>>(A, ext_actions, active, until_time, max_steps);
+    else if (mode == 2) nbiot_sim_kernel<NB_MIN_CTAS_LO><<<blocks, NB_WPB * 32, smem, st>>>(A, ext_actions, active, until_time, max_steps);
     else nbiot_reset_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, mode == 0 ? 1 : 0, h->seeds_dev);
     CK(cudaGetLastError());
     h->launches += 1;
@@ -324,6 +335,20 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     if (h->sim_hi) per_sm = per_sm_hi;
     if (per_sm < 1) per_sm = 1;
     if (const char *e = getenv("NBIOT_MAX_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   /* measurement knob */
+    {   /* the same choice for launches that do not stage the grid */
+        NbKernelArgs B = make_args(h, 0);
+        h->smem_short = NB_WPB * B.smem_per_warp;
+        int lo = 0, hi2 = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lo, nbiot_sim_kernel<NB_MIN_CTAS_LO>, NB_WPB * 32, h->smem_short));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hi2, nbiot_sim_kernel<NB_MIN_CTAS_HI>, NB_WPB * 32, h->smem_short));
+        h->sim_hi_short = hi2 > lo && (long long)n_inst > (long long)prop.multiProcessorCount * lo * NB_WPB;
+        if (const char *e = getenv("NBIOT_SIM_BUILD")) h->sim_hi_short = !strcmp(e, "hi");
+        int ps = h->sim_hi_short ? hi2 : lo; if (ps < 1) ps = 1;
+        int need_s = (n_inst + NB_WPB - 1) / NB_WPB, cap_s = prop.multiProcessorCount * ps;
+        h->blocks_short = need_s < cap_s ? need_s : cap_s;
+        h->stage_policy = -1;
+        if (const char *e = getenv("NBIOT_STAGE_GRID")) h->stage_policy = atoi(e) ? 1 : 0;       /* measurement knob */
+    }
     int need = (n_inst + NB_WPB - 1) / NB_WPB;
     int cap = prop.multiProcessorCount * per_sm;
     h->blocks = need < cap ? need : cap;

@@ -41,6 +41,7 @@ struct Staged {
         c->lut2 = e->lut2; c->mcs = e->mcs; c->conf = *(const nbiot_conf_hot_t *)&e->conf; c->ctrl = &e->cc.ctrl;
         c->W = L.grid_w; c->ue_cap = L.ue_cap; c->ra_cap = L.ra_cap; c->hist_cap = L.hist_cap; c->C = L.n_carriers;
         c->evlog = (e->evlog && i == 0) ? e->evlog : NULL; c->evlog_cap = e->evlog_cap;
+        c->grid = (uint16_t *)(buf + sizeof(NbCtx) + sizeof(NbHdr));
         if (load) {
             memcpy(buf + sizeof(NbCtx), (NbHdr *)(s + L.off_hdr) + i, sizeof(NbHdr));
             memcpy(buf + sizeof(NbCtx) + sizeof(NbHdr), (uint16_t *)(s + L.off_grid) + (size_t)i * L.n_carriers * L.grid_w, gbytes);
