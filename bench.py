@@ -287,6 +287,13 @@ def main():
                      'note': 'algorithmic bytes of SURVEY 8(d) (a per-subframe UE scan); the kernel skips idle subframes, so its DRAM traffic is far below this'},
         'wall_s_timed_region': wall1,
     }
+    print('episode statistics (job):', [int(v) for v in job_stats.tolist()], file=sys.stderr)     # equal for every kernel / scheduler that runs the same batch
+    if os.environ.get('NBIOT_SCHED', '').startswith('queue'):
+        qs = (ctypes.c_ulonglong * 32)()
+        _cabi.check(env.L.nbiot_queue_stats(env._h, qs))
+        line['config']['scheduler'] = 'migrating instances (NBIOT_SCHED=queue)'
+        print('queue stats: tasks', list(qs)[0:10], 'cycles', list(qs)[10:20], 'hops', qs[20], 'local', qs[21], 'switches', qs[22],
+              'idle_polls', qs[23], 'bail', qs[24], file=sys.stderr)
     if world == 1 and not os.environ.get('NBIOT_BENCH_NO_CPU'):          # (measurement sweeps skip the CPU leg)
         r = cpu_reference_arm(40, 0, cells_per_step=64 * (os.cpu_count() or 1))     # ~15 CPU-seconds of work
         line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}

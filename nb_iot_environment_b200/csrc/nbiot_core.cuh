@@ -55,6 +55,9 @@ struct __attribute__((aligned(16))) NbCtx {
     int32_t *evlog;           /* optional (t, type) pop log for debugging */
     int W, ue_cap, ra_cap, hist_cap, C, evlog_cap;
     uint16_t *grid;           /* the look-ahead ring: staged in shared memory behind the header, or in place in HBM (short launches) */
+#ifdef NB_TASKS
+    int tk_until, tk_max_steps;   /* bounds of this launch (see "tasks" at the end of the file) */
+#endif
 };
 
 #if defined(__CUDA_ARCH__)
@@ -1701,5 +1704,163 @@ NB_FN int nbc_controller_advance(NbCtx &c, const NbCtrlDev *ctrl, const uint8_t 
     else c.rec->fault = h->fault;
     return steps;
 }
+
+#ifdef NB_TASKS
+/* ------------------------------------------------------------------ tasks
+ * The control flow of one instance -- Controller.step / run_until (controller.py:185-195, :234-288) around
+ * NodeB.step (node_b.py:228-245) around NodeB.advance_fel (:191-204) -- cut into TASKS: one heavy handler each
+ * (a NodeB step of one decision state, an NPRACH occasion, a msg3 or NPUSCH reception, the final record).
+ * Everything between two handlers (event selection, the light events, the controller's loop tests and the
+ * internal agents) is the glue that runs at the end of every task and names the next one. Nothing lives in
+ * registers or in the per-warp context between tasks -- the control state is in the header (NbHdr.tk_*) -- so any
+ * warp of any SM can run the next task of any instance: the migrating-instance kernel (nbiot_queue.cu) moves an
+ * instance to an SM whose warps are all in that task's handler, which keeps an SM's instruction working set to one
+ * handler + glue instead of the whole event cycle. nbc_task_chain runs the same tasks in turn on one owner
+ * (CPU builds) and is step for step the monolithic nbc_controller_advance above. */
+enum { NB_TK_DONE = -1, NB_TK_BEGIN = 0, NB_TK_STEP_DATA = 1, NB_TK_STEP_RARW = 2, NB_TK_STEP_RAREND = 3, NB_TK_STEP_UPDATE = 4,
+       NB_TK_NPRACH_START = 5, NB_TK_MSG3 = 6, NB_TK_NPUSCH_END = 7, NB_TK_FINISH = 8, NB_TK_GLUE = 9, NB_TK_N = 10 };
+/* NB_TASK_SPLIT_GLUE = 1: the glue is a task class of its own (a handler names NB_TK_GLUE, the glue names the next handler), which
+ * halves the code an SM of the migrating-instance kernel walks through per class at the price of twice the hops */
+#ifndef NB_TASK_SPLIT_GLUE
+#define NB_TASK_SPLIT_GLUE 0
+#endif
+enum { NB_PH_FEL = 0, NB_PH_STEPPED = 1 };
+
+/* NodeB.advance_fel (node_b.py:191-204) + check_event (:248-261): pop events, handling the light ones in place,
+ * until a heavy one is due (returns its task class, arguments in NbHdr.tk_*) or a decision is needed (returns 0) */
+NB_FN int nbc_fel_next(NbCtx &c)
+{
+    NbHdr *h = nbc_hdr(c);
+    for (;;) {
+        if (NB_FATAL(c)) return 0;
+        int code; uint64_t key = nbc_next_event(c, &code);
+        if (code < 0) { NB_FAULT(c, NBIOT_FAULT_EVENT_SLOTS); return 0; }
+        int t = (int)(key >> 32);
+        h->subframes_done += (int64_t)(t - h->time);
+        h->time = t; h->cur_key = key;
+        nbc_erase_past_sf(c, t);                               /* carrier_set.step(t) */
+        if (NB_FATAL(c)) return 0;
+        if (c.evlog) nbc_log_event(c, t, code);
+        h->events += 1;
+        if (code == 0) {
+            h->keys[0] = NB_KEY_NONE;
+            if (h->state == NB_ST_RAR_WINDOW || h->state == NB_ST_SCHEDULING) return 0;
+            nbc_schedule_NPDCCH(c, h->NPDCCH_sf_left);
+        } else if (code == 1) {
+            h->keys[1] = NB_KEY_NONE; h->cur_t = t; h->state = NB_ST_NPRACH_UPDATE;
+            return 0;
+        } else if (code < 5) {
+            int ce = code - 2;
+            h->tk_occ = h->occ[ce][h->occ_head_start[ce] % NB_OCC_RING];
+            h->occ_head_start[ce] += 1;
+            nbc_occ_keys(h, ce);
+            h->tk_a = ce;
+            return NB_TK_NPRACH_START;
+        } else if (code < 8) {
+            int ce = code - 5;
+            h->occ_head_end[ce] += 1;
+            nbc_occ_keys(h, ce);
+            nbc_NPRACH_end(c, ce, t);
+        } else if (code == 8) {
+            nbc_MAC_timeout(c, h->next_mac_idx);
+        } else {
+            int i = code - 16;
+            NbEvent e = h->pool[i];
+            nbc_pool_release(c, i);
+            if (e.type == NB_EV_RAR_END) {
+                h->cur_ce = e.ce; h->cur_wid = e.aux; h->cur_t = t; h->state = NB_ST_RAR_WINDOW_END;
+                return 0;
+            }
+            h->tk_a = e.aux; h->tk_b = t;
+            return e.type == NB_EV_MSG3 ? NB_TK_MSG3 : NB_TK_NPUSCH_END;
+        }
+    }
+}
+
+NB_DEV int nbc_step_class(int state)                             /* NodeB.step (node_b.py:228-245): the handler of a decision state */
+{
+    return state == NB_ST_SCHEDULING ? NB_TK_STEP_DATA : state == NB_ST_RAR_WINDOW ? NB_TK_STEP_RARW :
+           state == NB_ST_RAR_WINDOW_END ? NB_TK_STEP_RAREND : state == NB_ST_NPRACH_UPDATE ? NB_TK_STEP_UPDATE : 0;
+}
+
+/* between two handlers: the rest of advance_fel, then the controller's loop (controller.py:234-288) */
+NB_FN int nbc_task_glue(NbCtx &c)
+{
+    NbHdr *h = nbc_hdr(c);
+    const NbCtrlDev *ctrl = c.ctrl;
+    for (;;) {
+        if (h->tk_phase == NB_PH_FEL) {
+            int k = nbc_fel_next(c);
+            if (k) return k;
+            h->tk_phase = NB_PH_STEPPED;
+        }
+        /* a NodeB step has run to the next decision */
+        h->tk_steps += 1;
+        if (NB_FATAL(c)) return NB_TK_FINISH;
+        if ((ctrl->ext_state_mask >> h->state) & 1u) { nbc_apply_writes(c, &ctrl->state_writes[h->state]); return NB_TK_FINISH; }
+        if (!(h->tk_steps < c.tk_max_steps && !(c.tk_until >= 0 && h->time >= c.tk_until))) return NB_TK_FINISH;
+        nbc_node_info(c, 0, 0.0);                              /* an internal agent looks at nothing */
+        nbc_apply_writes(c, &ctrl->state_writes[h->state]);
+        h->tk_phase = NB_PH_FEL;
+        int k = nbc_step_class(h->state);
+        if (k) return k;
+    }
+}
+
+/* first task of a launch: the external action (or the internal agents of the current state), then the first handler.
+ * c.tk_until / c.tk_max_steps hold the launch's bounds (set by whoever fills the context). */
+NB_FN int nbc_task_begin(NbCtx &c, const uint8_t *ext_action)
+{
+    NbHdr *h = nbc_hdr(c);
+    const NbCtrlDev *ctrl = c.ctrl;
+    h->tk_steps = 0; h->tk_phase = NB_PH_FEL;
+    if (NB_FATAL(c)) return NB_TK_FINISH;
+    if (ext_action) {
+        NB_NOUNROLL
+        for (int i = 0; i < ctrl->ext_k; ++i) h->ctrl_action[ctrl->ext_a_mask[i]] = ext_action[i];
+        nbc_apply_writes(c, &ctrl->ext_post);
+    } else nbc_apply_writes(c, &ctrl->state_writes[h->state]);
+    if (!(0 < c.tk_max_steps && !(c.tk_until >= 0 && h->time >= c.tk_until))) return NB_TK_FINISH;
+    int k = nbc_step_class(h->state);
+    if (k) return k;
+    h->tk_phase = NB_PH_FEL;                                   /* a state without a handler (node_b.py:228-245 `default`): advance_fel only */
+    return nbc_task_glue(c);
+}
+
+/* run task k (k != NB_TK_BEGIN) of the instance and the glue behind it; returns the next task (NB_TK_DONE after NB_TK_FINISH) */
+NB_DEV int nbc_task_run(NbCtx &c, int k)
+{
+    NbHdr *h = nbc_hdr(c);
+    switch (k) {
+    case NB_TK_STEP_DATA: nbc_step_data(c, h->ctrl_action); break;
+    case NB_TK_STEP_RARW: nbc_step_RAR_window(c, h->ctrl_action); break;
+    case NB_TK_STEP_RAREND: nbc_step_RAR_end(c, h->ctrl_action); break;
+    case NB_TK_STEP_UPDATE: nbc_step_update(c, h->ctrl_action); break;
+    case NB_TK_NPRACH_START: nbc_NPRACH_start(c, h->tk_a, h->tk_occ); break;
+    case NB_TK_MSG3: nbc_msg3_event(c, h->tk_a, h->tk_b); break;
+    case NB_TK_NPUSCH_END: nbc_NPUSCH_end(c, h->tk_a, h->tk_b); break;
+    case NB_TK_GLUE: return nbc_task_glue(c);
+    default:                                                   /* NB_TK_FINISH */
+        if (h->tk_steps > 0) nbc_node_info(c, 1, nbc_reward(c));
+        else c.rec->fault = h->fault;
+        return NB_TK_DONE;
+    }
+#if NB_TASK_SPLIT_GLUE
+    return NB_TK_GLUE;
+#else
+    return nbc_task_glue(c);
+#endif
+}
+
+/* the chain run by one owner; returns the NodeB steps taken */
+NB_FN int nbc_task_chain(NbCtx &c, const uint8_t *ext_action, int until_time, int max_steps)
+{
+    c.tk_until = until_time; c.tk_max_steps = max_steps;
+    int k = nbc_task_begin(c, ext_action);
+    NB_NOUNROLL
+    while (k != NB_TK_DONE) k = nbc_task_run(c, k);
+    return nbc_hdr(c)->tk_steps;
+}
+#endif /* NB_TASKS */
 
 #endif /* NBIOT_CORE_CUH */

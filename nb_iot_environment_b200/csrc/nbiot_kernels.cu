@@ -25,6 +25,7 @@
 
 #include "nbiot.h"
 #include "nbiot_core.cuh"
+#include "nbiot_launch.h"
 
 #ifndef NB_WPB
 #define NB_WPB 4   /* warps (instances in flight) per CTA */
@@ -40,19 +41,6 @@
 #define NB_MIN_CTAS_HI 9
 #endif
 
-struct NbKernelArgs {
-    uint8_t *state;
-    NbLayout L;
-    const nbiot_conf_t *conf;
-    const NbCtaConst *ctrl;      /* controller tables + cold configuration */
-    const uint16_t *lut2;
-    const uint8_t *mcs;
-    unsigned int *counter;
-    int32_t *evlog; int evlog_cap;
-    int smem_per_warp, hdr_bytes16, grid_bytes16;
-    int stage_grid;              /* 1: the look-ahead ring is staged in shared memory; 0: used in place in HBM (short launches) */
-};
-
 struct nbiot_handle {
     nbiot_conf_t conf;
     nbiot_ctrl_t ctrl;
@@ -67,6 +55,8 @@ struct nbiot_handle {
     unsigned int *counter_dev;
     int blocks, smem_bytes, sim_hi;
     int blocks_short, smem_short, sim_hi_short, stage_policy;     /* geometry of launches that leave the grid in HBM */
+    int q_all;                   /* test knob: short launches too */
+    NbQueueRt *q;                /* migrating-instance kernel (nbiot_queue.cu) for long launches; NULL: warp-per-instance kernel */
     long long launches;
     int32_t *evlog; int evlog_cap;
     /* staging for nbiot_step_host */
@@ -81,34 +71,6 @@ static int set_err(int code, const char *fmt, const char *a = "", const char *b 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(NBIOT_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
 /* ------------------------------------------------------------------ device side */
-__device__ __forceinline__ void nb_copy16(void *dst, const void *src, int n16)
-{
-    const uint4 *s = (const uint4 *)src; uint4 *d = (uint4 *)dst;
-    for (int i = threadIdx.x & 31; i < n16; i += 32) d[i] = s[i];
-}
-
-__device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int i, const NbCtaConst *s_cc)
-{
-    const NbLayout &L = A.L;
-    uint8_t *s = A.state;
-    for (int k = 0; k < 3; ++k) c.ra[k] = (NbRaEntry *)(s + L.off_ra) + ((size_t)i * 3 + k) * L.ra_cap;
-    c.conn = (NbConnEntry *)(s + L.off_conn) + (size_t)i * L.ue_cap;
-    c.cont = (NbContEntry *)(s + L.off_cont) + (size_t)i * L.ue_cap;
-    c.ue = (NbUe *)(s + L.off_ue) + (size_t)i * L.ue_cap;
-    c.free_stack = (uint16_t *)(s + L.off_free) + (size_t)i * L.ue_cap;
-    c.occ = (NbOccHist *)(s + L.off_occ) + i;
-    c.incoming = (double *)(s + L.off_incoming) + (size_t)i * L.hist_cap;
-    c.delays = (int32_t *)(s + L.off_delays) + (size_t)i * L.hist_cap;
-    c.service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
-    c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
-    c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
-    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = *(const nbiot_conf_hot_t *)A.conf; c.ctrl = &s_cc->ctrl;
-    c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
-    c.evlog = i == 0 ? A.evlog : nullptr; c.evlog_cap = A.evlog_cap;
-    c.grid = A.stage_grid ? (uint16_t *)((unsigned char *)&c + sizeof(NbCtx) + sizeof(NbHdr))
-                          : (uint16_t *)(A.state + A.L.off_grid) + (size_t)i * A.L.n_carriers * A.L.grid_w;
-}
-
 /* Claim instances from the work counter; stage [ctx | header | grid] in this warp's shared-memory slice;
  * run `body`; write header and grid back. */
 template <bool LOAD, class Body>
@@ -262,7 +224,12 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
     int stage = h->stage_policy >= 0 ? h->stage_policy : !(mode == 2 && ext_actions && (h->ctrl.ext_state_mask & frequent));
     NbKernelArgs A = make_args(h, stage);
     int blocks = stage ? h->blocks : h->blocks_short, smem = stage ? h->smem_bytes : h->smem_short, hi = stage ? h->sim_hi : h->sim_hi_short;
-    if (mode == 2 && hi) nbiot_sim_kernel<NB_MIN_CTAS_HI><<<blocks, NB_WPB * 32, smem, st>>>(A, ext_actions, active, until_time, max_steps);
+    if (mode == 2 && (stage || h->q_all) && h->q) {
+        int rc = nbq_launch(h->q, A, ext_actions, active, until_time, max_steps, st, g_err, sizeof g_err);
+        if (rc) return rc;
+        h->launches += 1;                              /* the queue-initialisation kernel */
+    }
+    else if (mode == 2 && hi) nbiot_sim_kernel<NB_MIN_CTAS_HI><<<blocks, NB_WPB * 32, smem, st>>>(A, ext_actions, active, until_time, max_steps);
     else if (mode == 2) nbiot_sim_kernel<NB_MIN_CTAS_LO><<<blocks, NB_WPB * 32, smem, st>>>(A, ext_actions, active, until_time, max_steps);
     else nbiot_reset_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, mode == 0 ? 1 : 0, h->seeds_dev);
     CK(cudaGetLastError());
@@ -352,6 +319,12 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     int need = (n_inst + NB_WPB - 1) / NB_WPB;
     int cap = prop.multiProcessorCount * per_sm;
     h->blocks = need < cap ? need : cap;
+    h->q = nullptr;
+    {   /* NBIOT_SCHED = "queue": long launches run on the migrating-instance kernel; "warp" (default): one warp owns an instance for the launch */
+        const char *e = getenv("NBIOT_SCHED");
+        h->q_all = e && !strcmp(e, "queue_all");         /* test knob: every advance, short launches included */
+        if (e && (!strcmp(e, "queue") || h->q_all)) { int rq = nbq_create(&h->q, n_inst, device, 0, g_err, sizeof g_err); if (rq) return rq; }
+    }
     int rc = launch_sim(h, 0, nullptr, -1, 0, st);     /* construct + reset every instance */
     if (rc) return rc;
     *out = h;
@@ -365,6 +338,7 @@ int nbiot_destroy(nbiot_handle_t *h)
     cudaFree(h->conf_dev); cudaFree(h->ctrl_dev); cudaFree(h->lut2_dev); cudaFree(h->mcs_dev); cudaFree(h->seeds_dev); cudaFree(h->counter_dev);
     cudaFree(h->act_dev); cudaFree(h->obs_dev); cudaFree(h->rew_dev); cudaFree(h->items_dev);
     cudaFreeHost(h->act_pin); cudaFreeHost(h->obs_pin); cudaFreeHost(h->rew_pin);
+    nbq_destroy(h->q);
     delete h;
     return 0;
 }
@@ -541,6 +515,13 @@ int nbiot_set_event_log(nbiot_handle_t *h, int32_t *evlog_dev, int cap)
     if (!h) return set_err(NBIOT_E_INVALID, "nbiot_set_event_log: null handle");
     h->evlog = evlog_dev; h->evlog_cap = evlog_dev ? cap : 0;
     return 0;
+}
+
+int nbiot_queue_stats(nbiot_handle_t *h, unsigned long long out[32])
+{
+    if (!h || !out) return set_err(NBIOT_E_INVALID, "nbiot_queue_stats: null argument");
+    if (!h->q) return set_err(NBIOT_E_INVALID, "nbiot_queue_stats: the batch does not use the migrating-instance kernel");
+    return nbq_stats(h->q, out);
 }
 
 long long nbiot_launch_count(nbiot_handle_t *h) { return h ? h->launches : 0; }

@@ -1,0 +1,68 @@
+/*
+ * nbiot_launch.h -- what the two translation units of libnbiot_b200.so share (internal, not part of the C ABI):
+ * the kernel argument block, the staging helpers, and the entry points of the migrating-instance kernel
+ * (nbiot_queue.cu) that nbiot_kernels.cu launches for long advances.
+ */
+#ifndef NBIOT_LAUNCH_H
+#define NBIOT_LAUNCH_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "nbiot_core.cuh"
+
+struct NbKernelArgs {
+    uint8_t *state;
+    NbLayout L;
+    const nbiot_conf_t *conf;
+    const NbCtaConst *ctrl;      /* controller tables + cold configuration */
+    const uint16_t *lut2;
+    const uint8_t *mcs;
+    unsigned int *counter;
+    int32_t *evlog; int evlog_cap;
+    int smem_per_warp, hdr_bytes16, grid_bytes16;
+    int stage_grid;              /* 1: the look-ahead ring is staged in shared memory; 0: used in place in HBM (short launches) */
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void nb_copy16(void *dst, const void *src, int n16)
+{
+    const uint4 *s = (const uint4 *)src; uint4 *d = (uint4 *)dst;
+    for (int i = threadIdx.x & 31; i < n16; i += 32) d[i] = s[i];
+}
+
+__device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int i, const NbCtaConst *s_cc)
+{
+    const NbLayout &L = A.L;
+    uint8_t *s = A.state;
+    for (int k = 0; k < 3; ++k) c.ra[k] = (NbRaEntry *)(s + L.off_ra) + ((size_t)i * 3 + k) * L.ra_cap;
+    c.conn = (NbConnEntry *)(s + L.off_conn) + (size_t)i * L.ue_cap;
+    c.cont = (NbContEntry *)(s + L.off_cont) + (size_t)i * L.ue_cap;
+    c.ue = (NbUe *)(s + L.off_ue) + (size_t)i * L.ue_cap;
+    c.free_stack = (uint16_t *)(s + L.off_free) + (size_t)i * L.ue_cap;
+    c.occ = (NbOccHist *)(s + L.off_occ) + i;
+    c.incoming = (double *)(s + L.off_incoming) + (size_t)i * L.hist_cap;
+    c.delays = (int32_t *)(s + L.off_delays) + (size_t)i * L.hist_cap;
+    c.service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
+    c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
+    c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
+    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = *(const nbiot_conf_hot_t *)A.conf; c.ctrl = &s_cc->ctrl;
+    c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
+    c.evlog = i == 0 ? A.evlog : nullptr; c.evlog_cap = A.evlog_cap;
+    c.grid = A.stage_grid ? (uint16_t *)((unsigned char *)&c + sizeof(NbCtx) + sizeof(NbHdr))
+                          : (uint16_t *)(A.state + A.L.off_grid) + (size_t)i * A.L.n_carriers * A.L.grid_w;
+}
+
+#endif
+
+/* ---- migrating-instance kernel (nbiot_queue.cu) ---- */
+struct NbQueueRt;                                   /* device-side queues of one handle */
+int nbq_create(NbQueueRt **out, int n_inst, int device, int smem_per_warp_nogrid, char *err, size_t err_len);
+void nbq_destroy(NbQueueRt *q);
+/* Controller.step / run_until for every (active) instance, as migrating tasks; same contract as nbiot_sim_kernel */
+int nbq_launch(NbQueueRt *q, const NbKernelArgs &A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps,
+               cudaStream_t st, char *err, size_t err_len);
+/* per-class task counts and cycles of the launches so far (measurement aid): out[0..9] tasks, out[10..19] cycles, out[20] hops, out[21] local continuations, ... */
+int nbq_stats(NbQueueRt *q, unsigned long long out[32]);
+void nbq_geometry(NbQueueRt *q, int *blocks, int *warps_per_block, int *smem_bytes);
+
+#endif /* NBIOT_LAUNCH_H */

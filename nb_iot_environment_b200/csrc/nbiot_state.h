@@ -176,6 +176,12 @@ typedef struct __attribute__((aligned(16))) NbHdr {
     /* ---- pending system events ---- */
     uint64_t pool_free;               /* bit i set: pool[i] is free */
     NbEvent pool[NB_EV_POOL];
+    /* ---- control state between two tasks of the migrating-instance kernel (nbiot_core.cuh "tasks"): the NodeB steps taken
+     *      in this launch, the phase of the controller loop, and the arguments of the event handler that runs next
+     *      (at the end: the offsets of everything the warp-per-instance kernel touches stay what they were) ---- */
+    int32_t tk_steps, tk_phase, tk_a, tk_b;
+    NbOccasion tk_occ;
+    int32_t tk_pad;
 } NbHdr;
 
 /* device-side form of nbiot_ctrl_t (include/nbiot_ctrl.h): write tables as (bit mask, values) */

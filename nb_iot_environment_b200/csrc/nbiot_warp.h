@@ -23,7 +23,7 @@
 
 #define NB_LANES 32
 #define NB_DEV __device__ __forceinline__
-#define NB_FN __device__ __noinline__
+#define NB_FN static __device__ __noinline__
 /* functions with a single call site: NB_INLINE_SINGLE = 0 keeps them out of line, 1 inlines the small ones, 2 all */
 #ifndef NB_INLINE_SINGLE
 #define NB_INLINE_SINGLE 1
@@ -35,32 +35,32 @@
 #if NB_INLINE_MULTI >= 3
 #define NB_FNM3 __device__ __forceinline__
 #else
-#define NB_FNM3 __device__ __noinline__
+#define NB_FNM3 static __device__ __noinline__
 #endif
 #if NB_INLINE_MULTI >= 4
 #define NB_FNM4 __device__ __forceinline__
 #else
-#define NB_FNM4 __device__ __noinline__
+#define NB_FNM4 static __device__ __noinline__
 #endif
 #if NB_INLINE_MULTI >= 1
 #define NB_FNM __device__ __forceinline__
 #else
-#define NB_FNM __device__ __noinline__
+#define NB_FNM static __device__ __noinline__
 #endif
 #if NB_INLINE_MULTI >= 2
 #define NB_FNM2 __device__ __forceinline__
 #else
-#define NB_FNM2 __device__ __noinline__
+#define NB_FNM2 static __device__ __noinline__
 #endif
 #if NB_INLINE_SINGLE >= 1
 #define NB_FN1S __device__ __forceinline__
 #else
-#define NB_FN1S __device__ __noinline__
+#define NB_FN1S static __device__ __noinline__
 #endif
 #if NB_INLINE_SINGLE >= 2
 #define NB_FN1 __device__ __forceinline__
 #else
-#define NB_FN1 __device__ __noinline__
+#define NB_FN1 static __device__ __noinline__
 #endif
 #define NB_FULL 0xFFFFFFFFu
 #define NB_NOUNROLL _Pragma("unroll 1")

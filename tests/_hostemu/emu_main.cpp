@@ -60,6 +60,11 @@ struct Staged {
 extern "C" {
 
 int emu_lanes(void) { return NB_LANES; }
+#ifdef NBIOT_EMU_TASKS
+int emu_tasks(void) { return 1; }
+#else
+int emu_tasks(void) { return 0; }
+#endif
 int emu_hdr_size(void) { return (int)sizeof(NbHdr); }
 
 void *emu_create(const nbiot_conf_t *conf, int n_inst, const uint64_t *seeds, const uint16_t *lut2, const uint8_t *mcs, const nbiot_ctrl_t *ctrl)
@@ -87,11 +92,23 @@ void emu_reset(void *p)
 void emu_advance(void *p, const uint8_t *ext_actions, int until_time, int max_steps, int32_t *steps_out)
 {
     Emu *e = (Emu *)p;
+#ifdef NBIOT_EMU_TASKS
+    // the task chain of the migrating-instance kernel, with the instance stored to and reloaded from the state buffer between
+    // two tasks into a fresh context -- what a hop to another SM does -- so that nothing can survive outside NbHdr
+    for (int i = 0; i < e->L.n_inst; ++i) {
+        const uint8_t *a = ext_actions ? ext_actions + (size_t)i * e->cc.ctrl.ext_k : NULL;
+        int k;
+        { Staged st(e, i, true); st.c->tk_until = until_time; st.c->tk_max_steps = max_steps; k = nbc_task_begin(*st.c, a); }
+        while (k != NB_TK_DONE) { Staged st(e, i, true); st.c->tk_until = until_time; st.c->tk_max_steps = max_steps; k = nbc_task_run(*st.c, k); }
+        if (steps_out) steps_out[i] = ((NbHdr *)(e->state + e->L.off_hdr) + i)->tk_steps;
+    }
+#else
     for (int i = 0; i < e->L.n_inst; ++i) {
         Staged st(e, i, true);
         int s = nbc_controller_advance(*st.c, &e->cc.ctrl, ext_actions ? ext_actions + (size_t)i * e->cc.ctrl.ext_k : NULL, until_time, max_steps);
         if (steps_out) steps_out[i] = s;
     }
+#endif
 }
 
 // statistics histories of instance i: which = 0 delay, 1 connection, 2 access, 3 bits; returns the number recorded

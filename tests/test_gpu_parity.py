@@ -142,6 +142,37 @@ def test_grid_in_place_equals_staged_grid(monkeypatch):
         assert np.array_equal(states[0], s)
 
 
+def test_migrating_instances_equal_warp_per_instance(monkeypatch):
+    """NBIOT_SCHED=queue_all: every advance runs on the migrating-instance kernel (csrc/nbiot_queue.cu: the control flow cut
+    into tasks, cells handed between SMs through per-class queues). Same states as the warp-per-instance kernel, bit for bit,
+    on short launches (external scheduling agent, 2 carriers) and on a long one; only the task-control words at the end of the
+    header, which the warp-per-instance kernel never writes, may differ."""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv, _cabi
+    hdr = _cabi.load().nbiot_hdr_bytes()
+    states = []
+    for sched in (None, 'queue_all'):
+        if sched is None:
+            monkeypatch.delenv('NBIOT_SCHED', raising=False)
+        else:
+            monkeypatch.setenv('NBIOT_SCHED', sched)
+        N = 700                                                 # more cells than one wave of workers on a few SMs, ragged
+        env = BatchedNBIoTEnv(CFG3, agents_conf=NPUSCH_AGENTS, ext_agent=0, num_envs=N, seeds=list(range(N)), n_carriers=2, ue_cap=512, grid_w=2048, hist_cap=64)
+        env.reset()
+        r = np.random.default_rng(5)
+        for _ in range(60):
+            env.step(_random_ext_actions(r, env.action_nvec, N))
+        env.run_until(6000)
+        torch.cuda.synchronize()
+        st = env.state.cpu().numpy().copy()
+        h = st[:N * hdr].reshape(N, hdr)
+        h[:, hdr - 32:] = 0                                     # NbHdr.tk_*
+        states.append(st)
+        assert env.stats()['faulted'] == 0
+        env.close()
+    assert np.array_equal(states[0], states[1])
+
+
 def _random_ext_actions(rng, nvec, n):
     return np.stack([rng.integers(0, m, size=n) for m in nvec], axis=1).astype(np.uint8)
 

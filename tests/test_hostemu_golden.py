@@ -52,3 +52,10 @@ def test_core_scalar_logic(case, oracle_lib):
 @pytest.mark.parametrize('case', ['cfg1_default', 'cfg4_two_carriers_bursty', 'overload'])
 def test_core_lane_parallel_sections(case, oracle_lib):
     _replay(case, 32, 400)
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_core_task_chain(case, oracle_lib):
+    """The same core cut into tasks (nbiot_core.cuh "tasks"), the instance stored and reloaded between two tasks:
+    the control flow of the migrating-instance kernel, against the same golden traces."""
+    _replay(case, '1t', 10 ** 9)
