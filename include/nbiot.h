@@ -73,6 +73,9 @@ const char *nbiot_last_error(void);
  * and keeps ownership: the buffer is the complete simulation state, so saving it is a checkpoint. */
 size_t nbiot_state_bytes(const nbiot_conf_t *conf, int n_inst);
 size_t nbiot_hdr_bytes(void);
+/* trailing bytes of each header that hold the task-control words of the migrating-instance kernel (NBIOT_SCHED=queue); only that
+ * kernel writes them, everything else in the state buffer is independent of the kernel that produced it */
+size_t nbiot_hdr_task_bytes(void);
 
 /* replaces create_system(rng, conf) + Controller(node, agents) for n_inst cells
  * (system/system_creator.py:22-59, controller.py:30-41). seeds/lut2/mcs are host pointers:

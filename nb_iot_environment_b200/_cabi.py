@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('NBIOT_LIB') or os.path.join(_HERE, 'libnbiot_b200.so')   # NBIOT_LIB: an alternative build (tuning experiments)
 
 # every symbol include/nbiot.h declares
-SYMBOLS = ['nbiot_abi_version', 'nbiot_last_error', 'nbiot_state_bytes', 'nbiot_hdr_bytes', 'nbiot_create', 'nbiot_destroy',
+SYMBOLS = ['nbiot_abi_version', 'nbiot_last_error', 'nbiot_state_bytes', 'nbiot_hdr_bytes', 'nbiot_hdr_task_bytes', 'nbiot_create', 'nbiot_destroy',
            'nbiot_set_controller', 'nbiot_reset', 'nbiot_advance', 'nbiot_advance_masked', 'nbiot_records_ptr', 'nbiot_hist_ptrs', 'nbiot_gather_obs',
            'nbiot_reduce_stats', 'nbiot_step_host', 'nbiot_stat_ptrs', 'nbiot_stat_counts', 'nbiot_stat_histogram', 'nbiot_set_event_log', 'nbiot_launch_count', 'nbiot_launch_geometry', 'nbiot_queue_stats',
            'nbiot_rng_u01', 'nbiot_rng_pair', 'nbiot_rng_normal', 'nbiot_rng_bounded',
@@ -61,6 +61,8 @@ def load():
     L.nbiot_state_bytes.restype = ctypes.c_size_t
     L.nbiot_state_bytes.argtypes = [ctypes.POINTER(NbiotConf), i32]
     L.nbiot_hdr_bytes.restype = ctypes.c_size_t
+    if hasattr(L, 'nbiot_hdr_task_bytes'):
+        L.nbiot_hdr_task_bytes.restype = ctypes.c_size_t
     L.nbiot_create.argtypes = [ctypes.POINTER(NbiotConf), i32, i32, vp, ctypes.c_size_t, vp, vp, vp, ctypes.POINTER(NbiotCtrl), vp, ctypes.POINTER(vp)]
     L.nbiot_destroy.argtypes = [vp]
     L.nbiot_set_controller.argtypes = [vp, ctypes.POINTER(NbiotCtrl), vp]

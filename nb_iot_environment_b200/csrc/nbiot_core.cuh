@@ -60,6 +60,18 @@ struct __attribute__((aligned(16))) NbCtx {
 #endif
 };
 
+/* specialised builds: NB_FIXED_C = 1 compiles the carrier loops for single-carrier cells, NB_NO_EVLOG drops the debug event log */
+#ifdef NB_FIXED_C
+#define NB_NC(c) NB_FIXED_C
+#else
+#define NB_NC(c) ((c).C)
+#endif
+#ifdef NB_NO_EVLOG
+#define NB_EVLOG(c) ((int32_t *)0)
+#else
+#define NB_EVLOG(c) ((c).evlog)
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define NB_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 #else
@@ -253,7 +265,7 @@ NB_DEV void nbc_sclog_register(NbCtx &c, int t, int ce, int sc)   /* carrier.py:
 NB_DEV int nbc_sclog_check(NbCtx &c, int t, int ce)               /* carrier.py:267-271, :454-459 */
 {
     NbHdr *h = nbc_hdr(c);
-    if (c.C == 1 || t == 0) return 0;
+    if (NB_NC(c) == 1 || t == 0) return 0;
     int n = h->sclog_n < NB_SCLOG ? h->sclog_n : NB_SCLOG;
     NB_NOUNROLL
     for (int i = 0; i < n; ++i) if (h->sclog_t[i] == t) return h->sclog_sc[i][ce];
@@ -270,10 +282,10 @@ NB_FN void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
     if (b - h->t_now > c.W) { NB_FAULT(c, NBIOT_FAULT_LOOKAHEAD); return; }
     /* fresh columns start empty */
     NB_NOUNROLL
-    for (int cc = 0; cc < c.C; ++cc) nbc_grid_update(c, cc, a, b - a, 0u, 0);
+    for (int cc = 0; cc < NB_NC(c); ++cc) nbc_grid_update(c, cc, a, b - a, 0u, 0);
     int cursor[2][3];
     NB_NOUNROLL
-    for (int cc = 0; cc < c.C; ++cc)
+    for (int cc = 0; cc < NB_NC(c); ++cc)
         NB_NOUNROLL
         for (int ce = 0; ce < 3; ++ce) {
             NbResource &r = h->res[cc][ce];
@@ -289,7 +301,7 @@ NB_FN void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
         /* earliest start in (column, carrier, CE) order */
         int best = b, bc = -1, bce = -1;
         NB_NOUNROLL
-        for (int cc = 0; cc < c.C; ++cc)
+        for (int cc = 0; cc < NB_NC(c); ++cc)
             NB_NOUNROLL
             for (int ce = 0; ce < 3; ++ce) {
                 NbResource &r = h->res[cc][ce];
@@ -341,7 +353,7 @@ NB_FNM4 int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int
         }
         int from = h->t_now + d;
         NB_NOUNROLL
-        for (int ci = 0; ci < c.C; ++ci) {
+        for (int ci = 0; ci < NB_NC(c); ++ci) {
             int cc = ci == 0 ? carrier_id : (carrier_id == 0 ? 1 : 0);
             uint32_t busy = nbc_grid_busy(c, cc, from, N_sf);
             /* first free aligned group of N_sc subcarriers (offsets_per_sc, carrier.py:29-34): fold the
@@ -461,7 +473,7 @@ NB_FN1 void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int
     if (th_C1 == 0) { periods[1] = nb_nprach_period_list[0]; N_sfs[1] = 0; N_scs[1] = 0; }
     int per_carrier[2][3];
     NB_NOUNROLL
-    for (int cc = 0; cc < c.C; ++cc)
+    for (int cc = 0; cc < NB_NC(c); ++cc)
         NB_NOUNROLL
         for (int i = 0; i < 3; ++i) {
             int take = N_scs[i] < 12 ? N_scs[i] : 12;
@@ -471,7 +483,7 @@ NB_FN1 void nbc_carrier_update_ra(NbCtx &c, const int args[3][3], int th_C1, int
     int sc_off[3], sf_off[3];
     (void)nbc_compute_offsets(periods, N_sfs, per_carrier[0], sc_off, sf_off);   /* validity ignored (carrier.py:638) */
     NB_NOUNROLL
-    for (int cc = 0; cc < c.C; ++cc)
+    for (int cc = 0; cc < NB_NC(c); ++cc)
         NB_NOUNROLL
         for (int ce = 0; ce < 3; ++ce) {
             int rt = h->res[cc][0].t_start;
@@ -1154,7 +1166,7 @@ struct NbSched { int carrier, i, I_tbs, delay, N_sc, N_rep, N_ru; };
 
 NB_DEV int nbc_scheduling_action(NbCtx &c, const uint8_t *a, int RAR_action, NbSched *p)   /* action_reader.py:25-66 */
 {
-    if (a[NB_A_CARRIER] >= c.C || a[NB_A_NREP] > 7 || a[NB_A_DELAY] > 3 || a[NB_A_SC] > 3) { NB_FAULT(c, NBIOT_FAULT_ACTION); return 0; }
+    if (a[NB_A_CARRIER] >= NB_NC(c) || a[NB_A_NREP] > 7 || a[NB_A_DELAY] > 3 || a[NB_A_SC] > 3) { NB_FAULT(c, NBIOT_FAULT_ACTION); return 0; }
     p->carrier = a[NB_A_CARRIER]; p->i = a[NB_A_ID]; p->N_ru = a[NB_A_NRU];
     p->N_rep = nb_n_rep_list[a[NB_A_NREP] & 7];
     int I_mcs = a[NB_A_IMCS];
@@ -1319,7 +1331,7 @@ NB_FN1 void nbc_step_update(NbCtx &c, const uint8_t *a)          /* node_b.py:69
     int conf[16];
     NB_NOUNROLL
     for (int i = 0; i < 16; ++i) conf[i] = a[nb_nprach_item_idx[i]];
-    int sc_max = c.C == 1 ? 3 : 7;
+    int sc_max = NB_NC(c) == 1 ? 3 : 7;
     if (conf[1] > 7 || conf[2] > 7 || conf[3] > 10 || conf[4] > 15 || conf[5] > 14 || conf[6] > 14 || conf[7] > 6 || conf[10] > 6 ||
         conf[13] > 6 || conf[9] > sc_max || conf[12] > sc_max || conf[15] > sc_max) { NB_FAULT(c, NBIOT_FAULT_ACTION); return; }
     int th_C1 = nb_threshold_list[conf[5]], th_C0 = nb_threshold_list[conf[6]];
@@ -1357,11 +1369,28 @@ NB_FN1S uint64_t nbc_next_event(NbCtx &c, int *code)
     nbw_run([&]() -> int {
         nbw_sync();
         uint64_t k = NB_KEY_NONE; int cd = -1;
+#if NB_LANES == 32
+        /* one key per lane covers the fixed slots and pool[0 .. 32 - NB_FIXED_KEYS); the pool hands out its lowest free entry, so
+         * the entries above that are in use only when more than 22 events are pending: a second pass then, and only then */
+        {
+            int j = nbw_lane();
+            uint64_t kj = j < NB_FIXED_KEYS ? h->keys[j] : h->pool[j - NB_FIXED_KEYS].key;
+            if (kj < k) { k = kj; cd = j < NB_FIXED_KEYS ? j : j + (16 - NB_FIXED_KEYS); }
+            if ((~h->pool_free & ((1ULL << NB_EV_POOL) - 1ULL)) >> (32 - NB_FIXED_KEYS)) {
+                j += 32;
+                if (j < NB_FIXED_KEYS + NB_EV_POOL) {
+                    kj = h->pool[j - NB_FIXED_KEYS].key;
+                    if (kj < k) { k = kj; cd = j + (16 - NB_FIXED_KEYS); }
+                }
+            }
+        }
+#else
         NB_NOUNROLL
         for (int j = nbw_lane(); j < NB_FIXED_KEYS + NB_EV_POOL; j += NB_LANES) {
             uint64_t kj = j < NB_FIXED_KEYS ? h->keys[j] : h->pool[j - NB_FIXED_KEYS].key;
             if (kj < k) { k = kj; cd = j < NB_FIXED_KEYS ? j : j + (16 - NB_FIXED_KEYS); }
         }
+#endif
         uint64_t m = nbw_min_u64(k);
         uint32_t who = nbw_ballot(k == m && cd >= 0);
         int src = who ? nbw_ffs(who) - 1 : 0;
@@ -1392,7 +1421,7 @@ NB_FN void nbc_advance_fel(NbCtx &c)
         h->time = t; h->cur_key = key;
         nbc_erase_past_sf(c, t);                               /* carrier_set.step(t) */
         if (NB_FATAL(c)) return;
-        if (c.evlog) nbc_log_event(c, t, code);
+        if (NB_EVLOG(c)) nbc_log_event(c, t, code);
         h->events += 1;
         if (code == 0) {
             h->keys[0] = NB_KEY_NONE;
@@ -1530,7 +1559,7 @@ NB_FNM4 void nbc_node_info(NbCtx &c, int write_record, double reward)
     else if (h->state == NB_ST_NPRACH_UPDATE && h->time != 0) {
         /* PerfMonitor.estimate_carrier_resources (perf_monitor.py:204-222) */
         int period = h->time - h->perf_t;
-        int64_t total = 12LL * c.C * period;
+        int64_t total = 12LL * NB_NC(c) * period;
         int64_t signalling = h->NPRACH_resources + h->msg3_resources;
         if (write_record) {
             occ_nprach = NB_DIV((double)h->NPRACH_resources, (double)total);
@@ -1740,7 +1769,7 @@ NB_FN int nbc_fel_next(NbCtx &c)
         h->time = t; h->cur_key = key;
         nbc_erase_past_sf(c, t);                               /* carrier_set.step(t) */
         if (NB_FATAL(c)) return 0;
-        if (c.evlog) nbc_log_event(c, t, code);
+        if (NB_EVLOG(c)) nbc_log_event(c, t, code);
         h->events += 1;
         if (code == 0) {
             h->keys[0] = NB_KEY_NONE;

@@ -18,6 +18,7 @@
  * see DESIGN.md).
  */
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,20 +27,6 @@
 #include "nbiot.h"
 #include "nbiot_core.cuh"
 #include "nbiot_launch.h"
-
-#ifndef NB_WPB
-#define NB_WPB 4   /* warps (instances in flight) per CTA */
-#endif
-/* The hot kernel is built twice: MINB = 7 (72 registers: the budget that lets 7 CTAs = 28 warps live on an SM, which is what the
- * shared-memory slice of a grid_w = 2048 instance allows) and MINB = 9 (56 registers, 36 warps: what a grid_w = 1024 slice allows).
- * Instruction supply, not registers, bounds this kernel (profiles/r01_icache.txt), so the extra warps win wherever shared memory
- * lets them be resident: +11 % on the config-5 sweep. nbiot_create picks the build with the most resident warps for the batch. */
-#ifndef NB_MIN_CTAS_LO
-#define NB_MIN_CTAS_LO 7
-#endif
-#ifndef NB_MIN_CTAS_HI
-#define NB_MIN_CTAS_HI 9
-#endif
 
 struct nbiot_handle {
     nbiot_conf_t conf;
@@ -55,6 +42,8 @@ struct nbiot_handle {
     unsigned int *counter_dev;
     int blocks, smem_bytes, sim_hi;
     int blocks_short, smem_short, sim_hi_short, stage_policy;     /* geometry of launches that leave the grid in HBM */
+    NbSimVariant k_gen, k_c1;    /* builds of the warp-per-instance kernels (nbiot_simk.cuh) */
+    int use_c1;                  /* single-carrier batch: the c1 build (the generic one while an event log is attached) */
     int q_all;                   /* test knob: short launches too */
     NbQueueRt *q;                /* migrating-instance kernel (nbiot_queue.cu) for long launches; NULL: warp-per-instance kernel */
     long long launches;
@@ -71,59 +60,9 @@ static int set_err(int code, const char *fmt, const char *a = "", const char *b 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(NBIOT_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
 /* ------------------------------------------------------------------ device side */
-/* Claim instances from the work counter; stage [ctx | header | grid] in this warp's shared-memory slice;
- * run `body`; write header and grid back. */
-template <bool LOAD, class Body>
-__device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, const uint8_t *active, Body body)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ NbCtaConst s_ctrl;                      /* the controller tables + cold configuration, once per CTA */
-    for (int k = threadIdx.x; k < (int)(sizeof(NbCtaConst) / 4); k += blockDim.x) ((uint32_t *)&s_ctrl)[k] = ((const uint32_t *)A.ctrl)[k];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *my = smem + (size_t)warp * A.smem_per_warp;
-    NbCtx &c = *(NbCtx *)my;
-    unsigned char *hdr_s = my + sizeof(NbCtx), *grid_s = hdr_s + sizeof(NbHdr);
-    NbHdr *hdr_g = (NbHdr *)(A.state + A.L.off_hdr);
-    uint16_t *grid_g = (uint16_t *)(A.state + A.L.off_grid);
-    const size_t grid_elems = (size_t)A.L.n_carriers * A.L.grid_w;
-    for (;;) {
-        int i = 0;
-        if (lane == 0) i = (int)atomicAdd(A.counter, 1u);
-        i = __shfl_sync(0xFFFFFFFFu, i, 0);
-        if (i >= A.L.n_inst) break;
-        if (active && !active[i]) continue;
-        if (lane == 0) nb_fill_ctx(c, A, i, &s_ctrl);
-        if (LOAD) {
-            nb_copy16(hdr_s, hdr_g + i, A.hdr_bytes16);
-            if (A.stage_grid) nb_copy16(grid_s, grid_g + (size_t)i * grid_elems, A.grid_bytes16);
-        }
-        __syncwarp();
-        body(c, i);
-        __syncwarp();
-        nb_copy16(hdr_g + i, hdr_s, A.hdr_bytes16);
-        if (A.stage_grid) nb_copy16(grid_g + (size_t)i * grid_elems, grid_s, A.grid_bytes16);
-        __syncwarp();
-    }
-}
-
-/* the hot kernel: Controller.step / run_until for every instance */
-template <int MINB>
-__global__ void __launch_bounds__(NB_WPB * 32, MINB)
-nbiot_sim_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps)
-{
-    nb_for_each_instance<true>(A, active, [&](NbCtx &c, int i) {
-        nbc_controller_advance(c, c.ctrl, ext_actions ? ext_actions + (size_t)i * c.ctrl->ext_k : nullptr, until_time, max_steps);
-    });
-}
-
-/* create_system + NodeB.reset (construct = 1) or NodeB.reset alone */
-__global__ void __launch_bounds__(NB_WPB * 32)
-nbiot_reset_kernel(NbKernelArgs A, int construct, const uint64_t *seeds)
-{
-    if (construct) nb_for_each_instance<false>(A, nullptr, [&](NbCtx &c, int i) { nbc_construct(c, seeds[i], c.ctrl); nbc_reset(c); });
-    else nb_for_each_instance<true>(A, nullptr, [&](NbCtx &c, int) { nbc_reset(c); });
-}
+/* the simulation kernels live in nbiot_simk.cuh: this translation unit holds their generic build (1 or 2 carriers, event log) */
+#define NB_SIM_VARIANT generic
+#include "nbiot_simk.cuh"
 
 /* Controller.get_obs (controller.py:105-120) for the whole batch: one thread per (instance, obs element) */
 __global__ void nbiot_obs_kernel(const nbiot_record_t *rec, int n_inst, const nbiot_obs_item_t *items, int n_items, int obs_dim,
@@ -213,6 +152,8 @@ static NbKernelArgs make_args(nbiot_handle_t *h, int stage_grid = 1)
     return A;
 }
 
+static const NbSimVariant *sim_variant(const nbiot_handle_t *h) { return h->use_c1 && !h->evlog ? &h->k_c1 : &h->k_gen; }
+
 static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, int until_time, int max_steps, cudaStream_t st, const uint8_t *active = nullptr)
 {
     CK(cudaSetDevice(h->device));
@@ -229,9 +170,16 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
         if (rc) return rc;
         h->launches += 1;                              /* the queue-initialisation kernel */
     }
-    else if (mode == 2 && hi) nbiot_sim_kernel<NB_MIN_CTAS_HI><<<blocks, NB_WPB * 32, smem, st>>>(A, ext_actions, active, until_time, max_steps);
-    else if (mode == 2) nbiot_sim_kernel<NB_MIN_CTAS_LO><<<blocks, NB_WPB * 32, smem, st>>>(A, ext_actions, active, until_time, max_steps);
-    else nbiot_reset_kernel<<<h->blocks, NB_WPB * 32, h->smem_bytes, st>>>(A, mode == 0 ? 1 : 0, h->seeds_dev);
+    else if (mode == 2) {
+        const NbSimVariant *v = sim_variant(h);
+        void *args[] = { (void *)&A, (void *)&ext_actions, (void *)&active, (void *)&until_time, (void *)&max_steps };
+        CK(cudaLaunchKernel(hi ? v->sim_hi : v->sim_lo, dim3(blocks), dim3(NB_WPB * 32), args, (size_t)smem, st));
+    } else {
+        int construct = mode == 0 ? 1 : 0;
+        const uint64_t *seeds = h->seeds_dev;
+        void *args[] = { (void *)&A, (void *)&construct, (void *)&seeds };
+        CK(cudaLaunchKernel(sim_variant(h)->reset, dim3(h->blocks), dim3(NB_WPB * 32), args, (size_t)h->smem_bytes, st));
+    }
     CK(cudaGetLastError());
     h->launches += 1;
     return 0;
@@ -248,6 +196,7 @@ size_t nbiot_state_bytes(const nbiot_conf_t *conf, int n_inst)
     return (size_t)nb_make_layout(conf, n_inst).total;
 }
 size_t nbiot_hdr_bytes(void) { return sizeof(NbHdr); }
+size_t nbiot_hdr_task_bytes(void) { return sizeof(NbHdr) - offsetof(NbHdr, tk_steps); }
 
 int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_dev, size_t state_bytes,
                  const uint64_t *seeds, const uint16_t *lut2, const uint8_t *mcs, const struct nbiot_ctrl *ctrl,
@@ -289,13 +238,17 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if ((size_t)h->smem_bytes > prop.sharedMemPerBlockOptin) return set_err(NBIOT_E_INVALID, "grid_w too large for the shared memory of one CTA");
-    CK(cudaFuncSetAttribute(nbiot_sim_kernel<NB_MIN_CTAS_LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-    CK(cudaFuncSetAttribute(nbiot_sim_kernel<NB_MIN_CTAS_HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-    CK(cudaFuncSetAttribute(nbiot_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    nb_sim_variant_generic(&h->k_gen); nb_sim_variant_c1(&h->k_c1);
+    h->use_c1 = L.n_carriers == 1;
+    if (const char *e = getenv("NBIOT_SIM_VARIANT")) h->use_c1 = h->use_c1 && strcmp(e, "generic") != 0;   /* measurement knob */
+    for (const NbSimVariant *v : { &h->k_gen, &h->k_c1 })
+        for (const void *f : { v->sim_lo, v->sim_hi, v->reset })
+            CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    const NbSimVariant *kv = h->use_c1 ? &h->k_c1 : &h->k_gen;       /* both builds have the same launch bounds and register budgets */
     int per_sm = 0;
     int per_sm_hi = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nbiot_sim_kernel<NB_MIN_CTAS_LO>, NB_WPB * 32, h->smem_bytes));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_hi, nbiot_sim_kernel<NB_MIN_CTAS_HI>, NB_WPB * 32, h->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kv->sim_lo, NB_WPB * 32, h->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_hi, kv->sim_hi, NB_WPB * 32, h->smem_bytes));
     /* the leaner-register build only when it really puts more CTAs on an SM AND the batch has the instances to fill them */
     h->sim_hi = per_sm_hi > per_sm && (long long)n_inst > (long long)prop.multiProcessorCount * per_sm * NB_WPB;
     if (const char *e = getenv("NBIOT_SIM_BUILD")) h->sim_hi = !strcmp(e, "hi");      /* measurement knob: "lo" / "hi" */
@@ -306,8 +259,8 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
         NbKernelArgs B = make_args(h, 0);
         h->smem_short = NB_WPB * B.smem_per_warp;
         int lo = 0, hi2 = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lo, nbiot_sim_kernel<NB_MIN_CTAS_LO>, NB_WPB * 32, h->smem_short));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hi2, nbiot_sim_kernel<NB_MIN_CTAS_HI>, NB_WPB * 32, h->smem_short));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lo, kv->sim_lo, NB_WPB * 32, h->smem_short));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hi2, kv->sim_hi, NB_WPB * 32, h->smem_short));
         h->sim_hi_short = hi2 > lo && (long long)n_inst > (long long)prop.multiProcessorCount * lo * NB_WPB;
         if (const char *e = getenv("NBIOT_SIM_BUILD")) h->sim_hi_short = !strcmp(e, "hi");
         int ps = h->sim_hi_short ? hi2 : lo; if (ps < 1) ps = 1;

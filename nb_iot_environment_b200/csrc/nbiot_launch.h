@@ -54,6 +54,11 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
 
 #endif
 
+/* ---- builds of the warp-per-instance kernels (nbiot_simk.cuh) ---- */
+struct NbSimVariant { const void *sim_lo, *sim_hi, *reset; int warps_per_block; };
+void nb_sim_variant_generic(NbSimVariant *out);
+void nb_sim_variant_c1(NbSimVariant *out);
+
 /* ---- migrating-instance kernel (nbiot_queue.cu) ---- */
 struct NbQueueRt;                                   /* device-side queues of one handle */
 int nbq_create(NbQueueRt **out, int n_inst, int device, int smem_per_warp_nogrid, char *err, size_t err_len);

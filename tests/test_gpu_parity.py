@@ -149,7 +149,7 @@ def test_migrating_instances_equal_warp_per_instance(monkeypatch):
     header, which the warp-per-instance kernel never writes, may differ."""
     import torch
     from nb_iot_environment_b200 import BatchedNBIoTEnv, _cabi
-    hdr = _cabi.load().nbiot_hdr_bytes()
+    hdr, tk = _cabi.load().nbiot_hdr_bytes(), _cabi.load().nbiot_hdr_task_bytes()
     states = []
     for sched in (None, 'queue_all'):
         if sched is None:
@@ -166,7 +166,7 @@ def test_migrating_instances_equal_warp_per_instance(monkeypatch):
         torch.cuda.synchronize()
         st = env.state.cpu().numpy().copy()
         h = st[:N * hdr].reshape(N, hdr)
-        h[:, hdr - 32:] = 0                                     # NbHdr.tk_*
+        h[:, hdr - tk:] = 0                                     # NbHdr.tk_*
         states.append(st)
         assert env.stats()['faulted'] == 0
         env.close()

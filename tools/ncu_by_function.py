@@ -6,11 +6,11 @@ executed instructions, stall samples and the share of samples that are instructi
 import csv, os, re, subprocess, sys, tempfile, bisect
 src = sys.argv[1]
 lib = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'nb_iot_environment_b200', 'libnbiot_b200.so')
-KERNEL = os.environ.get('NBIOT_PROFILE_KERNEL', 'nbiot_sim_kernelILi7')   # the 72-register build (bench workload)
+KERNEL = os.environ.get('NBIOT_PROFILE_KERNEL', 'nbk_c116nbiot_sim_kernelILi7')   # the 72-register build (bench workload)
 d = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=d, capture_output=True)
-cub = [f for f in os.listdir(d) if f.endswith('.cubin')][-1]
-txt = subprocess.run(['nvdisasm', '-c', os.path.join(d, cub)], capture_output=True, text=True).stdout
+cubs = sorted(f for f in os.listdir(d) if f.endswith('.cubin'))      # one per translation unit of the library
+txt = '\n'.join(subprocess.run(['nvdisasm', '-c', os.path.join(d, cub)], capture_output=True, text=True).stdout for cub in cubs)
 # function start offsets inside the sim kernel's section
 starts, names, insec, cur = [], [], False, None
 for line in txt.splitlines():

@@ -3,11 +3,11 @@
 usage: python tools/sass_sizes.py [path/to/lib.so] [kernel substring]"""
 import os, re, subprocess, sys, tempfile
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'nb_iot_environment_b200', 'libnbiot_b200.so')
-want = sys.argv[2] if len(sys.argv) > 2 else 'nbiot_sim_kernelILi7'
+want = sys.argv[2] if len(sys.argv) > 2 else 'nbk_c116nbiot_sim_kernelILi7'
 d = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=d, capture_output=True)
-cub = [f for f in os.listdir(d) if f.endswith('.cubin')][-1]
-txt = subprocess.run(['nvdisasm', '-c', os.path.join(d, cub)], capture_output=True, text=True).stdout
+cubs = sorted(f for f in os.listdir(d) if f.endswith('.cubin'))      # one per translation unit of the library
+txt = '\n'.join(subprocess.run(['nvdisasm', '-c', os.path.join(d, cub)], capture_output=True, text=True).stdout for cub in cubs)
 cur, sizes, order = None, {}, []
 for line in txt.splitlines():
     m = re.match(r'^(\$?[\w\$\.]+):\s*$', line.strip())
