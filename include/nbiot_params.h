@@ -80,6 +80,8 @@ NB_CONST uint8_t nb_sf_delay_list[4] = { 8, 16, 32, 64 };                   /* p
 NB_CONST uint8_t nb_n_sc_list[4] = { 3, 6, 9, 12 };
 /* N_sc_selection_list (parameters.py:260-265), rows for N_sc = 1,3,6,12 */
 NB_CONST uint8_t nb_sc_fallback[4][3] = { { 12, 6, 3 }, { 12, 6, 1 }, { 12, 3, 1 }, { 6, 3, 1 } };
+/* lowest subcarrier of every aligned group of 1 / 3 / 6 / 12 subcarriers (offsets_per_sc, carrier.py:29-34), as a 12-bit mask */
+NB_CONST uint16_t nb_sc_heads[4] = { 0xFFFu, 0x249u, 0x041u, 0x001u };
 
 /* TBS_table rows for I_tbs = 0,1,2,3,4,6,8 (parameters.py:291-310) */
 NB_CONST uint16_t nb_tbs_table[7][8] = {

@@ -72,6 +72,14 @@ struct __attribute__((aligned(16))) NbCtx {
 #define NB_EVLOG(c) ((c).evlog)
 #endif
 
+/* NBIOT_EMU_COUNTERS (tests/_hostemu only): how often the first-fit search does what */
+#if defined(NBIOT_EMU_COUNTERS) && !defined(__CUDACC__)
+static long long nb_dbg_count[16];
+#define NB_COUNT(i, n) (nb_dbg_count[i] += (n))
+#else
+#define NB_COUNT(i, n) ((void)0)
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define NB_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 #else
@@ -344,10 +352,14 @@ NB_FNM4 int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int
     NbHdr *h = nbc_hdr(c);
     nbc_erase_past_sf(c, t);
     if (NB_FATAL(c)) return 0;
+    const int row = N_sc == 1 ? 0 : N_sc == 3 ? 1 : N_sc == 6 ? 2 : 3;      /* once per call: the loops below only index with it */
+    NB_COUNT(0, 1); NB_COUNT(5, t + 64 + N_sf <= h->t_ahead);
     NB_NOUNROLL
     for (int d = delay; d <= 64; d *= 2) {
         int new_t_ahead = t + d + N_sf;
+        NB_COUNT(1, 1); NB_COUNT(2, N_sf); NB_COUNT(6, d == delay);
         if (new_t_ahead > h->t_ahead) {
+            NB_COUNT(3, 1);
             nbc_extend_lookahead(c, new_t_ahead);
             if (NB_FATAL(c)) return 0;
         }
@@ -359,12 +371,12 @@ NB_FNM4 int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int
             /* first free aligned group of N_sc subcarriers (offsets_per_sc, carrier.py:29-34): fold the
              * group's bits onto its lowest one, then take the lowest clear group bit */
             uint32_t fold = busy;
-            if (N_sc >= 3) fold |= (busy >> 1) | (busy >> 2);
-            if (N_sc >= 6) fold |= fold >> 3;
-            if (N_sc == 12) fold |= fold >> 6;
-            uint32_t heads = N_sc == 1 ? 0xFFFu : N_sc == 3 ? 0x249u : N_sc == 6 ? 0x041u : 0x001u;
-            uint32_t pick = ~fold & heads;
+            if (row >= 1) fold |= (busy >> 1) | (busy >> 2);
+            if (row >= 2) fold |= fold >> 3;
+            if (row == 3) fold |= fold >> 6;
+            uint32_t pick = ~fold & nb_sc_heads[row];
             if (pick) {
+                NB_COUNT(4, 1); NB_COUNT(7, d == delay);
                 nbc_grid_or(c, cc, from, N_sf, ((1u << N_sc) - 1u) << (nbw_ffs(pick) - 1));
                 return new_t_ahead;
             }
@@ -379,7 +391,9 @@ NB_FNM3 int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc
     int spr = nbc_sf_per_ru(N_sc);
     if (spr < 0) { NB_FAULT(c, NBIOT_FAULT_ACTION); *out_sc = N_sc; *out_sf = 0; return 0; }
     int n_sc = N_sc, N_sf = spr * N_ru * N_rep;
+    NB_COUNT(8, 1);
     int t_ul_end = nbc_carrier_allocate(c, c_id, ref_t, delay, N_sc, N_sf);
+    NB_COUNT(9, t_ul_end != 0);
     if (!t_ul_end && c.conf.sc_adjustment && !NB_FATAL(c)) {
         int row = N_sc == 1 ? 0 : N_sc == 3 ? 1 : N_sc == 6 ? 2 : 3;
         NB_NOUNROLL

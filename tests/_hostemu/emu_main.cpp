@@ -65,6 +65,9 @@ int emu_tasks(void) { return 1; }
 #else
 int emu_tasks(void) { return 0; }
 #endif
+#ifdef NBIOT_EMU_COUNTERS
+void emu_debug_counts(long long out[16]) { for (int i = 0; i < 16; ++i) out[i] = nb_dbg_count[i]; }
+#endif
 int emu_hdr_size(void) { return (int)sizeof(NbHdr); }
 
 void *emu_create(const nbiot_conf_t *conf, int n_inst, const uint64_t *seeds, const uint16_t *lut2, const uint8_t *mcs, const nbiot_ctrl_t *ctrl)

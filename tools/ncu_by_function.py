@@ -24,7 +24,7 @@ for line in txt.splitlines():
     if m and cur and insec:
         starts.append(int(m.group(1), 16)); names.append(cur); cur = None
 def pretty(n):
-    n2 = re.sub(r'^\$_Z\d+nbiot_sim_kernel[^$]*\$', '', n)
+    n2 = n.split('$')[-1] if n.startswith('$_Z') else n        # $<kernel>$<function>
     out = subprocess.run(['c++filt', n2], capture_output=True, text=True).stdout.strip()
     out = re.sub(r'_INTERNAL_\w+::', '', out)
     return re.sub(r'\(.*', '', out)[:40]

@@ -19,7 +19,7 @@ for line in txt.splitlines():
     if cur and re.match(r'^\s+/\*[0-9a-f]{4,}\*/', line):
         sizes[cur] += 16
 def pretty(n):
-    n = re.sub(r'^\$_Z\d+\w+?\$', '', n) if n.startswith('$_Z') else n
+    n = n.split('$')[-1] if n.startswith('$_Z') else n        # $<kernel>$<function>
     try:
         return subprocess.run(['c++filt', n], capture_output=True, text=True).stdout.strip()[:90]
     except Exception:
