@@ -87,7 +87,20 @@ static long long nb_dbg_count[16];
 #endif
 NB_DEV NbHdr *nbc_hdr(NbCtx &c) { NbHdr *h = (NbHdr *)((char *)&c + sizeof(NbCtx)); NB_ASSUME_SHARED(h); return h; }
 NB_DEV const NbColdConf *nbc_cold(NbCtx &c) { return &((const NbCtaConst *)c.ctrl)->cold; }
+/* NB_GRID_STAGED: a build that only runs with the look-ahead ring staged behind the header (long launches): the ring is reached from the
+ * context pointer with constant offsets and shared-memory loads, not through a generic pointer that may also point into HBM */
+#ifdef NB_GRID_STAGED
+NB_DEV uint16_t *nbc_grid(NbCtx &c)
+{
+    /* through an integer: the ring lies beyond the NbHdr object behind the context, and pointer arithmetic past an object is
+     * not something the optimiser has to honour (it folded these loads to zero) */
+    uint16_t *g = (uint16_t *)((uintptr_t)&c + sizeof(NbCtx) + sizeof(NbHdr));
+    NB_ASSUME_SHARED(g);
+    return g;
+}
+#else
 NB_DEV uint16_t *nbc_grid(NbCtx &c) { return c.grid; }
+#endif
 #define NB_WARP_BYTES(C, W) (sizeof(NbCtx) + sizeof(NbHdr) + (size_t)(C) * (size_t)(W) * 2u)
 
 #define NB_FAULT(c, bit) (nbc_hdr(c)->fault |= (int32_t)(bit))
@@ -125,7 +138,11 @@ NB_DEV void nbc_pool_release(NbCtx &c, int i) { nbc_hdr(c)->pool[i].type = NB_EV
 struct __attribute__((aligned(16))) NbChunk { uint32_t w[4]; };
 
 NB_DEV NbChunk *nbc_chunk(NbCtx &c, int carrier, int q) { return (NbChunk *)&nbc_grid(c)[carrier * c.W + ((q << 3) & (c.W - 1))]; }
+#if defined(NB_FIXED_C) && NB_FIXED_C == 1
+NB_DEV uint16_t *nbc_col(NbCtx &c, int, int t) { return &nbc_grid(c)[t & (c.W - 1)]; }      /* one carrier: its index is 0 */
+#else
 NB_DEV uint16_t *nbc_col(NbCtx &c, int carrier, int t) { return &nbc_grid(c)[carrier * c.W + (t & (c.W - 1))]; }
+#endif
 
 /* 32-bit lane mask of word j (columns lo+2j, lo+2j+1) restricted to columns [first, last) of the chunk */
 NB_DEV uint32_t nbc_word_mask(int j, int first, int last)

@@ -42,7 +42,8 @@ struct nbiot_handle {
     unsigned int *counter_dev;
     int blocks, smem_bytes, sim_hi;
     int blocks_short, smem_short, sim_hi_short, stage_policy;     /* geometry of launches that leave the grid in HBM */
-    NbSimVariant k_gen, k_c1;    /* builds of the warp-per-instance kernels (nbiot_simk.cuh) */
+    NbSimVariant k_gen, k_c1, k_gs, k_c1s;   /* builds of the warp-per-instance kernels (nbiot_simk.cuh): generic / single carrier, ring anywhere / staged */
+    int use_staged_builds;       /* measurement knob NBIOT_SIM_STAGED_BUILDS=0: staged launches on the ring-anywhere builds */
     int use_c1;                  /* single-carrier batch: the c1 build (the generic one while an event log is attached) */
     int q_all;                   /* test knob: short launches too */
     NbQueueRt *q;                /* migrating-instance kernel (nbiot_queue.cu) for long launches; NULL: warp-per-instance kernel */
@@ -152,7 +153,12 @@ static NbKernelArgs make_args(nbiot_handle_t *h, int stage_grid = 1)
     return A;
 }
 
-static const NbSimVariant *sim_variant(const nbiot_handle_t *h) { return h->use_c1 && !h->evlog ? &h->k_c1 : &h->k_gen; }
+static const NbSimVariant *sim_variant(const nbiot_handle_t *h, int staged)
+{
+    int c1 = h->use_c1 && !h->evlog;
+    if (staged && h->use_staged_builds) return c1 ? &h->k_c1s : &h->k_gs;
+    return c1 ? &h->k_c1 : &h->k_gen;
+}
 
 static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, int until_time, int max_steps, cudaStream_t st, const uint8_t *active = nullptr)
 {
@@ -171,14 +177,14 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
         h->launches += 1;                              /* the queue-initialisation kernel */
     }
     else if (mode == 2) {
-        const NbSimVariant *v = sim_variant(h);
+        const NbSimVariant *v = sim_variant(h, stage);
         void *args[] = { (void *)&A, (void *)&ext_actions, (void *)&active, (void *)&until_time, (void *)&max_steps };
         CK(cudaLaunchKernel(hi ? v->sim_hi : v->sim_lo, dim3(blocks), dim3(NB_WPB * 32), args, (size_t)smem, st));
     } else {
         int construct = mode == 0 ? 1 : 0;
         const uint64_t *seeds = h->seeds_dev;
         void *args[] = { (void *)&A, (void *)&construct, (void *)&seeds };
-        CK(cudaLaunchKernel(sim_variant(h)->reset, dim3(h->blocks), dim3(NB_WPB * 32), args, (size_t)h->smem_bytes, st));
+        CK(cudaLaunchKernel(sim_variant(h, stage)->reset, dim3(h->blocks), dim3(NB_WPB * 32), args, (size_t)h->smem_bytes, st));
     }
     CK(cudaGetLastError());
     h->launches += 1;
@@ -238,10 +244,11 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if ((size_t)h->smem_bytes > prop.sharedMemPerBlockOptin) return set_err(NBIOT_E_INVALID, "grid_w too large for the shared memory of one CTA");
-    nb_sim_variant_generic(&h->k_gen); nb_sim_variant_c1(&h->k_c1);
+    nb_sim_variant_generic(&h->k_gen); nb_sim_variant_c1(&h->k_c1); nb_sim_variant_gs(&h->k_gs); nb_sim_variant_c1s(&h->k_c1s);
+    h->use_staged_builds = getenv("NBIOT_SIM_STAGED_BUILDS") ? atoi(getenv("NBIOT_SIM_STAGED_BUILDS")) : 1;
     h->use_c1 = L.n_carriers == 1;
     if (const char *e = getenv("NBIOT_SIM_VARIANT")) h->use_c1 = h->use_c1 && strcmp(e, "generic") != 0;   /* measurement knob */
-    for (const NbSimVariant *v : { &h->k_gen, &h->k_c1 })
+    for (const NbSimVariant *v : { &h->k_gen, &h->k_c1, &h->k_gs, &h->k_c1s })
         for (const void *f : { v->sim_lo, v->sim_hi, v->reset })
             CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     const NbSimVariant *kv = h->use_c1 ? &h->k_c1 : &h->k_gen;       /* both builds have the same launch bounds and register budgets */

@@ -58,6 +58,8 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
 struct NbSimVariant { const void *sim_lo, *sim_hi, *reset; int warps_per_block; };
 void nb_sim_variant_generic(NbSimVariant *out);
 void nb_sim_variant_c1(NbSimVariant *out);
+void nb_sim_variant_gs(NbSimVariant *out);
+void nb_sim_variant_c1s(NbSimVariant *out);
 
 /* ---- migrating-instance kernel (nbiot_queue.cu) ---- */
 struct NbQueueRt;                                   /* device-side queues of one handle */

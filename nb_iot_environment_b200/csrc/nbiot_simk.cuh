@@ -1,6 +1,8 @@
 /*
  * nbiot_simk.cuh -- the simulation kernels (warp-per-instance): included by one translation unit per BUILD of the core.
  *   nbiot_kernels.cu : generic build (1 or 2 carriers, optional event log)                    NB_SIM_VARIANT = generic
+ *   nbiot_sim_gs.cu  : generic + NB_GRID_STAGED (long launches: the ring is always in shared memory)   NB_SIM_VARIANT = gs
+ *   nbiot_sim_c1s.cu : c1 + NB_GRID_STAGED                                                             NB_SIM_VARIANT = c1s
  *   nbiot_sim_c1.cu  : NB_FIXED_C = 1, NB_NO_EVLOG -- the carrier loops and ring addressing compiled for single-carrier
  *                      cells: 3 % less SASS and 6-8 % faster on the headline workload (the kernel is bound by instruction
  *                      supply, profiles/r01_icache.txt, so less code pays twice)                NB_SIM_VARIANT = c1

@@ -6,7 +6,7 @@ import csv, os, re, subprocess, sys, tempfile
 src = sys.argv[1]
 lib = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'nb_iot_environment_b200', 'libnbiot_b200.so')
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 60
-KERNEL = os.environ.get('NBIOT_PROFILE_KERNEL', 'nbk_c116nbiot_sim_kernelILi7')   # the 72-register build (bench workload)
+KERNEL = os.environ.get('NBIOT_PROFILE_KERNEL', 'nbk_c1s16nbiot_sim_kernelILi7')   # the 72-register build (bench workload)
 d = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=d, capture_output=True)
 cubs = sorted(f for f in os.listdir(d) if f.endswith('.cubin'))      # one per translation unit of the library

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_r13.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_r13.log
+for r in 1 2; do
+  timeout 200 tools/ab.sh prev_$r NBIOT_SIM_STAGED_BUILDS=0
+  timeout 200 tools/ab.sh cur_$r
+done
+grep -h "episode statistics" gpurun_out/ab_prev_1.err gpurun_out/ab_cur_1.err | cut -c1-200
+timeout 300 python tools/sweep.py 100000 2>/dev/null | cut -c1-150
+NBIOT_SIM_STAGED_BUILDS=0 timeout 300 python tools/sweep.py 100000 2>/dev/null | cut -c1-150

@@ -3,7 +3,7 @@
 usage: python tools/sass_sizes.py [path/to/lib.so] [kernel substring]"""
 import os, re, subprocess, sys, tempfile
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'nb_iot_environment_b200', 'libnbiot_b200.so')
-want = sys.argv[2] if len(sys.argv) > 2 else 'nbk_c116nbiot_sim_kernelILi7'
+want = sys.argv[2] if len(sys.argv) > 2 else 'nbk_c1s16nbiot_sim_kernelILi7'
 d = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=d, capture_output=True)
 cubs = sorted(f for f in os.listdir(d) if f.endswith('.cubin'))      # one per translation unit of the library
