@@ -172,16 +172,25 @@ NB_FN1S uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
 {
     return (uint32_t)nbw_run([&]() -> int {
         uint32_t v = 0;
+        const uint16_t *g = nbc_col(c, carrier, 0);            /* column 0 of the carrier; the ring mask is loop-invariant */
+        const int wm = c.W - 1;
         NB_NOUNROLL
-        for (int k = nbw_lane(); k < n; k += NB_LANES) v |= *nbc_col(c, carrier, a + k);
+        for (int k = a + nbw_lane(); k < a + n; k += NB_LANES) v |= g[k & wm];
         return (int)nbw_or_u32(v);
     });
 }
 NB_FNM3 void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, int set)
 {
     nbw_run([&]() -> int {
-        NB_NOUNROLL
-        for (int k = nbw_lane(); k < n; k += NB_LANES) { uint16_t *p = nbc_col(c, carrier, a + k); *p = set ? (uint16_t)(*p | mask) : (uint16_t)0; }
+        uint16_t *g = nbc_col(c, carrier, 0);
+        const int wm = c.W - 1;
+        if (set) {
+            NB_NOUNROLL
+            for (int k = a + nbw_lane(); k < a + n; k += NB_LANES) g[k & wm] = (uint16_t)(g[k & wm] | mask);
+        } else {
+            NB_NOUNROLL
+            for (int k = a + nbw_lane(); k < a + n; k += NB_LANES) g[k & wm] = (uint16_t)0;
+        }
         nbw_sync();
         return 0;
     });
@@ -1313,9 +1322,17 @@ NB_FN1 void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:58
         int li = (int)NB_RINT(NB_MUL(u->loss, 10.0));
         if (li < 1214) li = 1214;
         if (li > 1713) { NB_FAULT(c, NBIOT_FAULT_MCS_KEY); return; }
-        int ti = NB_N_TBS - 1;
-        NB_NOUNROLL
-        for (int i = 0; i < NB_N_TBS; ++i) if (nb_tbs_list[i] >= u->buffer) { ti = i; break; }
+        /* utils.find_next_integer_index: the first transport block size that holds the buffer, one candidate per lane */
+        const int buf = u->buffer;
+        int ti = nbw_run([&]() -> int {
+            NB_NOUNROLL
+            for (int base = 0; base < NB_N_TBS; base += NB_LANES) {
+                int i = base + nbw_lane();
+                uint32_t m = nbw_ballot(i < NB_N_TBS && nb_tbs_list[i < NB_N_TBS ? i : 0] >= buf);
+                if (m) return base + nbw_ffs(m) - 1;
+            }
+            return NB_N_TBS - 1;
+        });
         tbs = nb_tbs_list[ti];
         const uint8_t *e = &c.mcs[((li - 1214) * NB_N_TBS + ti) * 3];
         I_tbs = NB_LDG(&e[0]); N_rep = NB_LDG(&e[1]); N_ru = NB_LDG(&e[2]);
