@@ -137,6 +137,9 @@ long long nbiot_launch_count(nbiot_handle_t *h);
  * (both only with NBIOT_Q_STATS=1), out[20] cells stored + queued, out[21] tasks continued on the same warp, out[22] class changes of an SM,
  * out[23] idle polls of the dispatchers, out[24] scheduler self-check (0 = fine); synchronises the device */
 int nbiot_queue_stats(nbiot_handle_t *h, unsigned long long out[32]);
+/* measurement aid (NBIOT_PROF_INST=1 at creation): { start ns, end ns, SM id, 0 } of every instance in the last simulation launch,
+ * out_host = uint64[n_inst][4]; synchronises the device */
+int nbiot_instance_times(nbiot_handle_t *h, unsigned long long *out_host);
 /* launch geometry chosen at creation: blocks, warps per block, dynamic shared memory per block */
 int nbiot_launch_geometry(nbiot_handle_t *h, int *blocks, int *warps_per_block, int *smem_bytes);
 
