@@ -205,6 +205,40 @@ def test_time_sliced_launch_equals_one_piece(monkeypatch):
     assert np.array_equal(states[0], states[1]) and np.array_equal(states[0], states[2])
 
 
+def test_builds_of_the_core_give_identical_states(monkeypatch):
+    """The simulation kernels exist in four builds of the core (csrc/nbiot_simk.cuh): generic / single-carrier x ring anywhere / ring
+    staged. A single-carrier batch run on each of them -- short launches (every decision external), long launches (NPRACH agent
+    external) and run_until -- ends in the same state buffer, byte for byte."""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    N = 200
+    states = []
+    for variant, staged in ((None, None), ('generic', None), (None, '0'), ('generic', '0')):
+        for k, v in (('NBIOT_SIM_VARIANT', variant), ('NBIOT_SIM_STAGED_BUILDS', staged)):
+            if v is None:
+                monkeypatch.delenv(k, raising=False)
+            else:
+                monkeypatch.setenv(k, v)
+        out = []
+        env = BatchedNBIoTEnv(dict(CFG1, ratio=0.5), agents_conf=NPRACH_AGENTS, ext_agent=3, num_envs=N, seeds=list(range(N)), ue_cap=512, grid_w=2048, hist_cap=512)
+        env.reset()
+        r = np.random.default_rng(21)
+        for _ in range(3):
+            env.step(_random_ext_actions(r, env.action_nvec, N))
+        env.run_until(12000)
+        torch.cuda.synchronize()
+        out.append(env.state.cpu().numpy().copy()); assert env.stats()['faulted'] == 0; env.close()
+        env = BatchedNBIoTEnv(CFG3, agents_conf=NPUSCH_AGENTS, ext_agent=0, num_envs=N, seeds=list(range(N)), ue_cap=512, grid_w=2048, hist_cap=64)
+        env.reset()
+        for _ in range(80):
+            env.step(_random_ext_actions(r, env.action_nvec, N))
+        torch.cuda.synchronize()
+        out.append(env.state.cpu().numpy().copy()); assert env.stats()['faulted'] == 0; env.close()
+        states.append(out)
+    for other in states[1:]:
+        assert np.array_equal(states[0][0], other[0]) and np.array_equal(states[0][1], other[1])
+
+
 def _random_ext_actions(rng, nvec, n):
     return np.stack([rng.integers(0, m, size=n) for m in nvec], axis=1).astype(np.uint8)
 
