@@ -393,6 +393,19 @@ NB_FNM4 int nbc_carrier_allocate(NbCtx &c, int carrier_id, int t, int delay, int
         NB_NOUNROLL
         for (int ci = 0; ci < NB_NC(c); ++ci) {
             int cc = ci == 0 ? carrier_id : (carrier_id == 0 ? 1 : 0);
+#ifndef NB_NO_EDGE_REJECT
+            /* the subcarriers busy in the first or the last column of the window are busy in the window: when they already leave
+             * no aligned group free -- the usual case in a loaded cell, where transmissions longer than the delays cover the window
+             * starts -- the window is lost without looking at the columns in between */
+            {
+                uint32_t eb = (uint32_t)*nbc_col(c, cc, from) | (uint32_t)*nbc_col(c, cc, from + N_sf - 1);
+                uint32_t ef = eb;
+                if (row >= 1) ef |= (eb >> 1) | (eb >> 2);
+                if (row >= 2) ef |= ef >> 3;
+                if (row == 3) ef |= ef >> 6;
+                if (!(~ef & nb_sc_heads[row])) { NB_COUNT(11, 1); continue; }
+            }
+#endif
             uint32_t busy = nbc_grid_busy(c, cc, from, N_sf);
             /* first free aligned group of N_sc subcarriers (offsets_per_sc, carrier.py:29-34): fold the
              * group's bits onto its lowest one, then take the lowest clear group bit */
