@@ -1769,7 +1769,7 @@ NB_FNM void nbc_apply_writes(NbCtx &c, const NbWrites *w)
  * ctrl->state_writes[s] holds the fixed actions of the internal agents of state s; for a state of
  * the external agent it holds only the agents listed before it (controller.py:283-288).
  * Returns the number of NodeB steps taken; the decision record is rewritten iff it is > 0. */
-NB_FN int nbc_controller_advance(NbCtx &c, const NbCtrlDev *ctrl, const uint8_t *ext_action, int until_time, int max_steps, int slice_time = -1)
+NB_FN int nbc_controller_advance(NbCtx &c, const NbCtrlDev *ctrl, const uint8_t *ext_action, int until_time, int max_steps)
 {
     NbHdr *h = nbc_hdr(c);
     int steps = 0;
@@ -1781,12 +1781,6 @@ NB_FN int nbc_controller_advance(NbCtx &c, const NbCtrlDev *ctrl, const uint8_t 
     } else nbc_apply_writes(c, &ctrl->state_writes[h->state]);
     NB_NOUNROLL
     while (steps < max_steps && !(until_time >= 0 && h->time >= until_time)) {
-        if (slice_time >= 0 && h->time >= slice_time && steps > 0) {
-            /* end of a time slice (nbiot_simk.cuh nb_run_quanta), not of the launch: what the loop does between two NodeB steps,
-             * no record; the next slice re-enters with the internal agents of the current state */
-            nbc_node_info(c, 0, 0.0);
-            return steps;
-        }
         if (steps > 0) {
             nbc_node_info(c, 0, 0.0);                          /* an internal agent looks at nothing */
             nbc_apply_writes(c, &ctrl->state_writes[h->state]);

@@ -40,7 +40,6 @@ struct nbiot_handle {
     uint8_t *mcs_dev;
     uint64_t *seeds_dev;
     unsigned int *counter_dev;
-    NbRequeue *rq_dev; uint32_t *rq_slots; unsigned int rq_mask; int quantum;   /* time-sliced long launches (nbiot_simk.cuh nb_run_quanta); quantum = 0: off */
     unsigned long long *prof_dev;   /* NBIOT_PROF_INST=1: per-instance timing of the last launch */
     int blocks, smem_bytes, sim_hi;
     int blocks_short, smem_short, sim_hi_short, stage_policy;     /* geometry of launches that leave the grid in HBM */
@@ -147,8 +146,7 @@ static NbKernelArgs make_args(nbiot_handle_t *h, int stage_grid = 1)
 {
     NbKernelArgs A;
     A.state = h->state; A.L = h->L; A.conf = h->conf_dev; A.ctrl = h->ctrl_dev; A.lut2 = h->lut2_dev; A.mcs = h->mcs_dev;
-    A.counter = h->counter_dev; A.prof = h->prof_dev;
-    A.quantum = 0; A.rq = h->rq_dev; A.rq_slots = h->rq_slots; A.rq_mask = h->rq_mask; A.evlog = h->evlog; A.evlog_cap = h->evlog_cap;
+    A.counter = h->counter_dev; A.prof = h->prof_dev; A.evlog = h->evlog; A.evlog_cap = h->evlog_cap;
     A.hdr_bytes16 = (int)(sizeof(NbHdr) / 16);
     A.grid_bytes16 = (int)((size_t)h->L.n_carriers * h->L.grid_w * 2 / 16);
     A.stage_grid = stage_grid;
@@ -181,13 +179,6 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
     }
     else if (mode == 2) {
         const NbSimVariant *v = sim_variant(h, stage);
-        if (stage && h->quantum > 0 && max_steps >= (1 << 20)) {       /* a long launch of about one wave: time-sliced */
-            A.quantum = h->quantum;
-            int n = h->n_inst;
-            void *iargs[] = { (void *)&h->rq_dev, (void *)&active, (void *)&n };
-            CK(cudaLaunchKernel(v->requeue_init, dim3(1), dim3(256), iargs, 0, st));
-            h->launches += 1;
-        }
         void *args[] = { (void *)&A, (void *)&ext_actions, (void *)&active, (void *)&until_time, (void *)&max_steps };
         CK(cudaLaunchKernel(hi ? v->sim_hi : v->sim_lo, dim3(blocks), dim3(NB_WPB * 32), args, (size_t)smem, st));
     } else {
@@ -290,20 +281,6 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     int need = (n_inst + NB_WPB - 1) / NB_WPB;
     int cap = prop.multiProcessorCount * per_sm;
     h->blocks = need < cap ? need : cap;
-    {   /* time slicing (opt-in, NBIOT_QUANTUM = subframes per slice): meant for launches of about one wave of the resident warps, whose
-         * tail leaves a quarter of the warp-time idle; measured on the headline workload it costs more than the rebalancing returns
-         * (13.5 ms per step unsliced, 13.65 / 13.9 / 14.25 ms at 1000 / 500 / 250 subframes per slice), so it is off by default */
-        int q = getenv("NBIOT_QUANTUM") ? atoi(getenv("NBIOT_QUANTUM")) : 0;
-        h->quantum = (q > 0 && (long long)n_inst <= 2LL * cap * NB_WPB) ? q : 0;
-        if (h->quantum) {
-            unsigned int rcap = 1024; while (rcap < (unsigned int)n_inst + (unsigned int)(cap * NB_WPB) + 64u) rcap <<= 1;
-            h->rq_mask = rcap - 1u;
-            CK(cudaMalloc(&h->rq_dev, sizeof(NbRequeue)));
-            CK(cudaMalloc(&h->rq_slots, sizeof(uint32_t) * rcap));
-            CK(cudaMemset(h->rq_dev, 0, sizeof(NbRequeue)));
-            CK(cudaMemset(h->rq_slots, 0, sizeof(uint32_t) * rcap));
-        }
-    }
     h->q = nullptr;
     {   /* NBIOT_SCHED = "queue": long launches run on the migrating-instance kernel; "warp" (default): one warp owns an instance for the launch */
         const char *e = getenv("NBIOT_SCHED");
@@ -320,7 +297,7 @@ int nbiot_destroy(nbiot_handle_t *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->conf_dev); cudaFree(h->ctrl_dev); cudaFree(h->lut2_dev); cudaFree(h->mcs_dev); cudaFree(h->seeds_dev); cudaFree(h->counter_dev); cudaFree(h->prof_dev); cudaFree(h->rq_dev); cudaFree(h->rq_slots);
+    cudaFree(h->conf_dev); cudaFree(h->ctrl_dev); cudaFree(h->lut2_dev); cudaFree(h->mcs_dev); cudaFree(h->seeds_dev); cudaFree(h->counter_dev); cudaFree(h->prof_dev);
     cudaFree(h->act_dev); cudaFree(h->obs_dev); cudaFree(h->rew_dev); cudaFree(h->items_dev);
     cudaFreeHost(h->act_pin); cudaFreeHost(h->obs_pin); cudaFreeHost(h->rew_pin);
     nbq_destroy(h->q);

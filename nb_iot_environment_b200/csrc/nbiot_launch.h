@@ -22,19 +22,8 @@ struct NbKernelArgs {
     int32_t *evlog; int evlog_cap;
     int smem_per_warp, hdr_bytes16, grid_bytes16;
     int stage_grid;              /* 1: the look-ahead ring is staged in shared memory; 0: used in place in HBM (short launches) */
-    /* time slicing of long launches (nbiot_simk.cuh, nb_run_quanta): 0 = off, else the simulated subframes a warp advances a cell
-     * before it hands it back to the re-queue ring */
-    int quantum;
-    struct NbRequeue *rq;
-    uint32_t *rq_slots; unsigned int rq_mask;
 };
 
-/* re-queue ring of a time-sliced launch: cells that have not finished wait here for the next free warp (any SM) */
-struct NbRequeue {
-    unsigned int tail; unsigned int pad0[31];
-    unsigned int head; unsigned int pad1[31];
-    int remaining; int pad2[31];
-};
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ void nb_copy16(void *dst, const void *src, int n16)
@@ -68,7 +57,7 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
 #endif
 
 /* ---- builds of the warp-per-instance kernels (nbiot_simk.cuh) ---- */
-struct NbSimVariant { const void *sim_lo, *sim_hi, *reset, *requeue_init; int warps_per_block; };
+struct NbSimVariant { const void *sim_lo, *sim_hi, *reset; int warps_per_block; };
 void nb_sim_variant_generic(NbSimVariant *out);
 void nb_sim_variant_c1(NbSimVariant *out);
 void nb_sim_variant_gs(NbSimVariant *out);

@@ -181,7 +181,7 @@ typedef struct __attribute__((aligned(16))) NbHdr {
      *      (at the end: the offsets of everything the warp-per-instance kernel touches stay what they were) ---- */
     int32_t tk_steps, tk_phase, tk_a, tk_b;
     NbOccasion tk_occ;
-    int32_t tk_slice;                 /* time-sliced launches (nbiot_simk.cuh): 1 while the cell's launch is under way */
+    int32_t tk_pad;
 } NbHdr;
 
 /* device-side form of nbiot_ctrl_t (include/nbiot_ctrl.h): write tables as (bit mask, values) */

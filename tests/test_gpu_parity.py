@@ -173,38 +173,6 @@ def test_migrating_instances_equal_warp_per_instance(monkeypatch):
     assert np.array_equal(states[0], states[1])
 
 
-def test_time_sliced_launch_equals_one_piece(monkeypatch):
-    """Long launches of about one wave are time-sliced (csrc/nbiot_simk.cuh nb_run_quanta: a warp advances a cell by NBIOT_QUANTUM
-    subframes, then the cell waits in a ring for the next free warp of any SM). Cutting an advance into slices changes nothing:
-    same states as NBIOT_QUANTUM=0, bit for bit, with an external NPRACH agent (one launch per 3000 subframes) and on run_until."""
-    import torch
-    from nb_iot_environment_b200 import BatchedNBIoTEnv, _cabi
-    hdr, tk = _cabi.load().nbiot_hdr_bytes(), _cabi.load().nbiot_hdr_task_bytes()
-    states = []
-    N = 600
-    for q in ('0', '97', None):
-        if q is None:
-            monkeypatch.delenv('NBIOT_QUANTUM', raising=False)
-        else:
-            monkeypatch.setenv('NBIOT_QUANTUM', q)
-        env = BatchedNBIoTEnv(dict(CFG1, ratio=0.5), agents_conf=NPRACH_AGENTS, ext_agent=3, num_envs=N, seeds=list(range(N)), ue_cap=512, grid_w=2048, hist_cap=512)
-        env.reset()
-        r = np.random.default_rng(11)
-        for _ in range(4):
-            env.step(_random_ext_actions(r, env.action_nvec, N))
-        env.run_until(14000)
-        active = np.zeros(N, dtype=bool); active[::3] = True    # a masked step: only every third cell advances
-        env.step(_random_ext_actions(r, env.action_nvec, N), active=active)
-        torch.cuda.synchronize()
-        st = env.state.cpu().numpy().copy()
-        h = st[:N * hdr].reshape(N, hdr)
-        h[:, hdr - tk:] = 0
-        states.append(st)
-        assert env.stats()['faulted'] == 0
-        env.close()
-    assert np.array_equal(states[0], states[1]) and np.array_equal(states[0], states[2])
-
-
 def test_builds_of_the_core_give_identical_states(monkeypatch):
     """The simulation kernels exist in four builds of the core (csrc/nbiot_simk.cuh): generic / single-carrier x ring anywhere / ring
     staged. A single-carrier batch run on each of them -- short launches (every decision external), long launches (NPRACH agent
