@@ -169,8 +169,31 @@ def test_migrating_instances_equal_warp_per_instance(monkeypatch):
         h[:, hdr - tk:] = 0                                     # NbHdr.tk_*
         states.append(st)
         assert env.stats()['faulted'] == 0
+        if sched is not None:                                   # the scheduler's own counters: cells were handed on, nothing gave up
+            import ctypes
+            qs = (ctypes.c_ulonglong * 32)()
+            _cabi.check(env.L.nbiot_queue_stats(env._h, qs))
+            assert qs[20] > 0 and qs[24] == 0
         env.close()
     assert np.array_equal(states[0], states[1])
+
+
+def test_per_cell_launch_timing(monkeypatch):
+    """NBIOT_PROF_INST=1: start / end time and SM of every cell in the last simulation launch (measurement aid, tools/inst_times.py)"""
+    from nb_iot_environment_b200 import BatchedNBIoTEnv, _cabi
+    monkeypatch.setenv('NBIOT_PROF_INST', '1')
+    N = 64
+    env = BatchedNBIoTEnv(CFG1, num_envs=N, seeds=list(range(N)), ue_cap=256, grid_w=1024)
+    env.reset(); env.run_until(3000)
+    out = np.zeros((N, 4), dtype=np.uint64)
+    _cabi.check(env.L.nbiot_instance_times(env._h, out.ctypes.data))
+    assert (out[:, 1] > out[:, 0]).all() and (out[:, 2] < 1024).all()
+    env.close()
+    monkeypatch.delenv('NBIOT_PROF_INST')
+    env = BatchedNBIoTEnv(CFG1, num_envs=2, ue_cap=64, grid_w=256)
+    with pytest.raises(Exception):
+        _cabi.check(env.L.nbiot_instance_times(env._h, out.ctypes.data))
+    env.close()
 
 
 def test_builds_of_the_core_give_identical_states(monkeypatch):
