@@ -1562,13 +1562,17 @@ NB_FN1 void nbc_write_record(NbCtx &c, double reward, double occ_nprach, double 
         r->n_rx = h->n_rx; r->n_err = h->n_err; r->n_unfit = h->n_unfit; r->n_acc = h->n_acc;
         if (h->n_rx > NBIOT_STEP_LIST || h->n_err > NBIOT_STEP_LIST || h->n_unfit > NBIOT_STEP_LIST || h->n_acc > NBIOT_STEP_LIST)
             NB_FAULT(c, NBIOT_FAULT_LIST_TRUNC);
-        NB_NOUNROLL
-        for (int i = 0; i < NBIOT_STEP_LIST; ++i) {
-            if (i < h->n_rx) { r->rx_id[i] = h->rx_id[i]; r->rx_delay[i] = h->rx_delay[i]; }
-            if (i < h->n_err) r->err_id[i] = h->err_id[i];
-            if (i < h->n_unfit) r->unfit_id[i] = h->unfit_id[i];
-            if (i < h->n_acc) { r->acc_id[i] = h->acc_id[i]; r->acc_delay[i] = h->acc_delay[i]; }
-        }
+        nbw_run([&]() -> int {                                  /* one list position per lane */
+            NB_NOUNROLL
+            for (int i = nbw_lane(); i < NBIOT_STEP_LIST; i += NB_LANES) {
+                if (i < h->n_rx) { r->rx_id[i] = h->rx_id[i]; r->rx_delay[i] = h->rx_delay[i]; }
+                if (i < h->n_err) r->err_id[i] = h->err_id[i];
+                if (i < h->n_unfit) r->unfit_id[i] = h->unfit_id[i];
+                if (i < h->n_acc) { r->acc_id[i] = h->acc_id[i]; r->acc_delay[i] = h->acc_delay[i]; }
+            }
+            nbw_sync();
+            return 0;
+        });
     } else if (h->state == NB_ST_RAR_WINDOW) {
         int max_CE = nb_ce_for_sf_left[h->NPDCCH_sf_left];
         NB_NOUNROLL
