@@ -32,7 +32,17 @@ __device__ __forceinline__ void nb_copy16(void *dst, const void *src, int n16)
     for (int i = threadIdx.x & 31; i < n16; i += 32) d[i] = s[i];
 }
 
-__device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int i, const NbCtaConst *s_cc)
+/* the part of the context that is the same for every instance of a launch: once per warp */
+__device__ __forceinline__ void nb_fill_ctx_launch(NbCtx &c, const NbKernelArgs &A, const NbCtaConst *s_cc)
+{
+    const NbLayout &L = A.L;
+    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = *(const nbiot_conf_hot_t *)A.conf; c.ctrl = &s_cc->ctrl;
+    c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
+    c.evlog = nullptr; c.evlog_cap = A.evlog_cap;
+}
+
+/* the per-instance part: where the instance's arrays live in the state buffer */
+__device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int i)
 {
     const NbLayout &L = A.L;
     uint8_t *s = A.state;
@@ -47,9 +57,7 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
     c.service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
     c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
     c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
-    c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = *(const nbiot_conf_hot_t *)A.conf; c.ctrl = &s_cc->ctrl;
-    c.W = L.grid_w; c.ue_cap = L.ue_cap; c.ra_cap = L.ra_cap; c.hist_cap = L.hist_cap; c.C = L.n_carriers;
-    c.evlog = i == 0 ? A.evlog : nullptr; c.evlog_cap = A.evlog_cap;
+    c.evlog = i == 0 ? A.evlog : nullptr;
     c.grid = A.stage_grid ? (uint16_t *)((unsigned char *)&c + sizeof(NbCtx) + sizeof(NbHdr))
                           : (uint16_t *)(A.state + A.L.off_grid) + (size_t)i * A.L.n_carriers * A.L.grid_w;
 }

@@ -48,13 +48,14 @@ __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, cons
     NbHdr *hdr_g = (NbHdr *)(A.state + A.L.off_hdr);
     uint16_t *grid_g = (uint16_t *)(A.state + A.L.off_grid);
     const size_t grid_elems = (size_t)A.L.n_carriers * A.L.grid_w;
+    if (lane == 0) nb_fill_ctx_launch(c, A, &s_ctrl);
     for (;;) {
         int i = 0;
         if (lane == 0) i = (int)atomicAdd(A.counter, 1u);
         i = __shfl_sync(0xFFFFFFFFu, i, 0);
         if (i >= A.L.n_inst) break;
         if (active && !active[i]) continue;
-        if (lane == 0) nb_fill_ctx(c, A, i, &s_ctrl);
+        if (lane == 0) nb_fill_ctx(c, A, i);
         if (LOAD) {
             nb_copy16(hdr_s, hdr_g + i, A.hdr_bytes16);
             if (A.stage_grid) nb_copy16(grid_s, grid_g + (size_t)i * grid_elems, A.grid_bytes16);
