@@ -124,7 +124,12 @@ NB_FNM2 void nbc_pool_push(NbCtx &c, uint64_t key, int type, int ce, int aux)
 {
     NbHdr *h = nbc_hdr(c);
     if (!h->pool_free) { NB_FAULT(c, NBIOT_FAULT_EVENT_SLOTS); return; }
+#ifdef NB_TEST_POOL_HIGH
+    int i = 63 - __builtin_clzll(h->pool_free);              /* test builds (tests/_hostemu): highest free entry first, so that the second
+                                                              * pass of the event selection is exercised by ordinary traces */
+#else
     int i = nbw_ffsll(h->pool_free) - 1;
+#endif
     h->pool_free &= ~(1ULL << i);
     NbEvent e; e.key = key; e.aux = aux; e.type = (uint8_t)type; e.ce = (uint8_t)ce; e.pad0 = e.pad1 = 0;
     h->pool[i] = e;

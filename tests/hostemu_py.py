@@ -16,7 +16,7 @@ _LIBS = {}
 def lib(lanes):
     if lanes not in _LIBS:
         subprocess.check_call(['make', '-s', '-C', _HERE])
-        L = ctypes.CDLL(os.path.join(_HERE, '_build', f'libemu{lanes}.so'))      # lanes: 1, 32 or '1t' (1 lane, task chain)
+        L = ctypes.CDLL(os.path.join(_HERE, '_build', f'libemu{lanes}.so'))      # lanes: 1, 32, '1t' (1 lane, task chain) or '32h' (32 lanes, event pool filled from the top)
         L.emu_create.restype = ctypes.c_void_p
         L.emu_create.argtypes = [ctypes.POINTER(NbiotConf), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(NbiotCtrl)]
         L.emu_destroy.argtypes = [ctypes.c_void_p]
@@ -29,7 +29,7 @@ def lib(lanes):
         L.emu_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.emu_records.argtypes = [ctypes.c_void_p]
         L.emu_counters.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
-        assert L.emu_lanes() == (1 if lanes == '1t' else lanes) and L.emu_tasks() == (1 if lanes == '1t' else 0)
+        assert L.emu_lanes() == {'1t': 1, '32h': 32}.get(lanes, lanes) and L.emu_tasks() == (1 if lanes == '1t' else 0)
         _LIBS[lanes] = L
     return _LIBS[lanes]
 

@@ -59,3 +59,10 @@ def test_core_task_chain(case, oracle_lib):
     """The same core cut into tasks (nbiot_core.cuh "tasks"), the instance stored and reloaded between two tasks:
     the control flow of the migrating-instance kernel, against the same golden traces."""
     _replay(case, '1t', 10 ** 9)
+
+
+@pytest.mark.parametrize('case', ['cfg1_default', 'cfg3_npusch_random_policy'])
+def test_event_selection_second_pass(case, oracle_lib):
+    """The event selection looks at 32 keys per pass and takes a second pass only when pool entries above the first 22 are in use
+    (more than 22 pending events). This build hands the pool out from its highest entry, so every trace goes through the second pass."""
+    _replay(case, '32h', 300)
