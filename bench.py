@@ -44,22 +44,26 @@ AGENTS = [
      'next': -1, 'states': ['NPRACH_update']},
 ]
 EXT_AGENT = 3
-CAPS = dict(ue_cap=512, grid_w=int(os.environ.get('NBIOT_BENCH_GRID_W', '2048')), hist_cap=512)
+CAPS = dict(ue_cap=CONF['M'], grid_w=int(os.environ.get('NBIOT_BENCH_GRID_W', '2048')), hist_cap=512)   # live UEs <= M (closed population, ue_generator.py:38-42)
 METRIC = 'simulated subframe-instances/sec'
 UNIT = 'subframe-instances/s'
 WORKLOAD = ('configs[1]: NPRACH control scenario (scripts/nprach, M=1000, ratio=0.5, NPRACH agent external, '
             'uniform-random feasible NPRACH configurations), 4096 instances per GPU, 1 step = 3000 subframes per instance')
 
 
-def ext_actions(steps, n, seed):
-    """uint8[steps][n][8]: th_C1, th_C0, sc_C0..2, period_C0..2 (action items of agent 3)"""
+def ext_actions(steps, n, seed, first_cell=0):
+    """uint8[steps][n][8]: th_C1, th_C0, sc_C0..2, period_C0..2 (action items of agent 3). The action of cell g at step s is a
+    function of (seed, s, g) alone -- one generator per step, cells drawn in global order -- so the workload does not change with
+    --steps, --warmup, the number of ranks or the batch size."""
     from nb_iot_environment_b200 import parameters as par
-    rng = np.random.default_rng(seed)
     pairs = np.asarray([par.th_indexes[p] for p in par.th_pairs], dtype=np.uint8)       # 105 feasible (th_C1 <= th_C0) pairs
     a = np.zeros((steps, n, 8), dtype=np.uint8)
-    a[:, :, 0:2] = pairs[rng.integers(0, len(pairs), size=(steps, n))]
-    a[:, :, 2:5] = rng.integers(0, 4, size=(steps, n, 3))
-    a[:, :, 5:8] = rng.integers(0, 6, size=(steps, n, 3))
+    for s in range(steps):
+        rng = np.random.Generator(np.random.Philox(key=[seed, s]))
+        r = rng.integers(0, 1 << 32, size=(first_cell + n, 8), dtype=np.uint64)[first_cell:]
+        a[s, :, 0:2] = pairs[(r[:, 0] * len(pairs)) >> 32]
+        a[s, :, 2:5] = (r[:, 2:5] * 4) >> 32
+        a[s, :, 5:8] = (r[:, 5:8] * 6) >> 32
     return a
 
 
@@ -201,7 +205,7 @@ def main():
         seeds = np.zeros_like(np.asarray(seeds))
     env = BatchedNBIoTEnv(CONF, agents_conf=AGENTS, ext_agent=EXT_AGENT, num_envs=N, seeds=seeds, device=local_rank, **CAPS)
     total_steps = W + 2 * K
-    acts_host = ext_actions(total_steps, N, seed=1234 + rank)
+    acts_host = ext_actions(total_steps, N, seed=1234, first_cell=rank * N)
     if os.environ.get('NBIOT_BENCH_SAME'):
         acts_host[:] = acts_host[:, :1]
     acts_pinned = torch.from_numpy(acts_host).pin_memory()

@@ -80,7 +80,7 @@ static long long nb_dbg_count[16];
 #define NB_COUNT(i, n) ((void)0)
 #endif
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(NB_TPC)
 #define NB_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 #else
 #define NB_ASSUME_SHARED(p) ((void)0)
@@ -172,7 +172,45 @@ NB_DEV uint32_t nbc_scan_chunks(NbCtx &c, int carrier, int a, int n)
     return acc;
 }
 
-#if NB_GRID_MODE == 0
+#if NB_LANES == 1
+/* one lane owns the cell (thread-per-cell kernel, 1-lane CPU build): four columns per 8-byte word, ragged ends one by one.
+ * The ring is 8-byte aligned and W is a multiple of 4, so a word whose first column index is a multiple of 4 never wraps. */
+typedef uint64_t __attribute__((may_alias)) nb_u64a;
+NB_FN1S uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
+{
+    const uint16_t *g = nbc_col(c, carrier, 0);
+    const int wm = c.W - 1;
+    int k = a, e = a + n;
+    uint32_t v = 0; uint64_t v8 = 0;
+    NB_NOUNROLL
+    while (k < e && (k & 3)) { v |= g[k & wm]; ++k; }
+    NB_NOUNROLL
+    for (; k + 4 <= e; k += 4) v8 |= *(const nb_u64a *)&g[k & wm];
+    NB_NOUNROLL
+    while (k < e) { v |= g[k & wm]; ++k; }
+    v8 |= v8 >> 32;
+    v |= (uint32_t)v8 | ((uint32_t)v8 >> 16);
+    return v & 0xFFFFu;
+}
+NB_FNM3 void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, int set)
+{
+    uint16_t *g = nbc_col(c, carrier, 0);
+    const int wm = c.W - 1;
+    int k = a, e = a + n;
+    const uint64_t m4 = (uint64_t)(mask & 0xFFFFu) * 0x0001000100010001ULL;
+    NB_NOUNROLL
+    while (k < e && (k & 3)) { g[k & wm] = set ? (uint16_t)(g[k & wm] | mask) : (uint16_t)0; ++k; }
+    if (set) {
+        NB_NOUNROLL
+        for (; k + 4 <= e; k += 4) { nb_u64a *p = (nb_u64a *)&g[k & wm]; *p = *p | m4; }
+    } else {
+        NB_NOUNROLL
+        for (; k + 4 <= e; k += 4) *(nb_u64a *)&g[k & wm] = 0ULL;
+    }
+    NB_NOUNROLL
+    while (k < e) { g[k & wm] = set ? (uint16_t)(g[k & wm] | mask) : (uint16_t)0; ++k; }
+}
+#elif NB_GRID_MODE == 0
 NB_FN1S uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
 {
     return (uint32_t)nbw_run([&]() -> int {
@@ -1432,6 +1470,20 @@ NB_FN1S uint64_t nbc_next_event(NbCtx &c, int *code)
     if (!h->mac_valid) nbc_mac_refresh(c);
     h->keys[8] = h->cont_n > 0 ? h->next_mac : NB_KEY_NONE;
     uint64_t best = NB_KEY_NONE; int bcode = -1;
+#if NB_LANES == 1
+    /* one lane: the fixed slots, then only the pool entries that hold an event (keys are unique, so no tie to break) */
+    {
+        NB_NOUNROLL
+        for (int j = 0; j < 9; ++j) { uint64_t kj = h->keys[j]; if (kj < best) { best = kj; bcode = j; } }
+        uint64_t used = ~h->pool_free & ((1ULL << NB_EV_POOL) - 1ULL);
+        NB_NOUNROLL
+        while (used) {
+            int i = nbw_ffsll(used) - 1; used &= used - 1ULL;
+            uint64_t kj = h->pool[i].key;
+            if (kj < best) { best = kj; bcode = 16 + i; }
+        }
+    }
+#else
     nbw_run([&]() -> int {
         nbw_sync();
         uint64_t k = NB_KEY_NONE; int cd = -1;
@@ -1463,6 +1515,7 @@ NB_FN1S uint64_t nbc_next_event(NbCtx &c, int *code)
         best = m; bcode = (int)nbw_shfl((uint32_t)cd, src);
         return 0;
     });
+#endif
     *code = best == NB_KEY_NONE ? -1 : bcode;
     return best;
 }

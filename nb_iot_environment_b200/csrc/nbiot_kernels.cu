@@ -44,6 +44,8 @@ struct nbiot_handle {
     int blocks, smem_bytes, sim_hi;
     int blocks_short, smem_short, sim_hi_short, stage_policy;     /* geometry of launches that leave the grid in HBM */
     NbSimVariant k_gen, k_c1, k_gs, k_c1s;   /* builds of the warp-per-instance kernels (nbiot_simk.cuh): generic / single carrier, ring anywhere / staged */
+    NbSimVariant k_tpc_gen, k_tpc_c1;        /* builds of the thread-per-cell kernel (nbiot_simt.cuh) */
+    int use_tpc;                 /* advances run on the thread-per-cell kernel (large batches; NBIOT_KERNEL=tpc|warp overrides) */
     int use_staged_builds;       /* measurement knob NBIOT_SIM_STAGED_BUILDS=0: staged launches on the ring-anywhere builds */
     int use_c1;                  /* single-carrier batch: the c1 build (the generic one while an event log is attached) */
     int q_all;                   /* test knob: short launches too */
@@ -177,6 +179,14 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
         if (rc) return rc;
         h->launches += 1;                              /* the queue-initialisation kernel */
     }
+    else if (mode == 2 && h->use_tpc && !h->evlog) {
+        /* one thread per cell: header in local memory, ring / lists / UE records in place in HBM */
+        NbKernelArgs T = make_args(h, 0);
+        const NbSimVariant *v = h->use_c1 ? &h->k_tpc_c1 : &h->k_tpc_gen;
+        int threads = v->warps_per_block * 32;
+        void *args[] = { (void *)&T, (void *)&ext_actions, (void *)&active, (void *)&until_time, (void *)&max_steps };
+        CK(cudaLaunchKernel(v->sim_lo, dim3((h->n_inst + threads - 1) / threads), dim3(threads), args, 0, st));
+    }
     else if (mode == 2) {
         const NbSimVariant *v = sim_variant(h, stage);
         void *args[] = { (void *)&A, (void *)&ext_actions, (void *)&active, (void *)&until_time, (void *)&max_steps };
@@ -247,6 +257,12 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     CK(cudaGetDeviceProperties(&prop, device));
     if ((size_t)h->smem_bytes > prop.sharedMemPerBlockOptin) return set_err(NBIOT_E_INVALID, "grid_w too large for the shared memory of one CTA");
     nb_sim_variant_generic(&h->k_gen); nb_sim_variant_c1(&h->k_c1); nb_sim_variant_gs(&h->k_gs); nb_sim_variant_c1s(&h->k_c1s);
+    nb_sim_variant_tpc_gen(&h->k_tpc_gen); nb_sim_variant_tpc_c1(&h->k_tpc_c1);
+    /* Which kernel advances the batch. One warp per cell keeps a cell's latency low but repeats the scalar control logic on 32
+     * lanes; one thread per cell shares every common instruction between 32 cells but needs the cells to fill the machine
+     * (148 SMs x 16 warps x 32 lanes = 75 776) -- DESIGN.md section 6c has the measured crossover. */
+    h->use_tpc = n_inst >= NB_TPC_MIN_CELLS;
+    if (const char *e = getenv("NBIOT_KERNEL")) { if (!strcmp(e, "tpc")) h->use_tpc = 1; else if (!strcmp(e, "warp")) h->use_tpc = 0; }
     h->use_staged_builds = getenv("NBIOT_SIM_STAGED_BUILDS") ? atoi(getenv("NBIOT_SIM_STAGED_BUILDS")) : 1;
     h->use_c1 = L.n_carriers == 1;
     if (const char *e = getenv("NBIOT_SIM_VARIANT")) h->use_c1 = h->use_c1 && strcmp(e, "generic") != 0;   /* measurement knob */

@@ -70,6 +70,12 @@ void nb_sim_variant_generic(NbSimVariant *out);
 void nb_sim_variant_c1(NbSimVariant *out);
 void nb_sim_variant_gs(NbSimVariant *out);
 void nb_sim_variant_c1s(NbSimVariant *out);
+/* ---- builds of the thread-per-cell kernel (nbiot_simt.cuh) ---- */
+void nb_sim_variant_tpc_gen(NbSimVariant *out);
+void nb_sim_variant_tpc_c1(NbSimVariant *out);
+#ifndef NB_TPC_MIN_CELLS
+#define NB_TPC_MIN_CELLS 32768      /* batches from this size on advance on the thread-per-cell kernel */
+#endif
 
 /* ---- migrating-instance kernel (nbiot_queue.cu) ---- */
 struct NbQueueRt;                                   /* device-side queues of one handle */

@@ -1,0 +1,80 @@
+/*
+ * nbiot_simt.cuh -- the thread-per-cell simulation kernel: one THREAD advances one cell, a warp carries 32 unrelated cells.
+ *
+ * The warp-per-cell kernel (nbiot_simk.cuh) spends 31/32 of its issue slots on copies of the scalar control logic of the reference
+ * (event selection, NodeB FSM, first-fit search, receptions) and is bound by instruction supply, not by memory
+ * (DESIGN.md section 6). With the batches of BASELINE.json configs[2..4] (65 536 ... 4 000 000 cells) there are enough cells to
+ * fill the machine with one cell per lane: the same core source is compiled with NB_TPC (a "warp" of ONE lane, nbiot_warp.h), the
+ * lane-parallel sections become scalar loops, and 32 cells share every instruction they have in common; cells of a warp that
+ * sit in different handlers diverge and reconverge at the event loop.
+ *
+ * State: the per-cell header (NbHdr, 3.5 KB) is copied into the thread's LOCAL memory for the launch. Local memory is
+ * interleaved by the hardware -- word w of lane l sits next to word w of lane l+1 -- so the 32 headers of a warp are read and
+ * written with coalesced, L1-cached accesses although the source addresses them as one plain struct; the copy in and out
+ * is 2 x 3.5 KB per cell per launch. The look-ahead ring, the lists and the UE records stay in HBM and are reached with the
+ * cell's own pointers (scattered 8- and 16-byte accesses through L1/L2).
+ *
+ * Included by one translation unit per build (single carrier / generic), like nbiot_simk.cuh.
+ */
+#ifndef NBIOT_SIMT_CUH
+#define NBIOT_SIMT_CUH
+
+#ifndef NB_TPC
+#error "nbiot_simt.cuh needs NB_TPC (the one-lane build of the core)"
+#endif
+#include "nbiot_core.cuh"
+#include "nbiot_launch.h"
+
+#ifndef NB_TPC_THREADS
+#define NB_TPC_THREADS 128
+#endif
+#ifndef NB_TPC_MIN_CTAS
+#define NB_TPC_MIN_CTAS 4
+#endif
+
+#define NB_CAT2(a, b) a##b
+#define NB_CAT(a, b) NB_CAT2(a, b)
+namespace NB_CAT(nbk_, NB_SIM_VARIANT) {
+
+struct __align__(16) NbLocal { NbCtx c; NbHdr h; };      /* nbc_hdr(c) = the bytes behind the context */
+
+__global__ void __launch_bounds__(NB_TPC_THREADS, NB_TPC_MIN_CTAS)
+nbiot_simt_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps)
+{
+    __shared__ NbCtaConst s_ctrl;                      /* the controller tables + cold configuration, once per CTA */
+    for (int k = threadIdx.x; k < (int)(sizeof(NbCtaConst) / 4); k += blockDim.x) ((uint32_t *)&s_ctrl)[k] = ((const uint32_t *)A.ctrl)[k];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.L.n_inst) return;
+    if (active && !active[i]) return;
+    NbLocal L;
+    nb_fill_ctx_launch(L.c, A, &s_ctrl);
+    nb_fill_ctx(L.c, A, i);
+    uint4 *hg = (uint4 *)((NbHdr *)(A.state + A.L.off_hdr) + i), *hl = (uint4 *)&L.h;
+    NB_NOUNROLL
+    for (int k = 0; k < (int)(sizeof(NbHdr) / 16); ++k) hl[k] = hg[k];
+    unsigned long long t0 = 0;
+    if (A.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    nbc_controller_advance(L.c, L.c.ctrl, ext_actions ? ext_actions + (size_t)i * L.c.ctrl->ext_k : nullptr, until_time, max_steps);
+    if (A.prof) {
+        unsigned long long t1; unsigned int smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        A.prof[4 * (size_t)i] = t0; A.prof[4 * (size_t)i + 1] = t1; A.prof[4 * (size_t)i + 2] = smid; A.prof[4 * (size_t)i + 3] = 0ull;
+    }
+    NB_NOUNROLL
+    for (int k = 0; k < (int)(sizeof(NbHdr) / 16); ++k) hg[k] = hl[k];
+}
+
+}   /* namespace nbk_<variant> */
+
+void NB_CAT(nb_sim_variant_, NB_SIM_VARIANT)(NbSimVariant *out)
+{
+    using namespace NB_CAT(nbk_, NB_SIM_VARIANT);
+    out->sim_lo = (const void *)nbiot_simt_kernel;
+    out->sim_hi = (const void *)nbiot_simt_kernel;
+    out->reset = nullptr;                               /* construction and reset run on the warp-per-cell kernels */
+    out->warps_per_block = NB_TPC_THREADS / 32;
+}
+
+#endif /* NBIOT_SIMT_CUH */

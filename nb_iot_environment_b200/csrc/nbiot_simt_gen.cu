@@ -1,0 +1,11 @@
+/*
+ * nbiot_simt_gen.cu -- the thread-per-cell kernel, generic build (1 or 2 carriers; see nbiot_simt.cuh).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define NB_TPC 1
+#define NB_NO_EVLOG 1
+#define NB_SIM_VARIANT tpc_gen
+#include "nbiot.h"
+#include "nbiot_simt.cuh"

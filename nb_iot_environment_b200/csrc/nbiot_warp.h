@@ -64,12 +64,26 @@
 #endif
 #define NB_FULL 0xFFFFFFFFu
 #define NB_NOUNROLL _Pragma("unroll 1")
+#ifdef NB_TPC
+/* thread-per-cell build (nbiot_simt.cu): one THREAD owns a cell, a warp carries 32 unrelated cells. The lane-parallel sections
+ * degenerate to scalar loops (a "warp" of one lane, exactly the NBIOT_EMU_LANES == 1 build the CPU tests run), nothing is
+ * exchanged between the lanes, and divergence between the 32 cells of a warp is left to the hardware. */
+#undef NB_LANES
+#define NB_LANES 1
+NB_DEV int nbw_lane() { return 0; }
+NB_DEV void nbw_sync() {}
+NB_DEV uint32_t nbw_ballot(int p) { return p ? 1u : 0u; }
+NB_DEV uint32_t nbw_shfl(uint32_t v, int) { return v; }
+NB_DEV uint32_t nbw_shfl_xor(uint32_t v, int) { return v; }
+NB_DEV uint32_t nbw_atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+#else
 NB_DEV int nbw_lane() { return (int)(threadIdx.x & 31u); }
 NB_DEV void nbw_sync() { __syncwarp(NB_FULL); }
 NB_DEV uint32_t nbw_ballot(int p) { return __ballot_sync(NB_FULL, p); }
 NB_DEV uint32_t nbw_shfl(uint32_t v, int src) { return __shfl_sync(NB_FULL, v, src); }
 NB_DEV uint32_t nbw_shfl_xor(uint32_t v, int m) { return __shfl_xor_sync(NB_FULL, v, m); }
 NB_DEV uint32_t nbw_atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
+#endif
 NB_DEV int nbw_popc(uint32_t v) { return __popc(v); }
 NB_DEV int nbw_ffs(uint32_t v) { return __ffs((int)v); }
 NB_DEV int nbw_popcll(uint64_t v) { return __popcll(v); }
@@ -145,7 +159,9 @@ NB_DEV uint64_t nbw_shfl64(uint64_t v, int src)
 
 NB_DEV uint64_t nbw_min_u64(uint64_t v)
 {
-#if defined(__CUDA_ARCH__)
+#if NB_LANES == 1
+    return v;
+#elif defined(__CUDA_ARCH__)
     /* two redux.sync steps: the smallest high word, then the smallest low word among its holders */
     uint32_t hi = (uint32_t)(v >> 32), mh = __reduce_min_sync(NB_FULL, hi);
     uint32_t ml = __reduce_min_sync(NB_FULL, hi == mh ? (uint32_t)v : 0xFFFFFFFFu);
@@ -162,7 +178,9 @@ NB_DEV uint64_t nbw_min_u64(uint64_t v)
 
 NB_DEV uint32_t nbw_or_u32(uint32_t v)
 {
-#if defined(__CUDA_ARCH__)
+#if NB_LANES == 1
+    return v;
+#elif defined(__CUDA_ARCH__)
     return __reduce_or_sync(NB_FULL, v);
 #else
     for (int m = NB_LANES / 2; m > 0; m >>= 1) v |= nbw_shfl_xor(v, m);
@@ -172,7 +190,9 @@ NB_DEV uint32_t nbw_or_u32(uint32_t v)
 
 NB_DEV int32_t nbw_add_i32(int32_t v)
 {
-#if defined(__CUDA_ARCH__)
+#if NB_LANES == 1
+    return v;
+#elif defined(__CUDA_ARCH__)
     return __reduce_add_sync(NB_FULL, v);
 #else
     for (int m = NB_LANES / 2; m > 0; m >>= 1) v += (int32_t)nbw_shfl_xor((uint32_t)v, m);

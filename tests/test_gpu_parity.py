@@ -40,8 +40,16 @@ def _built():
     g.build()
 
 
+@pytest.fixture(params=['warp', 'tpc'])
+def kernel(request, monkeypatch):
+    """both simulation kernels: one warp per cell (csrc/nbiot_simk.cuh) and one thread per cell (csrc/nbiot_simt.cuh); without the
+    knob nbiot_create picks by batch size"""
+    monkeypatch.setenv('NBIOT_KERNEL', request.param)
+    return request.param
+
+
 @pytest.mark.parametrize('case', CASES)
-def test_golden_traces_and_oracle(case):
+def test_golden_traces_and_oracle(case, kernel):
     """NodeB.step-level replay of the reference's traces: every decision record of every seed."""
     from nb_iot_environment_b200 import BatchedNBIoTEnv
     from oracle.oracle_py import OracleCell
@@ -178,6 +186,38 @@ def test_migrating_instances_equal_warp_per_instance(monkeypatch):
     assert np.array_equal(states[0], states[1])
 
 
+def test_thread_per_cell_equals_warp_per_cell(monkeypatch):
+    """NBIOT_KERNEL=tpc: every advance runs on the thread-per-cell kernel (csrc/nbiot_simt.cuh: the one-lane build of the core, header
+    in local memory, 32 unrelated cells per warp). Same state buffer as the warp-per-cell kernel, byte for byte, on short launches
+    (external scheduling agent, 2 carriers), on long ones (NPRACH agent external, single-carrier build) and on run_until; ragged
+    batch sizes (not a multiple of the CTA), masked advances."""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    states = []
+    for kern in ('warp', 'tpc'):
+        monkeypatch.setenv('NBIOT_KERNEL', kern)
+        out = []
+        N = 700
+        env = BatchedNBIoTEnv(CFG3, agents_conf=NPUSCH_AGENTS, ext_agent=0, num_envs=N, seeds=list(range(N)), n_carriers=2, ue_cap=512, grid_w=2048, hist_cap=64)
+        env.reset()
+        r = np.random.default_rng(5)
+        for _ in range(60):
+            env.step(_random_ext_actions(r, env.action_nvec, N))
+        env.run_until(6000)
+        torch.cuda.synchronize()
+        out.append(env.state.cpu().numpy().copy()); assert env.stats()['faulted'] == 0; env.close()
+        N = 333
+        env = BatchedNBIoTEnv(dict(CFG1, ratio=0.5), agents_conf=NPRACH_AGENTS, ext_agent=3, num_envs=N, seeds=list(range(N)), ue_cap=1000, grid_w=2048, hist_cap=512)
+        env.reset()
+        for _ in range(3):
+            env.step(_random_ext_actions(r, env.action_nvec, N))
+        env.run_until(12000)
+        torch.cuda.synchronize()
+        out.append(env.state.cpu().numpy().copy()); assert env.stats()['faulted'] == 0; env.close()
+        states.append(out)
+    assert np.array_equal(states[0][0], states[1][0]) and np.array_equal(states[0][1], states[1][1])
+
+
 def test_per_cell_launch_timing(monkeypatch):
     """NBIOT_PROF_INST=1: start / end time and SM of every cell in the last simulation launch (measurement aid, tools/inst_times.py)"""
     from nb_iot_environment_b200 import BatchedNBIoTEnv, _cabi
@@ -235,7 +275,7 @@ def _random_ext_actions(rng, nvec, n):
 
 
 @pytest.mark.parametrize('scenario', ['nprach', 'npusch'])
-def test_controller_split_against_oracle(scenario):
+def test_controller_split_against_oracle(scenario, kernel):
     """config 2 / config 3: the external agent acts, the internal fixed-action agents live on the device."""
     from nb_iot_environment_b200 import BatchedNBIoTEnv
     from oracle_controller import OracleController
@@ -278,7 +318,7 @@ def test_controller_split_against_oracle(scenario):
     env.close()
 
 
-def test_run_until_on_internal_agents():
+def test_run_until_on_internal_agents(kernel):
     """config 1 / 5 style: no external agent, default agents on the device, one launch to the horizon."""
     from nb_iot_environment_b200 import BatchedNBIoTEnv
     from oracle_controller import OracleController
