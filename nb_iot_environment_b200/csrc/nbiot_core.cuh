@@ -474,6 +474,68 @@ NB_FNM3 int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc
     if (spr < 0) { NB_FAULT(c, NBIOT_FAULT_ACTION); *out_sc = N_sc; *out_sf = 0; return 0; }
     int n_sc = N_sc, N_sf = spr * N_ru * N_rep;
     NB_COUNT(8, 1);
+#if NB_LANES == 32 && !defined(NB_NO_EDGE_REJECT) && !defined(NB_NO_FAST_FIT)
+    /* All (subcarrier count, delay, carrier) combinations at once. The search below tries up to 4 x 4 x C windows one after the
+     * other and, in a loaded cell, loses most of them on the edge test alone (the subcarriers busy in the first or last column of
+     * a window leave no aligned group free). When every window of the search already lies inside the generated look-ahead, no
+     * combination can extend it, so the outcome of each is a function of the ring alone: one lane per combination, in the order
+     * of the search, takes the edge test; the ballot names the windows that still need their columns scanned, and they are
+     * scanned in that order. An attempt that fails everywhere -- two thirds of them on the NPRACH-control workload -- costs one
+     * pass instead of sixteen. */
+    {
+        NbHdr *h = nbc_hdr(c);
+        nbc_erase_past_sf(c, ref_t);
+        if (NB_FATAL(c)) { *out_sc = N_sc; *out_sf = N_sf; return 0; }
+        const int row0 = N_sc == 1 ? 0 : N_sc == 3 ? 1 : N_sc == 6 ? 2 : 3;
+        const int n_try = c.conf.sc_adjustment ? 4 : 1;
+        const int sc_min = n_try == 4 ? (nb_sc_fallback[row0][2] < N_sc ? nb_sc_fallback[row0][2] : N_sc) : N_sc;
+        const int t_now = h->t_now;
+        if (delay >= 1 && t_now + 64 + nbc_sf_per_ru(sc_min) * N_ru * N_rep <= h->t_ahead) {
+            const int unit = N_ru * N_rep;
+            NB_COUNT(12, 1);
+            uint32_t live = (uint32_t)nbw_run([&]() -> int {
+                const int l = nbw_lane(), s = l >> 3, k = (l >> 1) & 3, ci = l & 1;
+                const int nsc = s == 0 ? N_sc : nb_sc_fallback[row0][s > 0 ? s - 1 : 0];
+                const int d = delay << k;
+                int ok = s < n_try && d <= 64 && ci < NB_NC(c);
+                if (ok) {
+                    const int row = nsc == 1 ? 0 : nsc == 3 ? 1 : nsc == 6 ? 2 : 3;
+                    const int cc = ci == 0 ? c_id : (c_id == 0 ? 1 : 0), from = t_now + d, nsf = nbc_sf_per_ru(nsc) * unit;
+                    uint32_t ef = (uint32_t)*nbc_col(c, cc, from) | (uint32_t)*nbc_col(c, cc, from + nsf - 1);
+                    if (row >= 1) ef |= (ef >> 1) | (ef >> 2);
+                    if (row >= 2) ef |= ef >> 3;
+                    if (row == 3) ef |= ef >> 6;
+                    ok = (~ef & nb_sc_heads[row]) != 0u;
+                }
+                return (int)nbw_ballot(ok);
+            });
+            NB_COUNT(14, live == 0u);
+            NB_NOUNROLL
+            while (live) {
+                const int l = nbw_ffs(live) - 1; live &= live - 1u;
+                NB_COUNT(15, 1);
+                const int s = l >> 3, k = (l >> 1) & 3, ci = l & 1;
+                const int nsc = s == 0 ? N_sc : nb_sc_fallback[row0][s - 1];
+                const int row = nsc == 1 ? 0 : nsc == 3 ? 1 : nsc == 6 ? 2 : 3;
+                const int cc = ci == 0 ? c_id : (c_id == 0 ? 1 : 0), d = delay << k, from = t_now + d, nsf = nbc_sf_per_ru(nsc) * unit;
+                uint32_t busy = nbc_grid_busy(c, cc, from, nsf), fold = busy;
+                if (row >= 1) fold |= (busy >> 1) | (busy >> 2);
+                if (row >= 2) fold |= fold >> 3;
+                if (row == 3) fold |= fold >> 6;
+                uint32_t pick = ~fold & nb_sc_heads[row];
+                if (pick) {
+                    nbc_grid_or(c, cc, from, nsf, ((1u << nsc) - 1u) << (nbw_ffs(pick) - 1));
+                    *out_sc = nsc; *out_sf = nsf;
+                    NB_COUNT(13, 1);
+                    return ref_t + d + nsf;
+                }
+            }
+            n_sc = n_try == 4 ? nb_sc_fallback[row0][2] : N_sc;
+            *out_sc = n_sc; *out_sf = nbc_sf_per_ru(n_sc) * unit;
+            return 0;
+        }
+    }
+#endif
     int t_ul_end = nbc_carrier_allocate(c, c_id, ref_t, delay, N_sc, N_sf);
     NB_COUNT(9, t_ul_end != 0);
     if (!t_ul_end && c.conf.sc_adjustment && !NB_FATAL(c)) {

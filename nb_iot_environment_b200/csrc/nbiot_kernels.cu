@@ -185,7 +185,7 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
         const NbSimVariant *v = h->use_c1 ? &h->k_tpc_c1 : &h->k_tpc_gen;
         int threads = v->warps_per_block * 32;
         void *args[] = { (void *)&T, (void *)&ext_actions, (void *)&active, (void *)&until_time, (void *)&max_steps };
-        CK(cudaLaunchKernel(v->sim_lo, dim3((h->n_inst + threads - 1) / threads), dim3(threads), args, 0, st));
+        CK(cudaLaunchKernel(h->use_tpc == 2 ? v->sim_hi : v->sim_lo, dim3((h->n_inst + threads - 1) / threads), dim3(threads), args, 0, st));
     }
     else if (mode == 2) {
         const NbSimVariant *v = sim_variant(h, stage);
@@ -262,7 +262,7 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
      * lanes; one thread per cell shares every common instruction between 32 cells but needs the cells to fill the machine
      * (148 SMs x 16 warps x 32 lanes = 75 776) -- DESIGN.md section 6c has the measured crossover. */
     h->use_tpc = n_inst >= NB_TPC_MIN_CELLS;
-    if (const char *e = getenv("NBIOT_KERNEL")) { if (!strcmp(e, "tpc")) h->use_tpc = 1; else if (!strcmp(e, "warp")) h->use_tpc = 0; }
+    if (const char *e = getenv("NBIOT_KERNEL")) { if (!strcmp(e, "tpc")) h->use_tpc = 1; else if (!strcmp(e, "tpcv")) h->use_tpc = 2; else if (!strcmp(e, "warp")) h->use_tpc = 0; }
     h->use_staged_builds = getenv("NBIOT_SIM_STAGED_BUILDS") ? atoi(getenv("NBIOT_SIM_STAGED_BUILDS")) : 1;
     h->use_c1 = L.n_carriers == 1;
     if (const char *e = getenv("NBIOT_SIM_VARIANT")) h->use_c1 = h->use_c1 && strcmp(e, "generic") != 0;   /* measurement knob */

@@ -66,13 +66,58 @@ nbiot_simt_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *act
     for (int k = 0; k < (int)(sizeof(NbHdr) / 16); ++k) hg[k] = hl[k];
 }
 
+/* The same with VOTED DISPATCH. Left to themselves the 32 cells of a warp are in as many different event handlers as the event
+ * mix has classes, and SIMT divergence runs every handler present in turn with two or three active lanes each (measured: 2.5 of 32,
+ * profiles/r02a_*). Here the cell's control flow is the task chain of the core (nbiot_core.cuh "tasks": one heavy handler per
+ * task + the glue behind it, control state in NbHdr.tk_*): every round the warp votes for ONE task class -- the one with the most
+ * waiting lanes, waiting time breaking ties so that nobody starves -- and only the lanes that wait for it run; the others keep their
+ * task for a later round, when more lanes have joined their class. A handler is therefore entered by all its lanes together and
+ * walked once for all of them. */
+__global__ void __launch_bounds__(NB_TPC_THREADS, NB_TPC_MIN_CTAS)
+nbiot_simtv_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps)
+{
+    __shared__ NbCtaConst s_ctrl;
+    for (int k = threadIdx.x; k < (int)(sizeof(NbCtaConst) / 4); k += blockDim.x) ((uint32_t *)&s_ctrl)[k] = ((const uint32_t *)A.ctrl)[k];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = i < A.L.n_inst && !(active && !active[i]);
+    NbLocal L;
+    uint4 *hg = (uint4 *)((NbHdr *)(A.state + A.L.off_hdr) + (mine ? i : 0)), *hl = (uint4 *)&L.h;
+    int k = NB_TK_DONE;
+    if (mine) {
+        nb_fill_ctx_launch(L.c, A, &s_ctrl);
+        nb_fill_ctx(L.c, A, i);
+        NB_NOUNROLL
+        for (int w = 0; w < (int)(sizeof(NbHdr) / 16); ++w) hl[w] = hg[w];
+        L.c.tk_until = until_time; L.c.tk_max_steps = max_steps;
+        k = nbc_task_begin(L.c, ext_actions ? ext_actions + (size_t)i * L.c.ctrl->ext_k : nullptr);
+    }
+    int waited = 0;
+    for (;;) {
+        __syncwarp(NB_FULL);
+        if (!__ballot_sync(NB_FULL, k != NB_TK_DONE)) break;
+        int best = 0, best_score = 0;
+#pragma unroll
+        for (int cl = 1; cl < NB_TK_N; ++cl) {
+            int sc = __reduce_add_sync(NB_FULL, k == cl ? 4 + waited : 0);
+            if (sc > best_score) { best_score = sc; best = cl; }
+        }
+        if (k == best) { k = nbc_task_run(L.c, k); waited = 0; }
+        else if (k != NB_TK_DONE) waited += 1;
+    }
+    if (mine) {
+        NB_NOUNROLL
+        for (int w = 0; w < (int)(sizeof(NbHdr) / 16); ++w) hg[w] = hl[w];
+    }
+}
+
 }   /* namespace nbk_<variant> */
 
 void NB_CAT(nb_sim_variant_, NB_SIM_VARIANT)(NbSimVariant *out)
 {
     using namespace NB_CAT(nbk_, NB_SIM_VARIANT);
     out->sim_lo = (const void *)nbiot_simt_kernel;
-    out->sim_hi = (const void *)nbiot_simt_kernel;
+    out->sim_hi = (const void *)nbiot_simtv_kernel;
     out->reset = nullptr;                               /* construction and reset run on the warp-per-cell kernels */
     out->warps_per_block = NB_TPC_THREADS / 32;
 }

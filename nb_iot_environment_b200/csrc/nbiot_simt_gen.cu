@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #define NB_TPC 1
+#define NB_TASKS 1
 #define NB_NO_EVLOG 1
 #define NB_SIM_VARIANT tpc_gen
 #include "nbiot.h"

@@ -57,6 +57,13 @@ struct Staged {
     }
 };
 
+#ifdef NBIOT_EMU_TASKS
+// optional (instance, task class) log of the task chain: measurement aid for scheduling studies (tools/vote_sim.py)
+int32_t *emu_tasklog = NULL; int emu_tasklog_cap = 0, emu_tasklog_n = 0;
+extern "C" void emu_set_tasklog(int32_t *buf, int cap) { emu_tasklog = buf; emu_tasklog_cap = cap; emu_tasklog_n = 0; }
+extern "C" int emu_tasklog_len(void) { return emu_tasklog_n; }
+#endif
+
 extern "C" {
 
 int emu_lanes(void) { return NB_LANES; }
@@ -96,13 +103,17 @@ void emu_advance(void *p, const uint8_t *ext_actions, int until_time, int max_st
 {
     Emu *e = (Emu *)p;
 #ifdef NBIOT_EMU_TASKS
+    extern int32_t *emu_tasklog; extern int emu_tasklog_cap, emu_tasklog_n;
     // the task chain of the migrating-instance kernel, with the instance stored to and reloaded from the state buffer between
     // two tasks into a fresh context -- what a hop to another SM does -- so that nothing can survive outside NbHdr
     for (int i = 0; i < e->L.n_inst; ++i) {
         const uint8_t *a = ext_actions ? ext_actions + (size_t)i * e->cc.ctrl.ext_k : NULL;
         int k;
         { Staged st(e, i, true); st.c->tk_until = until_time; st.c->tk_max_steps = max_steps; k = nbc_task_begin(*st.c, a); }
-        while (k != NB_TK_DONE) { Staged st(e, i, true); st.c->tk_until = until_time; st.c->tk_max_steps = max_steps; k = nbc_task_run(*st.c, k); }
+        while (k != NB_TK_DONE) {
+            if (emu_tasklog && emu_tasklog_n < emu_tasklog_cap) { emu_tasklog[2 * emu_tasklog_n] = i; emu_tasklog[2 * emu_tasklog_n + 1] = k; emu_tasklog_n += 1; }
+            Staged st(e, i, true); st.c->tk_until = until_time; st.c->tk_max_steps = max_steps; k = nbc_task_run(*st.c, k);
+        }
         if (steps_out) steps_out[i] = ((NbHdr *)(e->state + e->L.off_hdr) + i)->tk_steps;
     }
 #else

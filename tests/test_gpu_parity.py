@@ -40,10 +40,10 @@ def _built():
     g.build()
 
 
-@pytest.fixture(params=['warp', 'tpc'])
+@pytest.fixture(params=['warp', 'tpc', 'tpcv'])
 def kernel(request, monkeypatch):
-    """both simulation kernels: one warp per cell (csrc/nbiot_simk.cuh) and one thread per cell (csrc/nbiot_simt.cuh); without the
-    knob nbiot_create picks by batch size"""
+    """the simulation kernels: one warp per cell (csrc/nbiot_simk.cuh), one thread per cell and one thread per cell with voted
+    dispatch (csrc/nbiot_simt.cuh); without the knob nbiot_create picks by batch size"""
     monkeypatch.setenv('NBIOT_KERNEL', request.param)
     return request.param
 
@@ -192,9 +192,16 @@ def test_thread_per_cell_equals_warp_per_cell(monkeypatch):
     (external scheduling agent, 2 carriers), on long ones (NPRACH agent external, single-carrier build) and on run_until; ragged
     batch sizes (not a multiple of the CTA), masked advances."""
     import torch
-    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from nb_iot_environment_b200 import BatchedNBIoTEnv, _cabi
+    hdr, tk = _cabi.load().nbiot_hdr_bytes(), _cabi.load().nbiot_hdr_task_bytes()
+
+    def snapshot(env, N):
+        torch.cuda.synchronize()
+        st = env.state.cpu().numpy().copy()
+        st[:N * hdr].reshape(N, hdr)[:, hdr - tk:] = 0          # NbHdr.tk_*: only the task-chain kernels write them
+        return st
     states = []
-    for kern in ('warp', 'tpc'):
+    for kern in ('warp', 'tpc', 'tpcv'):
         monkeypatch.setenv('NBIOT_KERNEL', kern)
         out = []
         N = 700
@@ -204,18 +211,17 @@ def test_thread_per_cell_equals_warp_per_cell(monkeypatch):
         for _ in range(60):
             env.step(_random_ext_actions(r, env.action_nvec, N))
         env.run_until(6000)
-        torch.cuda.synchronize()
-        out.append(env.state.cpu().numpy().copy()); assert env.stats()['faulted'] == 0; env.close()
+        out.append(snapshot(env, N)); assert env.stats()['faulted'] == 0; env.close()
         N = 333
         env = BatchedNBIoTEnv(dict(CFG1, ratio=0.5), agents_conf=NPRACH_AGENTS, ext_agent=3, num_envs=N, seeds=list(range(N)), ue_cap=1000, grid_w=2048, hist_cap=512)
         env.reset()
         for _ in range(3):
             env.step(_random_ext_actions(r, env.action_nvec, N))
         env.run_until(12000)
-        torch.cuda.synchronize()
-        out.append(env.state.cpu().numpy().copy()); assert env.stats()['faulted'] == 0; env.close()
+        out.append(snapshot(env, N)); assert env.stats()['faulted'] == 0; env.close()
         states.append(out)
-    assert np.array_equal(states[0][0], states[1][0]) and np.array_equal(states[0][1], states[1][1])
+    for other in states[1:]:
+        assert np.array_equal(states[0][0], other[0]) and np.array_equal(states[0][1], other[1])
 
 
 def test_per_cell_launch_timing(monkeypatch):
