@@ -142,6 +142,9 @@ int nbiot_queue_stats(nbiot_handle_t *h, unsigned long long out[32]);
 int nbiot_instance_times(nbiot_handle_t *h, unsigned long long *out_host);
 /* launch geometry chosen at creation: blocks, warps per block, dynamic shared memory per block */
 int nbiot_launch_geometry(nbiot_handle_t *h, int *blocks, int *warps_per_block, int *smem_bytes);
+/* which simulation kernel advances this batch: "warp-per-cell", "thread-per-cell" or "thread-per-cell, voted dispatch" (chosen at
+ * creation by batch size; NBIOT_KERNEL=warp|tpc|tpcv in the environment overrides; the results are bit-identical) */
+const char *nbiot_kernel_name(nbiot_handle_t *h);
 
 /* host twins of the counter-based random stream (include/nbiot_rng.h): the same compiled arithmetic
  * the kernels use, for the generator shim that drives the reference (rng argument of

@@ -85,6 +85,9 @@ def load():
         L.nbiot_queue_stats.argtypes = [vp, vp]
     L.nbiot_launch_count.argtypes = [vp]
     L.nbiot_launch_geometry.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    if hasattr(L, 'nbiot_kernel_name'):
+        L.nbiot_kernel_name.restype = ctypes.c_char_p
+        L.nbiot_kernel_name.argtypes = [vp]
     L.nbiot_rng_u01.restype = ctypes.c_double
     L.nbiot_rng_u01.argtypes = [u64, u64, u32]
     L.nbiot_rng_normal.restype = ctypes.c_double

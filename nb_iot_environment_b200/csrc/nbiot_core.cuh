@@ -474,7 +474,7 @@ NB_FNM3 int nbc_node_allocate(NbCtx &c, int c_id, int ref_t, int delay, int N_sc
     if (spr < 0) { NB_FAULT(c, NBIOT_FAULT_ACTION); *out_sc = N_sc; *out_sf = 0; return 0; }
     int n_sc = N_sc, N_sf = spr * N_ru * N_rep;
     NB_COUNT(8, 1);
-#if NB_LANES == 32 && !defined(NB_NO_EDGE_REJECT) && !defined(NB_NO_FAST_FIT)
+#if NB_LANES == 32 && !defined(NB_NO_EDGE_REJECT) && defined(NB_FAST_FIT)
     /* All (subcarrier count, delay, carrier) combinations at once. The search below tries up to 4 x 4 x C windows one after the
      * other and, in a loaded cell, loses most of them on the edge test alone (the subcarriers busy in the first or last column of
      * a window leave no aligned group free). When every window of the search already lies inside the generated look-ahead, no
@@ -1988,6 +1988,9 @@ NB_FN int nbc_fel_next(NbCtx &c)
             h->tk_a = e.aux; h->tk_b = t;
             return e.type == NB_EV_MSG3 ? NB_TK_MSG3 : NB_TK_NPUSCH_END;
         }
+#ifdef NB_GLUE_ONE_POP
+        return NB_TK_GLUE;                                     /* one event per glue task: the lanes of a warp pop in lock step */
+#endif
     }
 }
 

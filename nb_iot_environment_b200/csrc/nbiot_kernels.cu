@@ -523,6 +523,13 @@ int nbiot_launch_geometry(nbiot_handle_t *h, int *blocks, int *warps_per_block, 
     return 0;
 }
 
+const char *nbiot_kernel_name(nbiot_handle_t *h)
+{
+    if (!h) return "";
+    if (h->q) return "migrating cells (task queues)";
+    return h->use_tpc == 2 ? "thread-per-cell, voted dispatch" : h->use_tpc ? "thread-per-cell" : "warp-per-cell";
+}
+
 double nbiot_rng_u01(uint64_t seed, uint64_t ctr, uint32_t stream) { return nb_rng_u01(seed, ctr, stream); }
 void nbiot_rng_pair(uint64_t seed, uint64_t ctr, uint32_t stream, double *xy) { nb_rng_pair(seed, ctr, stream, &xy[0], &xy[1]); }
 double nbiot_rng_normal(uint64_t seed, uint64_t ctr, uint32_t stream) { return nb_rng_normal(seed, ctr, stream); }

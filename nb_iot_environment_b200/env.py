@@ -362,6 +362,10 @@ class BatchedNBIoTEnv:
         _cabi.check(self.L.nbiot_launch_geometry(self._h, ctypes.byref(b), ctypes.byref(w), ctypes.byref(s)))
         return {'blocks': b.value, 'warps_per_block': w.value, 'smem_bytes': s.value}
 
+    def kernel_name(self):
+        """which simulation kernel advances this batch (picked by batch size; NBIOT_KERNEL overrides)"""
+        return self.L.nbiot_kernel_name(self._h).decode() if hasattr(self.L, 'nbiot_kernel_name') else 'warp-per-cell'
+
     def enable_event_log(self, cap=1 << 16):
         self._evlog = torch.zeros((cap, 2), dtype=torch.int32, device=self.device)
         _cabi.check(self.L.nbiot_set_event_log(self._h, self._evlog.data_ptr(), cap))

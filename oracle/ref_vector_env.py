@@ -78,7 +78,18 @@ def run(conf, agents, ext_agent, seeds, actions, warmup, processes=None):
              for i in range(P)]
     for p in procs:
         p.start()
-    res = [out.get(timeout=1200) for _ in range(P)]
+    import queue
+    res, deadline = [], time.time() + 1200
+    while len(res) < P:
+        try:
+            res.append(out.get(timeout=2))
+        except queue.Empty:
+            dead = [p for p in procs if not p.is_alive() and p.exitcode not in (0, None)]
+            if dead or time.time() > deadline:       # a worker died before it could report (import error, spawn failure) or hangs
+                for p in procs:
+                    if p.is_alive():
+                        p.kill()
+                raise RuntimeError(f'reference worker exited with code {dead[0].exitcode}' if dead else 'reference workers timed out')
     for p in procs:
         p.join(timeout=30)
     errs = [r[3] for r in res if r[3]]

@@ -61,6 +61,13 @@ def test_core_task_chain(case, oracle_lib):
     _replay(case, '1t', 10 ** 9)
 
 
+@pytest.mark.parametrize('case', CASES)
+def test_core_task_chain_fine_grained(case, oracle_lib):
+    """The task chain as the voted-dispatch thread-per-cell kernel cuts it (csrc/nbiot_simt.cuh): the glue between two handlers is a
+    task class of its own and handles ONE event per task, so that the lanes of a warp pop their events in lock step."""
+    _replay(case, '1tg', 10 ** 9)
+
+
 @pytest.mark.parametrize('case', ['cfg1_default', 'cfg3_npusch_random_policy'])
 def test_event_selection_second_pass(case, oracle_lib):
     """The event selection looks at 32 keys per pass and takes a second pass only when pool entries above the first 22 are in use
