@@ -169,6 +169,7 @@ def cpu_reference_env_arm(steps, warmup, processes=None):
     P = processes or (os.cpu_count() or 1)
     acts = ext_actions(warmup + steps, P, seed=1234)
     r = rv.run(CONF, AGENTS, EXT_AGENT, list(range(P)), acts, warmup, P)
+    r['actions'] = acts
     r.update(kind='reference', cells=P,
              sample=f'{P} reference environments (one per process, {r["reference_dir"]}) x {steps} external steps of {SF_PER_STEP} subframes after '
                     f'{warmup} warm-up steps, same scenario, policy and Philox stream as cells 0..{P - 1} of the GPU job')
@@ -556,6 +557,11 @@ def main():
             r = cpu_reference_env_arm(10, 3)                              # ~1 s per process + import
         except Exception as e:
             print('reference environment leg failed:', repr(e), file=sys.stderr)
+        if r is not None:
+            try:
+                line['parity_vs_reference'] = reference_parity(local_rank, r)
+            except Exception as e:
+                print('live parity leg failed:', repr(e), file=sys.stderr)
         r = r or port
         line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
     sys.stdout.flush()
@@ -568,6 +574,29 @@ def main():
         print('FAULTED OR TRUNCATED INSTANCES in the timed workload (faulted, truncated):', bad, file=sys.stderr)
         return 3
     return 0
+
+
+def reference_parity(local_rank, r):
+    """The cells the reference environments just simulated on the host cores, simulated again on the GPU with the same seeds and
+    actions: observation and reward of every step against the UNMODIFIED reference, live on this box."""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    acts, traces = r['actions'], r['traces']
+    P = acts.shape[1]
+    env = BatchedNBIoTEnv(CONF, agents_conf=AGENTS, ext_agent=EXT_AGENT, num_envs=P, seeds=list(range(P)), device=local_rank, **CAPS)
+    env.reset()
+    worst, rewards_equal = 0.0, True
+    for s in range(acts.shape[0]):
+        obs, rew, _, _, _ = env.step(acts[s])
+        obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
+        for i in range(P):
+            o_ref, r_ref = np.asarray(traces[i][s][0], dtype=np.float64), traces[i][s][1]
+            den = np.maximum(np.abs(o_ref), 1e-300)
+            worst = max(worst, float(np.max(np.where(o_ref == obs[i], 0.0, np.abs(obs[i] - o_ref) / den))))
+            rewards_equal = rewards_equal and (r_ref == rew[i])
+    env.close()
+    return {'cells': P, 'steps': int(acts.shape[0]), 'obs_max_rel_err': worst, 'rewards_equal': bool(rewards_equal),
+            'against': 'the unmodified reference environments of cpu_baseline (same seeds, same actions), every step'}
 
 
 def warp_busy_fraction(local_rank, N, acts):

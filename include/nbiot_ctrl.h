@@ -17,6 +17,9 @@ typedef struct nbiot_ctrl {
     int8_t ext_post[24];              /* writes of the `next` chain after the external action     */
     int8_t state_writes[4][24];       /* fixed actions of the internal agents of each NodeB state */
     uint8_t init_action[24];          /* Controller._initialize_action result                     */
+    int8_t full_writes[4][24];        /* the same with EVERY agent of the state, the external one's fixed action included:
+                                         what Controller.run_until / single_step apply (controller.py:156-195), used by
+                                         advances without an external action */
 } nbiot_ctrl_t;
 
 #endif /* NBIOT_CTRL_H */

@@ -21,7 +21,8 @@ from .record import STATE_IDS
 class NbiotCtrl(ctypes.Structure):
     _fields_ = [('ext_state_mask', ctypes.c_uint32), ('ext_k', ctypes.c_int32),
                 ('ext_a_mask', ctypes.c_uint8 * 24), ('ext_post', ctypes.c_int8 * 24),
-                ('state_writes', (ctypes.c_int8 * 24) * 4), ('init_action', ctypes.c_uint8 * 24)]
+                ('state_writes', (ctypes.c_int8 * 24) * 4), ('init_action', ctypes.c_uint8 * 24),
+                ('full_writes', (ctypes.c_int8 * 24) * 4)]
 
 
 class AgentSpec:
@@ -80,6 +81,13 @@ class ControllerTables:
         for s in range(4):
             for i in range(24):
                 c.state_writes[s][i] = -1
+                c.full_writes[s][i] = -1
+        # Controller.single_step / run_until (controller.py:156-195): every agent of the state acts, whoever is registered as external
+        for sname, ids in self.agents_ids.items():
+            for aid in ids:
+                ag = self.agents[aid]
+                for idx, v in zip(ag.a_mask, ag.fixed_action):
+                    c.full_writes[STATE_IDS[sname]][idx] = v
         for i in range(24):
             c.ext_post[i] = -1
         init = self.initial_action()

@@ -57,6 +57,7 @@ struct __attribute__((aligned(16))) NbCtx {
     uint16_t *grid;           /* the look-ahead ring: staged in shared memory behind the header, or in place in HBM (short launches) */
 #ifdef NB_TASKS
     int tk_until, tk_max_steps;   /* bounds of this launch (see "tasks" at the end of the file) */
+    int tk_internal;              /* the launch has no external action: every agent of a state acts, no state hands control back */
 #endif
 };
 
@@ -1892,27 +1893,31 @@ NB_FNM void nbc_apply_writes(NbCtx &c, const NbWrites *w)
  *   max_steps  : bound on NodeB steps in this call
  * ctrl->state_writes[s] holds the fixed actions of the internal agents of state s; for a state of
  * the external agent it holds only the agents listed before it (controller.py:283-288).
+ * Without an external action (run_until / single_step, controller.py:156-195) EVERY agent of a state acts, the one
+ * registered as external with its fixed action (ctrl->full_writes), and no state hands control back.
  * Returns the number of NodeB steps taken; the decision record is rewritten iff it is > 0. */
 NB_FN int nbc_controller_advance(NbCtx &c, const NbCtrlDev *ctrl, const uint8_t *ext_action, int until_time, int max_steps)
 {
     NbHdr *h = nbc_hdr(c);
     int steps = 0;
     if (NB_FATAL(c)) { c.rec->fault = h->fault; return 0; }
+    const NbWrites *sw = ext_action ? ctrl->state_writes : ctrl->full_writes;
+    const uint32_t ext_mask = ext_action ? ctrl->ext_state_mask : 0u;
     if (ext_action) {
         NB_NOUNROLL
         for (int i = 0; i < ctrl->ext_k; ++i) h->ctrl_action[ctrl->ext_a_mask[i]] = ext_action[i];
         nbc_apply_writes(c, &ctrl->ext_post);
-    } else nbc_apply_writes(c, &ctrl->state_writes[h->state]);
+    } else nbc_apply_writes(c, &sw[h->state]);
     NB_NOUNROLL
     while (steps < max_steps && !(until_time >= 0 && h->time >= until_time)) {
         if (steps > 0) {
             nbc_node_info(c, 0, 0.0);                          /* an internal agent looks at nothing */
-            nbc_apply_writes(c, &ctrl->state_writes[h->state]);
+            nbc_apply_writes(c, &sw[h->state]);
         }
         nbc_node_step(c, h->ctrl_action);
         steps += 1;
         if (NB_FATAL(c)) break;
-        if ((ctrl->ext_state_mask >> h->state) & 1u) { nbc_apply_writes(c, &ctrl->state_writes[h->state]); break; }
+        if ((ext_mask >> h->state) & 1u) { nbc_apply_writes(c, &sw[h->state]); break; }
     }
     if (steps > 0) nbc_node_info(c, 1, nbc_reward(c));
     else c.rec->fault = h->fault;
@@ -2014,10 +2019,11 @@ NB_FN int nbc_task_glue(NbCtx &c)
         /* a NodeB step has run to the next decision */
         h->tk_steps += 1;
         if (NB_FATAL(c)) return NB_TK_FINISH;
-        if ((ctrl->ext_state_mask >> h->state) & 1u) { nbc_apply_writes(c, &ctrl->state_writes[h->state]); return NB_TK_FINISH; }
+        const NbWrites *sw = c.tk_internal ? ctrl->full_writes : ctrl->state_writes;
+        if (!c.tk_internal && ((ctrl->ext_state_mask >> h->state) & 1u)) { nbc_apply_writes(c, &sw[h->state]); return NB_TK_FINISH; }
         if (!(h->tk_steps < c.tk_max_steps && !(c.tk_until >= 0 && h->time >= c.tk_until))) return NB_TK_FINISH;
         nbc_node_info(c, 0, 0.0);                              /* an internal agent looks at nothing */
-        nbc_apply_writes(c, &ctrl->state_writes[h->state]);
+        nbc_apply_writes(c, &sw[h->state]);
         h->tk_phase = NB_PH_FEL;
         int k = nbc_step_class(h->state);
         if (k) return k;
@@ -2036,7 +2042,7 @@ NB_FN int nbc_task_begin(NbCtx &c, const uint8_t *ext_action)
         NB_NOUNROLL
         for (int i = 0; i < ctrl->ext_k; ++i) h->ctrl_action[ctrl->ext_a_mask[i]] = ext_action[i];
         nbc_apply_writes(c, &ctrl->ext_post);
-    } else nbc_apply_writes(c, &ctrl->state_writes[h->state]);
+    } else nbc_apply_writes(c, &ctrl->full_writes[h->state]);
     if (!(0 < c.tk_max_steps && !(c.tk_until >= 0 && h->time >= c.tk_until))) return NB_TK_FINISH;
     int k = nbc_step_class(h->state);
     if (k) return k;
@@ -2072,7 +2078,7 @@ NB_DEV int nbc_task_run(NbCtx &c, int k)
 /* the chain run by one owner; returns the NodeB steps taken */
 NB_FN int nbc_task_chain(NbCtx &c, const uint8_t *ext_action, int until_time, int max_steps)
 {
-    c.tk_until = until_time; c.tk_max_steps = max_steps;
+    c.tk_until = until_time; c.tk_max_steps = max_steps; c.tk_internal = ext_action ? 0 : 1;
     int k = nbc_task_begin(c, ext_action);
     NB_NOUNROLL
     while (k != NB_TK_DONE) k = nbc_task_run(c, k);

@@ -163,7 +163,7 @@ nbiot_simg_kernel(NbKernelArgs A, const uint8_t *ext_actions, int until_time, in
     if (lane == 0) {
         c.lut2 = A.lut2; c.mcs = A.mcs; c.conf = *(const nbiot_conf_hot_t *)A.conf; c.ctrl = &s_ctrl.ctrl;
         c.W = A.L.grid_w; c.ue_cap = A.L.ue_cap; c.ra_cap = A.L.ra_cap; c.hist_cap = A.L.hist_cap; c.C = A.L.n_carriers;
-        c.evlog = nullptr; c.evlog_cap = A.evlog_cap; c.tk_until = until_time; c.tk_max_steps = max_steps;
+        c.evlog = nullptr; c.evlog_cap = A.evlog_cap; c.tk_until = until_time; c.tk_max_steps = max_steps; c.tk_internal = ext_actions ? 0 : 1;
     }
     __syncwarp();
     unsigned long long st_hops = 0, st_local = 0;

@@ -89,7 +89,7 @@ nbiot_simtv_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *ac
         nb_fill_ctx(L.c, A, i);
         NB_NOUNROLL
         for (int w = 0; w < (int)(sizeof(NbHdr) / 16); ++w) hl[w] = hg[w];
-        L.c.tk_until = until_time; L.c.tk_max_steps = max_steps;
+        L.c.tk_until = until_time; L.c.tk_max_steps = max_steps; L.c.tk_internal = ext_actions ? 0 : 1;
         k = nbc_task_begin(L.c, ext_actions ? ext_actions + (size_t)i * L.c.ctrl->ext_k : nullptr);
     }
     int waited = 0;

@@ -191,6 +191,7 @@ typedef struct {
     uint8_t ext_a_mask[24];
     NbWrites ext_post, state_writes[4];
     uint8_t init_action[24];
+    NbWrites full_writes[4];              /* every agent of the state (advances without an external action) */
 } NbCtrlDev;
 
 /* configuration read on rare paths only (arrivals, departures): kept out of the per-warp context */
@@ -209,9 +210,9 @@ static inline NbCtrlDev nb_make_ctrl_dev(const nbiot_ctrl_t *c)
     NbCtrlDev d;
     d.ext_state_mask = c->ext_state_mask; d.ext_k = c->ext_k;
     for (int i = 0; i < 24; ++i) { d.ext_a_mask[i] = c->ext_a_mask[i]; d.init_action[i] = c->init_action[i]; }
-    for (int t = 0; t < 5; ++t) {
-        NbWrites *w = t < 4 ? &d.state_writes[t] : &d.ext_post;
-        const int8_t *src = t < 4 ? c->state_writes[t] : c->ext_post;
+    for (int t = 0; t < 9; ++t) {
+        NbWrites *w = t < 4 ? &d.state_writes[t] : t == 4 ? &d.ext_post : &d.full_writes[t - 5];
+        const int8_t *src = t < 4 ? c->state_writes[t] : t == 4 ? c->ext_post : c->full_writes[t - 5];
         w->mask = 0; w->pad = 0;
         for (int i = 0; i < 24; ++i) { w->val[i] = 0; if (i < 23 && src[i] >= 0) { w->mask |= 1u << i; w->val[i] = (uint8_t)src[i]; } }
     }

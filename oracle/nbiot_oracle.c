@@ -1350,16 +1350,20 @@ int orc_ctrl_advance(Oracle *o, const nbiot_ctrl_t *ctrl, int32_t *ctrl_action, 
 {
     int steps = 0;
     if (o->fault & NBIOT_FAULT_FATAL_MASK) return 0;
+    /* without an external action (run_until / single_step, controller.py:156-195) every agent of a state acts, the one
+     * registered as external included, and no state hands control back */
+    const int8_t (*sw)[24] = ext_action ? ctrl->state_writes : ctrl->full_writes;
+    const uint32_t ext_mask = ext_action ? ctrl->ext_state_mask : 0u;
     if (ext_action) {
         for (int i = 0; i < ctrl->ext_k; ++i) ctrl_action[ctrl->ext_a_mask[i]] = ext_action[i];
         ctrl_apply(ctrl_action, ctrl->ext_post);
-    } else ctrl_apply(ctrl_action, ctrl->state_writes[o->state]);
+    } else ctrl_apply(ctrl_action, sw[o->state]);
     while (steps < max_steps && !(until_time >= 0 && o->time >= until_time)) {
-        if (steps > 0) ctrl_apply(ctrl_action, ctrl->state_writes[o->state]);
+        if (steps > 0) ctrl_apply(ctrl_action, sw[o->state]);
         orc_step(o, ctrl_action, out);
         steps += 1;
         if (o->fault & NBIOT_FAULT_FATAL_MASK) break;
-        if ((ctrl->ext_state_mask >> o->state) & 1u) { ctrl_apply(ctrl_action, ctrl->state_writes[o->state]); break; }
+        if ((ext_mask >> o->state) & 1u) { ctrl_apply(ctrl_action, sw[o->state]); break; }
     }
     return steps;
 }

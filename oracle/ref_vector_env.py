@@ -48,21 +48,25 @@ def _worker(ref, conf, agents, ext_agent, seed, actions, warmup, barrier, out, i
         ctrl.set_ext_agent(ext_agent)
         env = gym.make('gym_system:System-v1', system=ctrl)
         env.reset()
+        trace = []                                   # (observation, reward) of every step: compared with the GPU's by the caller
         for a in actions[:warmup]:
-            env.step([int(x) for x in a])
+            o, r, _, _, _ = env.step([int(x) for x in a])
+            trace.append(([float(v) for v in o], float(r)))
         t_start = node.time
         barrier.wait(timeout=600)
         t0 = time.perf_counter()
         for a in actions[warmup:]:
-            env.step([int(x) for x in a])
+            o, r, _, _, _ = env.step([int(x) for x in a])
+            trace.append((o, r))
         dt = time.perf_counter() - t0
-        out.put((idx, dt, int(node.time - t_start), None))
+        trace = [([float(v) for v in o], float(r)) for o, r in trace]
+        out.put((idx, dt, int(node.time - t_start), None, trace))
     except Exception as e:          # a worker that dies must not leave the others at the barrier forever
         try:
             barrier.abort()
         except Exception:
             pass
-        out.put((idx, 0.0, 0, repr(e)))
+        out.put((idx, 0.0, 0, repr(e), None))
 
 
 def run(conf, agents, ext_agent, seeds, actions, warmup, processes=None):
@@ -97,5 +101,8 @@ def run(conf, agents, ext_agent, seeds, actions, warmup, processes=None):
         raise RuntimeError('reference worker failed: ' + errs[0])
     seconds = max(r[1] for r in res)
     subframes = sum(r[2] for r in res)
-    return {'value': subframes / max(seconds, 1e-9), 'seconds': seconds, 'subframes': subframes, 'cores': P,
+    traces = [None] * P
+    for r in res:
+        traces[r[0]] = r[4]
+    return {'traces': traces, 'value': subframes / max(seconds, 1e-9), 'seconds': seconds, 'subframes': subframes, 'cores': P,
             'per_core': sum(r[2] / max(r[1], 1e-9) for r in res) / P, 'reference_dir': 'oracle/_ref' if ref == REF_STAGED else ref}

@@ -109,10 +109,10 @@ void emu_advance(void *p, const uint8_t *ext_actions, int until_time, int max_st
     for (int i = 0; i < e->L.n_inst; ++i) {
         const uint8_t *a = ext_actions ? ext_actions + (size_t)i * e->cc.ctrl.ext_k : NULL;
         int k;
-        { Staged st(e, i, true); st.c->tk_until = until_time; st.c->tk_max_steps = max_steps; k = nbc_task_begin(*st.c, a); }
+        { Staged st(e, i, true); st.c->tk_until = until_time; st.c->tk_max_steps = max_steps; st.c->tk_internal = a ? 0 : 1; k = nbc_task_begin(*st.c, a); }
         while (k != NB_TK_DONE) {
             if (emu_tasklog && emu_tasklog_n < emu_tasklog_cap) { emu_tasklog[2 * emu_tasklog_n] = i; emu_tasklog[2 * emu_tasklog_n + 1] = k; emu_tasklog_n += 1; }
-            Staged st(e, i, true); st.c->tk_until = until_time; st.c->tk_max_steps = max_steps; k = nbc_task_run(*st.c, k);
+            Staged st(e, i, true); st.c->tk_until = until_time; st.c->tk_max_steps = max_steps; st.c->tk_internal = a ? 0 : 1; k = nbc_task_run(*st.c, k);
         }
         if (steps_out) steps_out[i] = ((NbHdr *)(e->state + e->L.off_hdr) + i)->tk_steps;
     }

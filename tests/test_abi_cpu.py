@@ -34,7 +34,7 @@ def test_struct_sizes_match(cuda_lib, oracle_lib):
     from nb_iot_environment_b200._cabi import ObsItem
     assert oracle_lib.orc_record_size() == RECORD_DTYPE.itemsize == 1632
     assert oracle_lib.orc_conf_size() == ctypes.sizeof(NbiotConf)
-    assert ctypes.sizeof(NbiotCtrl) == 8 + 24 + 24 + 96 + 24
+    assert ctypes.sizeof(NbiotCtrl) == 8 + 24 + 24 + 96 + 24 + 96
     assert ctypes.sizeof(ObsItem) == 24
     from nb_iot_environment_b200._cabi import MbTables, MB_STATE_BYTES
     assert ctypes.sizeof(MbTables) == 240 and MB_STATE_BYTES == 56          # nbiot_mb_tables_t / nbiot_mb_state_t (include/nbiot_agent.h)

@@ -350,6 +350,31 @@ def test_run_until_on_internal_agents(kernel):
     env.close()
 
 
+def test_run_until_with_an_external_agent_registered(kernel):
+    """Controller.run_until / single_step (controller.py:156-195) let EVERY agent of a state act -- the one registered as external
+    with its fixed action -- and run to the horizon; they do not stop at the external agent's first decision."""
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from oracle_controller import OracleController
+    for conf, agents, ext, T in ((dict(CFG1, ratio=0.5), NPRACH_AGENTS, 3, 9000), (CFG3, NPUSCH_AGENTS, 0, 4000)):
+        N = 6
+        seeds = list(range(40, 40 + N))
+        env = BatchedNBIoTEnv(conf, agents_conf=agents, ext_agent=ext, num_envs=N, seeds=seeds, ue_cap=conf['M'], grid_w=2048, hist_cap=1024)
+        env.reset()
+        env.run_until(T)
+        recs = env.records()
+        assert (recs['time'] >= T).all()
+        for i, s in enumerate(seeds):
+            c = OracleController(conf, s, agents_conf=agents, ext_agent=ext)
+            c.reset()
+            c.run_until(T)
+            assert not record_diff(c.rec, recs[i], rtol=0.0), i
+        # and the external agent takes over again afterwards
+        a = _random_ext_actions(np.random.default_rng(1), env.action_nvec, N)
+        env.step(a)
+        assert (env.records()['time'] > recs['time']).all()
+        env.close()
+
+
 def test_batch_independence_and_determinism_at_scale():
     """4096 cells (config 2 size): instance i of a large batch equals the same seed simulated alone,
     two runs are identical, and the reduced statistics equal the sum of the per-instance records."""

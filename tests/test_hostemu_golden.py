@@ -73,3 +73,24 @@ def test_event_selection_second_pass(case, oracle_lib):
     """The event selection looks at 32 keys per pass and takes a second pass only when pool entries above the first 22 are in use
     (more than 22 pending events). This build hands the pool out from its highest entry, so every trace goes through the second pass."""
     _replay(case, '32h', 300)
+
+
+@pytest.mark.parametrize('lanes', [1, '1tg'])
+def test_run_until_with_an_external_agent_registered(lanes, oracle_lib):
+    """Controller.run_until (controller.py:156-195) with an external agent registered: every agent of a state acts with its fixed
+    action and the cells run to the horizon (the core used to hand control back at the external agent's first decision)."""
+    from hostemu_py import EmuBatch
+    from nb_iot_environment_b200.controller import ControllerTables
+    from oracle_controller import OracleController
+    from test_gpu_parity import NPRACH_AGENTS
+    conf = {'ratio': 0.5, 'M': 1000, 'buffer_range': [100, 600], 'reward_criteria': 'throughput'}
+    seeds = [3, 4]
+    b = EmuBatch(conf, seeds, lanes=lanes, ctrl=ControllerTables(NPRACH_AGENTS, 3).build(), ue_cap=1000, grid_w=2048, hist_cap=1024)
+    b.reset()
+    recs, steps = b.advance(None, until_time=7000)
+    assert (recs['time'] >= 7000).all() and (steps > 100).all()
+    for i, s in enumerate(seeds):
+        c = OracleController(conf, s, agents_conf=NPRACH_AGENTS, ext_agent=3)
+        c.reset()
+        c.run_until(7000)
+        assert not record_diff(c.rec, recs[i], rtol=0.0)
