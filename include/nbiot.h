@@ -133,10 +133,6 @@ int nbiot_step_host(nbiot_handle_t *h, const uint8_t *actions_host, int until_ti
 int nbiot_set_event_log(nbiot_handle_t *h, int32_t *evlog_dev, int cap);
 /* kernel launches issued through this handle so far */
 long long nbiot_launch_count(nbiot_handle_t *h);
-/* measurement aid of the migrating-instance kernel (NBIOT_SCHED=queue): out[0..9] tasks run per class, out[10..19] cycles spent in them
- * (both only with NBIOT_Q_STATS=1), out[20] cells stored + queued, out[21] tasks continued on the same warp, out[22] class changes of an SM,
- * out[23] idle polls of the dispatchers, out[24] scheduler self-check (0 = fine); synchronises the device */
-int nbiot_queue_stats(nbiot_handle_t *h, unsigned long long out[32]);
 /* measurement aid (NBIOT_PROF_INST=1 at creation): { start ns, end ns, SM id, 0 } of every instance in the last simulation launch,
  * out_host = uint64[n_inst][4]; synchronises the device */
 int nbiot_instance_times(nbiot_handle_t *h, unsigned long long *out_host);

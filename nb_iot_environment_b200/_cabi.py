@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('NBIOT_LIB') or os.path.join(_HERE, 'libnbiot_b200.so'
 # every symbol include/nbiot.h declares
 SYMBOLS = ['nbiot_abi_version', 'nbiot_last_error', 'nbiot_state_bytes', 'nbiot_hdr_bytes', 'nbiot_hdr_task_bytes', 'nbiot_create', 'nbiot_destroy',
            'nbiot_set_controller', 'nbiot_reset', 'nbiot_advance', 'nbiot_advance_masked', 'nbiot_records_ptr', 'nbiot_hist_ptrs', 'nbiot_gather_obs',
-           'nbiot_reduce_stats', 'nbiot_step_host', 'nbiot_stat_ptrs', 'nbiot_stat_counts', 'nbiot_stat_histogram', 'nbiot_set_event_log', 'nbiot_launch_count', 'nbiot_launch_geometry', 'nbiot_kernel_name', 'nbiot_queue_stats', 'nbiot_instance_times',
+           'nbiot_reduce_stats', 'nbiot_step_host', 'nbiot_stat_ptrs', 'nbiot_stat_counts', 'nbiot_stat_histogram', 'nbiot_set_event_log', 'nbiot_launch_count', 'nbiot_launch_geometry', 'nbiot_kernel_name', 'nbiot_instance_times',
            'nbiot_rng_u01', 'nbiot_rng_pair', 'nbiot_rng_normal', 'nbiot_rng_bounded',
            # include/nbiot_agent.h
            'nbiot_mb_agent_create', 'nbiot_mb_agent_destroy', 'nbiot_mb_agent_act', 'nbiot_mb_agent_faults']
@@ -81,8 +81,6 @@ def load():
     L.nbiot_launch_count.restype = ctypes.c_longlong
     if hasattr(L, 'nbiot_instance_times'):
         L.nbiot_instance_times.argtypes = [vp, vp]
-    if hasattr(L, 'nbiot_queue_stats'):      # absent from older builds selected with NBIOT_LIB for A/B measurements
-        L.nbiot_queue_stats.argtypes = [vp, vp]
     L.nbiot_launch_count.argtypes = [vp]
     L.nbiot_launch_geometry.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
     if hasattr(L, 'nbiot_kernel_name'):

@@ -45,11 +45,10 @@ struct nbiot_handle {
     int blocks_short, smem_short, sim_hi_short, stage_policy;     /* geometry of launches that leave the grid in HBM */
     NbSimVariant k_gen, k_c1, k_gs, k_c1s;   /* builds of the warp-per-instance kernels (nbiot_simk.cuh): generic / single carrier, ring anywhere / staged */
     NbSimVariant k_tpc_gen, k_tpc_c1;        /* builds of the thread-per-cell kernel (nbiot_simt.cuh) */
-    int use_tpc;                 /* advances run on the thread-per-cell kernel (large batches; NBIOT_KERNEL=tpc|warp overrides) */
+    int use_tpc;                 /* long advances run on the thread-per-cell kernel: 1 plain, 2 voted dispatch (large batches) */
+    int tpc_forced;              /* NBIOT_KERNEL=tpc|tpcv: every advance, short launches included (tests, measurements) */
     int use_staged_builds;       /* measurement knob NBIOT_SIM_STAGED_BUILDS=0: staged launches on the ring-anywhere builds */
     int use_c1;                  /* single-carrier batch: the c1 build (the generic one while an event log is attached) */
-    int q_all;                   /* test knob: short launches too */
-    NbQueueRt *q;                /* migrating-instance kernel (nbiot_queue.cu) for long launches; NULL: warp-per-instance kernel */
     long long launches;
     int32_t *evlog; int evlog_cap;
     /* staging for nbiot_step_host */
@@ -174,12 +173,7 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
     int stage = h->stage_policy >= 0 ? h->stage_policy : !(mode == 2 && ext_actions && (h->ctrl.ext_state_mask & frequent));
     NbKernelArgs A = make_args(h, stage);
     int blocks = stage ? h->blocks : h->blocks_short, smem = stage ? h->smem_bytes : h->smem_short, hi = stage ? h->sim_hi : h->sim_hi_short;
-    if (mode == 2 && (stage || h->q_all) && h->q) {
-        int rc = nbq_launch(h->q, A, ext_actions, active, until_time, max_steps, st, g_err, sizeof g_err);
-        if (rc) return rc;
-        h->launches += 1;                              /* the queue-initialisation kernel */
-    }
-    else if (mode == 2 && h->use_tpc && !h->evlog) {
+    if (mode == 2 && h->use_tpc && !h->evlog && (stage || h->tpc_forced)) {
         /* one thread per cell: header in local memory, ring / lists / UE records in place in HBM */
         NbKernelArgs T = make_args(h, 0);
         const NbSimVariant *v = h->use_c1 ? &h->k_tpc_c1 : &h->k_tpc_gen;
@@ -233,6 +227,7 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     cudaStream_t st = (cudaStream_t)stream;
     nbiot_handle_t *h = new nbiot_handle_t();
     memset(h, 0, sizeof *h);
+    struct Guard { nbiot_handle_t *h; ~Guard() { if (h) nbiot_destroy(h); } } guard{ h };     /* every error return below frees what was allocated */
     h->conf = *conf; h->ctrl = *ctrl; h->L = L; h->device = device; h->n_inst = n_inst; h->state = (uint8_t *)state_dev;
     CK(cudaMalloc(&h->conf_dev, sizeof(nbiot_conf_t)));
     CK(cudaMalloc(&h->ctrl_dev, sizeof(NbCtaConst)));
@@ -261,14 +256,20 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     /* Which kernel advances the batch. One warp per cell keeps a cell's latency low but repeats the scalar control logic on 32
      * lanes; one thread per cell shares every common instruction between 32 cells but needs the cells to fill the machine
      * (148 SMs x 16 warps x 32 lanes = 75 776) -- DESIGN.md section 6c has the measured crossover. */
-    h->use_tpc = n_inst >= NB_TPC_MIN_CELLS;
-    if (const char *e = getenv("NBIOT_KERNEL")) { if (!strcmp(e, "tpc")) h->use_tpc = 1; else if (!strcmp(e, "tpcv")) h->use_tpc = 2; else if (!strcmp(e, "warp")) h->use_tpc = 0; }
+    h->use_tpc = n_inst >= NB_TPC_MIN_CELLS ? 2 : 0;
+    if (const char *e = getenv("NBIOT_KERNEL")) {
+        if (!strcmp(e, "tpc")) { h->use_tpc = 1; h->tpc_forced = 1; }
+        else if (!strcmp(e, "tpcv")) { h->use_tpc = 2; h->tpc_forced = 1; }
+        else if (!strcmp(e, "warp")) h->use_tpc = 0;
+    }
     h->use_staged_builds = getenv("NBIOT_SIM_STAGED_BUILDS") ? atoi(getenv("NBIOT_SIM_STAGED_BUILDS")) : 1;
     h->use_c1 = L.n_carriers == 1;
     if (const char *e = getenv("NBIOT_SIM_VARIANT")) h->use_c1 = h->use_c1 && strcmp(e, "generic") != 0;   /* measurement knob */
+    /* the attribute belongs to the function, not to the handle: always the device's maximum, so that a later, smaller batch cannot
+     * lower the limit under an earlier one */
     for (const NbSimVariant *v : { &h->k_gen, &h->k_c1, &h->k_gs, &h->k_c1s })
         for (const void *f : { v->sim_lo, v->sim_hi, v->reset })
-            CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+            CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     const NbSimVariant *kv = h->use_c1 ? &h->k_c1 : &h->k_gen;       /* both builds have the same launch bounds and register budgets */
     int per_sm = 0;
     int per_sm_hi = 0;
@@ -297,14 +298,9 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     int need = (n_inst + NB_WPB - 1) / NB_WPB;
     int cap = prop.multiProcessorCount * per_sm;
     h->blocks = need < cap ? need : cap;
-    h->q = nullptr;
-    {   /* NBIOT_SCHED = "queue": long launches run on the migrating-instance kernel; "warp" (default): one warp owns an instance for the launch */
-        const char *e = getenv("NBIOT_SCHED");
-        h->q_all = e && !strcmp(e, "queue_all");         /* test knob: every advance, short launches included */
-        if (e && (!strcmp(e, "queue") || h->q_all)) { int rq = nbq_create(&h->q, n_inst, device, 0, g_err, sizeof g_err); if (rq) return rq; }
-    }
     int rc = launch_sim(h, 0, nullptr, -1, 0, st);     /* construct + reset every instance */
     if (rc) return rc;
+    guard.h = nullptr;
     *out = h;
     return 0;
 }
@@ -316,7 +312,6 @@ int nbiot_destroy(nbiot_handle_t *h)
     cudaFree(h->conf_dev); cudaFree(h->ctrl_dev); cudaFree(h->lut2_dev); cudaFree(h->mcs_dev); cudaFree(h->seeds_dev); cudaFree(h->counter_dev); cudaFree(h->prof_dev);
     cudaFree(h->act_dev); cudaFree(h->obs_dev); cudaFree(h->rew_dev); cudaFree(h->items_dev);
     cudaFreeHost(h->act_pin); cudaFreeHost(h->obs_pin); cudaFreeHost(h->rew_pin);
-    nbq_destroy(h->q);
     delete h;
     return 0;
 }
@@ -495,13 +490,6 @@ int nbiot_set_event_log(nbiot_handle_t *h, int32_t *evlog_dev, int cap)
     return 0;
 }
 
-int nbiot_queue_stats(nbiot_handle_t *h, unsigned long long out[32])
-{
-    if (!h || !out) return set_err(NBIOT_E_INVALID, "nbiot_queue_stats: null argument");
-    if (!h->q) return set_err(NBIOT_E_INVALID, "nbiot_queue_stats: the batch does not use the migrating-instance kernel");
-    return nbq_stats(h->q, out);
-}
-
 int nbiot_instance_times(nbiot_handle_t *h, unsigned long long *out_host)
 {
     if (!h || !out_host) return set_err(NBIOT_E_INVALID, "nbiot_instance_times: null argument");
@@ -526,8 +514,7 @@ int nbiot_launch_geometry(nbiot_handle_t *h, int *blocks, int *warps_per_block, 
 const char *nbiot_kernel_name(nbiot_handle_t *h)
 {
     if (!h) return "";
-    if (h->q) return "migrating cells (task queues)";
-    return h->use_tpc == 2 ? "thread-per-cell, voted dispatch" : h->use_tpc ? "thread-per-cell" : "warp-per-cell";
+    return h->use_tpc == 2 ? "thread-per-cell, voted dispatch (long launches)" : h->use_tpc ? "thread-per-cell (long launches)" : "warp-per-cell";
 }
 
 double nbiot_rng_u01(uint64_t seed, uint64_t ctr, uint32_t stream) { return nb_rng_u01(seed, ctr, stream); }

@@ -1,7 +1,6 @@
 /*
  * nbiot_launch.h -- what the two translation units of libnbiot_b200.so share (internal, not part of the C ABI):
- * the kernel argument block, the staging helpers, and the entry points of the migrating-instance kernel
- * (nbiot_queue.cu) that nbiot_kernels.cu launches for long advances.
+ * the kernel argument block, the staging helpers, and the entry points of the builds of the simulation kernels.
  */
 #ifndef NBIOT_LAUNCH_H
 #define NBIOT_LAUNCH_H
@@ -76,16 +75,5 @@ void nb_sim_variant_tpc_c1(NbSimVariant *out);
 #ifndef NB_TPC_MIN_CELLS
 #define NB_TPC_MIN_CELLS 32768      /* batches from this size on advance on the thread-per-cell kernel */
 #endif
-
-/* ---- migrating-instance kernel (nbiot_queue.cu) ---- */
-struct NbQueueRt;                                   /* device-side queues of one handle */
-int nbq_create(NbQueueRt **out, int n_inst, int device, int smem_per_warp_nogrid, char *err, size_t err_len);
-void nbq_destroy(NbQueueRt *q);
-/* Controller.step / run_until for every (active) instance, as migrating tasks; same contract as nbiot_sim_kernel */
-int nbq_launch(NbQueueRt *q, const NbKernelArgs &A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps,
-               cudaStream_t st, char *err, size_t err_len);
-/* per-class task counts and cycles of the launches so far (measurement aid): out[0..9] tasks, out[10..19] cycles, out[20] hops, out[21] local continuations, ... */
-int nbq_stats(NbQueueRt *q, unsigned long long out[32]);
-void nbq_geometry(NbQueueRt *q, int *blocks, int *warps_per_block, int *smem_bytes);
 
 #endif /* NBIOT_LAUNCH_H */

@@ -65,15 +65,23 @@ class LazyInfos:
         self._env = env
         self._records = None
         self._hist = None
+        self._epoch = env._epoch          # the step this view belongs to: the records live in the state buffer and move on with it
+
+    def _check_fresh(self):
+        if self._epoch != self._env._epoch:
+            raise _cabi.NbiotError('this infos object belongs to an earlier step and was not read before the environment moved on: the reference '
+                                   'returns a snapshot dict, here the records are read on first use -- read infos (or infos.records) before the next step / reset')
 
     @property
     def records(self):
         if self._records is None:
+            self._check_fresh()
             self._records = self._env.records()
         return self._records
 
     def _hists(self):
         if self._hist is None:
+            self._check_fresh()
             self._hist = self._env.period_lists()
         return self._hist
 
@@ -127,6 +135,7 @@ class BatchedNBIoTEnv:
             _cabi.check(self.L.nbiot_create(ctypes.byref(self.cconf), self.num_envs, self.device.index, self.state.data_ptr(), nbytes,
                                             seeds.ctypes.data, lut.ctypes.data, mcs.ctypes.data, ctypes.byref(self.ctrl), st,
                                             ctypes.byref(self._h)))
+        self._epoch = 0                   # advances whenever the cells move (step / reset / run_until / load_state): stamps LazyInfos
         self._set_obs_items()
         self._obs = torch.zeros((self.num_envs, max(1, self.obs_dim)), dtype=torch.float64, device=self.device)
         self._reward = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
@@ -157,7 +166,11 @@ class BatchedNBIoTEnv:
     def action_nvec(self):
         """MultiDiscrete(a_max + 1) of the external agent (Discrete when it has a single item)."""
         if self.all_states_external:
-            return np.asarray([par.control_max_values[n][self.n_carriers - 1] for n in sorted(par.control_items, key=par.control_items.get)])
+            # one entry per INDEX of the shared vector (two pairs of items share an index, parameters.py:159-185): the largest maximum + 1
+            mx = [0] * par.N_actions
+            for name, idx in par.control_items.items():
+                mx[idx] = max(mx[idx], par.control_max_values[name][self.n_carriers - 1])
+            return np.asarray(mx, dtype=np.int64) + 1
         return self.tables.action_nvec()
 
     @property
@@ -190,27 +203,48 @@ class BatchedNBIoTEnv:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _gather(self):
+        """Controller.get_obs for the batch. The observation and reward tensors are the environment's own buffers, rewritten by
+        the next step (a learner that keeps them across steps clones them -- documented aliasing, as torch vector envs do);
+        pass fresh=True to step() for new tensors every call."""
         _cabi.check(self.L.nbiot_gather_obs(self._h, self._items, self._n_items, self._obs.data_ptr(), self._reward.data_ptr(), self._stream()))
         return self._obs[:, :self.obs_dim]
+
+    def _actions_u8(self, actions, k):
+        """int[N, k] -> uint8 on the device, refusing values a uint8 cast would wrap into another (possibly valid) action"""
+        if isinstance(actions, torch.Tensor):
+            a = actions.to(device=self.device).reshape(self.num_envs, k)
+            if a.dtype != torch.uint8:
+                if a.numel() and (int(a.min()) < 0 or int(a.max()) > 255):
+                    raise ValueError('action values must be in 0..255 (and below action_nvec)')
+                a = a.to(torch.uint8)
+            return a.contiguous()
+        a = np.asarray(actions).reshape(self.num_envs, k)
+        if a.dtype != np.uint8:
+            if a.size and (a.min() < 0 or a.max() > 255):
+                raise ValueError('action values must be in 0..255 (and below action_nvec)')
+            a = a.astype(np.uint8)
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
 
     def reset(self, seed=None, options=None):
         """(obs[N, D], infos). `seed` is ignored, as in the reference (environment.py:22-28)."""
         with torch.cuda.device(self.device):
             _cabi.check(self.L.nbiot_reset(self._h, self._stream()))
+            self._epoch += 1
             obs = self._gather()
         return obs, LazyInfos(self)
 
-    def step(self, actions, active=None):
+    def step(self, actions, active=None, fresh=False, validate=False):
         """actions: int[N, k] (k = number of action items of the external agent) as a CUDA tensor (stays on
         the device) or a host array (copied). Returns (obs, reward, terminated, truncated, infos).
         active: optional bool[N]; instances with False are not stepped at all (their observation, reward and
         record stay as they were) -- used by wrappers that answer without calling the environment."""
         k = self.ctrl.ext_k
         with torch.cuda.device(self.device):
-            if isinstance(actions, torch.Tensor):
-                a = actions.to(device=self.device, dtype=torch.uint8).reshape(self.num_envs, k).contiguous()
-            else:
-                a = torch.from_numpy(np.ascontiguousarray(np.asarray(actions).reshape(self.num_envs, k), dtype=np.uint8)).to(self.device)
+            a = self._actions_u8(actions, k)
+            if validate:                    # one compare + any() on the device, and a host sync: off by default, the kernel faults on what the reference raises on
+                nvec = torch.as_tensor(np.asarray(self.action_nvec), device=self.device)
+                if bool((a.to(torch.int64) >= nvec).any()):
+                    raise ValueError('action outside action_nvec')
             if active is None:
                 _cabi.check(self.L.nbiot_advance(self._h, a.data_ptr(), -1, 1 << 30, self._stream()))
             else:
@@ -218,14 +252,23 @@ class BatchedNBIoTEnv:
                 _cabi.check(self.L.nbiot_advance_masked(self._h, a.data_ptr(), m.data_ptr(), -1, 1 << 30, self._stream()))
                 self._last_mask = m
             self._last_actions = a          # keep alive until the kernel has consumed it
+            self._epoch += 1
             obs = self._gather()
-        return obs, self._reward, self._false, self._false, LazyInfos(self)
+            rew = self._reward
+            if fresh:
+                obs, rew = obs.clone(), rew.clone()
+        return obs, rew, self._false, self._false, LazyInfos(self)
 
     def step_host(self, actions_host, obs_out=None, reward_out=None):
         """The same step through host buffers in ONE C-ABI call (nbiot_step_host): actions are copied
         host->device, the observation and reward device->host, and the call returns synchronised."""
         k = self.ctrl.ext_k
-        a = np.ascontiguousarray(np.asarray(actions_host).reshape(self.num_envs, k), dtype=np.uint8)
+        a = np.asarray(actions_host).reshape(self.num_envs, k)
+        if a.dtype != np.uint8:
+            if a.size and (a.min() < 0 or a.max() > 255):
+                raise ValueError('action values must be in 0..255 (and below action_nvec)')
+            a = a.astype(np.uint8)
+        a = np.ascontiguousarray(a)
         if obs_out is None:
             obs_out = np.empty((self.num_envs, max(1, self.obs_dim)), dtype=np.float64)
         if reward_out is None:
@@ -233,6 +276,7 @@ class BatchedNBIoTEnv:
         with torch.cuda.device(self.device):
             _cabi.check(self.L.nbiot_step_host(self._h, a.ctypes.data, -1, 1 << 30, self._items, self._n_items,
                                                obs_out.ctypes.data, reward_out.ctypes.data, self._stream()))
+            self._epoch += 1
         return obs_out[:, :self.obs_dim], reward_out
 
     def run_until(self, time, max_steps=1 << 30):
@@ -240,17 +284,16 @@ class BatchedNBIoTEnv:
         clock reaches `time`."""
         with torch.cuda.device(self.device):
             _cabi.check(self.L.nbiot_advance(self._h, None, int(time), int(max_steps), self._stream()))
+            self._epoch += 1
 
     def node_step(self, actions23):
         """NodeB.step-level driving (all_states_external=True): one decision per call with the full 23-vector."""
         assert self.all_states_external
         with torch.cuda.device(self.device):
-            if isinstance(actions23, torch.Tensor):
-                a = actions23.to(device=self.device, dtype=torch.uint8).reshape(self.num_envs, par.N_actions).contiguous()
-            else:
-                a = torch.from_numpy(np.ascontiguousarray(np.asarray(actions23).reshape(self.num_envs, par.N_actions), dtype=np.uint8)).to(self.device)
+            a = self._actions_u8(actions23, par.N_actions)
             _cabi.check(self.L.nbiot_advance(self._h, a.data_ptr(), -1, 1, self._stream()))
             self._last_actions = a
+            self._epoch += 1
 
     # ------------------------------------------------------------------ results
     def record_field(self, name):
@@ -335,6 +378,9 @@ class BatchedNBIoTEnv:
         if snapshot.numel() != self.state.numel():
             raise ValueError('snapshot size does not match this environment (conf / capacities / num_envs differ)')
         self.state.copy_(snapshot.to(self.device))
+        self._epoch += 1
+        with torch.cuda.device(self.device):
+            self._gather()                  # the cached observation / reward follow the restored records
         torch.cuda.synchronize(self.device)
 
     def stats_tensor(self):

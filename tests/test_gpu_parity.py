@@ -150,42 +150,6 @@ def test_grid_in_place_equals_staged_grid(monkeypatch):
         assert np.array_equal(states[0], s)
 
 
-def test_migrating_instances_equal_warp_per_instance(monkeypatch):
-    """NBIOT_SCHED=queue_all: every advance runs on the migrating-instance kernel (csrc/nbiot_queue.cu: the control flow cut
-    into tasks, cells handed between SMs through per-class queues). Same states as the warp-per-instance kernel, bit for bit,
-    on short launches (external scheduling agent, 2 carriers) and on a long one; only the task-control words at the end of the
-    header, which the warp-per-instance kernel never writes, may differ."""
-    import torch
-    from nb_iot_environment_b200 import BatchedNBIoTEnv, _cabi
-    hdr, tk = _cabi.load().nbiot_hdr_bytes(), _cabi.load().nbiot_hdr_task_bytes()
-    states = []
-    for sched in (None, 'queue_all'):
-        if sched is None:
-            monkeypatch.delenv('NBIOT_SCHED', raising=False)
-        else:
-            monkeypatch.setenv('NBIOT_SCHED', sched)
-        N = 700                                                 # more cells than one wave of workers on a few SMs, ragged
-        env = BatchedNBIoTEnv(CFG3, agents_conf=NPUSCH_AGENTS, ext_agent=0, num_envs=N, seeds=list(range(N)), n_carriers=2, ue_cap=512, grid_w=2048, hist_cap=64)
-        env.reset()
-        r = np.random.default_rng(5)
-        for _ in range(60):
-            env.step(_random_ext_actions(r, env.action_nvec, N))
-        env.run_until(6000)
-        torch.cuda.synchronize()
-        st = env.state.cpu().numpy().copy()
-        h = st[:N * hdr].reshape(N, hdr)
-        h[:, hdr - tk:] = 0                                     # NbHdr.tk_*
-        states.append(st)
-        assert env.stats()['faulted'] == 0
-        if sched is not None:                                   # the scheduler's own counters: cells were handed on, nothing gave up
-            import ctypes
-            qs = (ctypes.c_ulonglong * 32)()
-            _cabi.check(env.L.nbiot_queue_stats(env._h, qs))
-            assert qs[20] > 0 and qs[24] == 0
-        env.close()
-    assert np.array_equal(states[0], states[1])
-
-
 def test_thread_per_cell_equals_warp_per_cell(monkeypatch):
     """NBIOT_KERNEL=tpc: every advance runs on the thread-per-cell kernel (csrc/nbiot_simt.cuh: the one-lane build of the core, header
     in local memory, 32 unrelated cells per warp). Same state buffer as the warp-per-cell kernel, byte for byte, on short launches
@@ -504,4 +468,129 @@ def test_reset_after_run_and_agent_reconfiguration():
             o = c.reset()
             assert np.array_equal(o, obs[i].cpu().numpy())
             assert not record_diff(c.rec, recs[i], rtol=0.0)
+    env.close()
+
+
+def test_api_guards():
+    """Round-1 review items: an infos object of an earlier step refuses to serve later data; load_state refreshes the cached
+    observation; action values that a uint8 cast would wrap are refused; the all-external action space has one entry per index of
+    the shared vector; a later, smaller batch does not lower the shared-memory limit of an earlier one."""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv, _cabi, parameters as par
+    N = 4
+    env = BatchedNBIoTEnv(dict(CFG1, ratio=0.5), agents_conf=NPRACH_AGENTS, ext_agent=3, num_envs=N, n_carriers=2, ue_cap=1000, grid_w=4096, hist_cap=512)
+    small = BatchedNBIoTEnv(CFG1, num_envs=2, ue_cap=64, grid_w=256)           # needs far less shared memory per CTA than `env`
+    small.reset(); small.run_until(500)
+    obs0, infos0 = env.reset()
+    assert infos0[0]['state'] == 'NPRACH_update'                               # read in time: fine, and cached
+    a = _random_ext_actions(np.random.default_rng(2), env.action_nvec, N)
+    obs1, rew1, _, _, infos1 = env.step(a, fresh=True)
+    keep1 = obs1.clone()
+    snap = env.save_state()
+    obs2, rew2, _, _, infos2 = env.step(a, validate=True)
+    assert infos0[0]['time'] == 0                                              # served from its own cache
+    with pytest.raises(_cabi.NbiotError):
+        infos1[0]                                                              # never read before the environment moved on
+    assert infos2[0]['time'] == 6000
+    assert torch.equal(obs1, keep1) and not torch.equal(obs2, keep1)           # fresh=True tensors are not overwritten by the next step
+    env.load_state(snap)
+    assert torch.equal(env._obs[:, :env.obs_dim], keep1)                       # the cached observation follows the restored records
+    with pytest.raises(ValueError):
+        env.step(a.astype(np.int64) + 256)
+    with pytest.raises(ValueError):
+        env.step(-a.astype(np.int64) - 1)
+    bad = a.copy(); bad[0, 2] = 200
+    with pytest.raises(ValueError):
+        env.step(bad, validate=True)
+    env.close(); small.close()
+    ext_all = BatchedNBIoTEnv(CFG1, num_envs=1, all_states_external=True, ue_cap=64, grid_w=256)
+    nvec = ext_all.action_nvec
+    assert len(nvec) == par.N_actions == 23 and nvec[par.control_items['Imcs']] == 7 and nvec[par.control_items['id']] == 4
+    ext_all.close()
+
+
+def _boundary_cells(N, per_cell_bytes):
+    """cells on both sides of every 4 GiB multiple inside an instance-major array of `per_cell_bytes` per cell"""
+    out = set()
+    k = 1
+    while k * (1 << 32) < N * per_cell_bytes:
+        i = (k * (1 << 32)) // per_cell_bytes
+        out.update(j for j in (i - 1, i, i + 1) if 0 <= j < N)
+        k += 1
+    return out
+
+
+def _sample_cells(N, arrays, n_random=160, seed=7):
+    idx = set(range(16)) | set(range(N - 16, N))
+    for b in arrays:
+        idx |= _boundary_cells(N, b)
+    rng = np.random.default_rng(seed)
+    idx |= set(int(i) for i in rng.integers(0, N, size=n_random))
+    return np.asarray(sorted(idx), dtype=np.int64)
+
+
+def test_parity_beyond_4gib_config3_setup():
+    """BASELINE configs[2] set-up (NPUSCH scenario, scheduling agent external, one launch per decision) with 131 072 cells: 21.7 GB
+    of state, every per-cell array several times past 4 GiB. 250+ sampled cells -- the first and last ones, both sides of every
+    4 GiB boundary of every array, random ones -- against the CPU oracle, bit for bit."""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from nb_iot_environment_b200.controller import ControllerTables
+    from nb_iot_environment_b200.record import make_conf, RECORD_DTYPE
+    from oracle import oracle_py
+    N, STEPS, caps = 131072, 40, dict(ue_cap=1024, grid_w=2048, hist_cap=64)
+    env = BatchedNBIoTEnv(CFG3, agents_conf=NPUSCH_AGENTS, ext_agent=0, num_envs=N, **caps)
+    assert env.state.numel() > 4 * (1 << 32)
+    ra_cap = caps['ue_cap'] + 64
+    arrays = [3504, 2 * caps['grid_w'], 3 * ra_cap * 16, caps['ue_cap'] * 16, caps['ue_cap'] * 64, caps['ue_cap'] * 2, RECORD_DTYPE.itemsize, ra_cap * 2]
+    idx = _sample_cells(N, arrays)
+    assert len(idx) >= 200
+    g = torch.Generator(device='cuda'); g.manual_seed(11)
+    nvec = torch.tensor(env.action_nvec, device='cuda')
+    env.reset()
+    acts = []
+    for s in range(STEPS):
+        a = (torch.rand((N, 3), device='cuda', generator=g) * nvec).to(torch.uint8)
+        env.step(a)
+        acts.append(a[torch.as_tensor(idx, device='cuda')].cpu().numpy())
+    recs = env.records()
+    assert env.stats()['faulted'] == 0
+    orecs = oracle_py.run_batch(make_conf(CFG3, **caps), ControllerTables(NPUSCH_AGENTS, 0).build(), idx.astype(np.uint64), actions=np.stack(acts), steps=STEPS)
+    bad = [int(i) for k, i in enumerate(idx) if record_diff(orecs[k], recs[i], rtol=0.0)]
+    assert not bad, f'{len(bad)} of {len(idx)} sampled cells differ from the oracle, first: {bad[:5]}'
+    env.close()
+
+
+def test_parity_beyond_4gib_two_carriers():
+    """BASELINE configs[3] set-up (two carriers, M=3000 bursty, every decision external) with 24 576 cells x 447 KB = 11 GB of state:
+    sampled cells on both sides of every 4 GiB boundary against the CPU oracle, bit for bit."""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from nb_iot_environment_b200.controller import ControllerTables
+    from nb_iot_environment_b200.record import make_conf, RECORD_DTYPE
+    from oracle import oracle_py
+    CFG4 = {'M': 3000, 'ratio': 0.5, 'buffer_range': [100, 600], 'reward_criteria': 'throughput', 'random': True}
+    N, STEPS, caps = 24576, 120, dict(ue_cap=3000, grid_w=2048, hist_cap=64)
+    env = BatchedNBIoTEnv(CFG4, num_envs=N, n_carriers=2, all_states_external=True, **caps)
+    assert env.state.numel() > 2 * (1 << 32)
+    ra_cap = caps['ue_cap'] + 64
+    idx = _sample_cells(N, [2 * 2 * caps['grid_w'], 3 * ra_cap * 16, caps['ue_cap'] * 16, caps['ue_cap'] * 64, caps['ue_cap'] * 2], n_random=200)
+    mx = torch.tensor([1, 3, 6, 7, 3, 3, 4, 11, 7, 7, 10, 15, 5, 7, 7, 5, 7, 7, 5, 7, 7, 14, 14], device='cuda') + 1
+    g = torch.Generator(device='cuda'); g.manual_seed(12)
+    env.reset()
+    acts = []
+    sel = torch.as_tensor(idx, device='cuda')
+    for s in range(STEPS):
+        a = (torch.rand((N, 23), device='cuda', generator=g) * mx).to(torch.uint8)
+        a[:, 5] = torch.where(a[:, 5] == 2, torch.full_like(a[:, 5], 3), a[:, 5])          # sc = 2 is invalid (SURVEY App. C #13)
+        rar = env.record_field('state') == 2                                              # RAR_window: ce_level / rar_Imcs share items 1 / 2
+        a[:, 1] = torch.where(rar, a[:, 1] % 3, a[:, 1]); a[:, 2] = torch.where(rar, a[:, 2] % 3, a[:, 2])
+        env.node_step(a)
+        acts.append(a[sel].cpu().numpy())
+    recs = env.records()
+    assert env.stats()['faulted'] == 0
+    orecs = oracle_py.run_batch(make_conf(CFG4, n_carriers=2, **caps), ControllerTables(n_carriers=2).build(all_states_external=True), idx.astype(np.uint64),
+                                actions=np.stack(acts), steps=STEPS)
+    bad = [int(i) for k, i in enumerate(idx) if record_diff(orecs[k], recs[i], rtol=0.0)]
+    assert not bad, f'{len(bad)} of {len(idx)} sampled cells differ from the oracle, first: {bad[:5]}'
     env.close()
