@@ -250,7 +250,7 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     h->smem_bytes = NB_WPB * A.smem_per_warp;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    if ((size_t)h->smem_bytes > prop.sharedMemPerBlockOptin) return set_err(NBIOT_E_INVALID, "grid_w too large for the shared memory of one CTA");
+    if ((size_t)h->smem_bytes + sizeof(NbCtaConst) + 64 > prop.sharedMemPerBlockOptin) return set_err(NBIOT_E_INVALID, "grid_w too large for the shared memory of one CTA");
     nb_sim_variant_generic(&h->k_gen); nb_sim_variant_c1(&h->k_c1); nb_sim_variant_gs(&h->k_gs); nb_sim_variant_c1s(&h->k_c1s);
     nb_sim_variant_tpc_gen(&h->k_tpc_gen); nb_sim_variant_tpc_c1(&h->k_tpc_c1);
     /* Which kernel advances the batch. One warp per cell keeps a cell's latency low but repeats the scalar control logic on 32
@@ -268,8 +268,11 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     /* the attribute belongs to the function, not to the handle: always the device's maximum, so that a later, smaller batch cannot
      * lower the limit under an earlier one */
     for (const NbSimVariant *v : { &h->k_gen, &h->k_c1, &h->k_gs, &h->k_c1s })
-        for (const void *f : { v->sim_lo, v->sim_hi, v->reset })
-            CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+        for (const void *f : { v->sim_lo, v->sim_hi, v->reset }) {
+            cudaFuncAttributes fa;
+            CK(cudaFuncGetAttributes(&fa, f));                 /* the opt-in maximum covers static + dynamic shared memory */
+            CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)));
+        }
     const NbSimVariant *kv = h->use_c1 ? &h->k_c1 : &h->k_gen;       /* both builds have the same launch bounds and register budgets */
     int per_sm = 0;
     int per_sm_hi = 0;
