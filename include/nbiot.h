@@ -105,6 +105,11 @@ int nbiot_advance_masked(nbiot_handle_t *h, const uint8_t *ext_actions_dev, cons
 int nbiot_records_ptr(nbiot_handle_t *h, void **records_dev);
 int nbiot_hist_ptrs(nbiot_handle_t *h, void **incoming_dev, void **delays_dev, void **service_dev, int *hist_cap);
 
+/* the per-cell sample ring of conf['traces'] / conf['statistics'] (PerfMonitor.nprach_sample, rar_sample, rar_window_sample,
+ * register_*_resources, npusch_delivered; perf_monitor.py:61-79, :111-140, :161-202): trace_dev = nbiot_trace_rec_t[n_inst][trace_cap]
+ * inside the state buffer (NULL when off), entry k of an instance at k % trace_cap; counts_dev = int32[n_inst] samples since reset */
+int nbiot_trace_ptrs(nbiot_handle_t *h, void **trace_dev, int *trace_cap);
+int nbiot_trace_counts(nbiot_handle_t *h, int32_t *counts_dev, void *stream);
 /* conf.stat_cap > 0 (conf['statistics']): the per-departure histories of PerfMonitor (perf_monitor.py:61-84, :161-171; the arrays
  * experiments_RL.py:139-140 / experiments_MAMBRL.py:121-122 save) as rings in HBM.
  * stat_dev = int32[n_inst][4][stat_cap]: 0 delay_history, 1 connection_history, 2 access_history, 3 acked bits (th_history = bits / delay);

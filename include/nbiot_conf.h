@@ -42,6 +42,22 @@ typedef struct nbiot_conf {
     int32_t cluster_hi;       /* conf['cluster_ues'][1]                                         */
     double cluster_prob;      /* conf['cluster_prob']                                           */
     double cluster_range;     /* conf['cluster_range'] in km (divided by the cell range when used) */
+    int32_t trace_cap;        /* entries of the per-cell sample ring (below) kept per instance; 0 = off                   */
+    int32_t trace_mask;       /* which samples are recorded: NBIOT_TR_* bits. conf['traces'] sets the NPRACH and msg3 samples
+                                 (PerfMonitor.nprach_sample / rar_sample, perf_monitor.py:61-69, :111-140), conf['statistics'] the
+                                 RAR-window samples, the three resource histories and the departures
+                                 (rar_window_sample, register_*_resources, npusch_delivered; :71-79, :125-129, :161-202)  */
 } nbiot_conf_t;
+
+/* one sample of the ring (16 bytes), in the order the reference appends to its lists */
+enum { NBIOT_TR_NPRACH = 1, NBIOT_TR_MSG3 = 2, NBIOT_TR_RARWIN = 4, NBIOT_TR_RES_MSG3 = 8, NBIOT_TR_RES_NPUSCH = 16, NBIOT_TR_RES_NPRACH = 32,
+       NBIOT_TR_DEPART = 64 };
+typedef struct nbiot_trace_rec {
+    int32_t t;                /* time of the sample                                                                         */
+    int32_t a, b;             /* NPRACH: n_ues, detections | MSG3: detection, error + 2 * collision | RARWIN: RAR_in + (RAR_attmp << 16),
+                                 RAR_sent + (RAR_ids << 16) | RES_*: subcarriers x subframes, 0 | DEPART: 0, 0               */
+    uint8_t type, ce;         /* NBIOT_TR_* bit, CE level                                                                   */
+    uint16_t pad;
+} nbiot_trace_rec_t;
 
 #endif /* NBIOT_CONF_H */

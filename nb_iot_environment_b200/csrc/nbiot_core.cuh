@@ -109,6 +109,19 @@ NB_DEV uint16_t *nbc_grid(NbCtx &c) { return c.grid; }
 #define NB_STATE(e) ((e).st_ce & 15u)
 #define NB_CE(e) (((e).st_ce >> 4) & 3u)
 
+/* PerfMonitor's sample lists (perf_monitor.py:61-79: nprach_sample, rar_sample, rar_window_sample, register_*_resources, npusch_delivered)
+ * as one ring of 16-byte samples per cell in HBM, in the order the reference appends; out of line and off unless conf['traces'] /
+ * conf['statistics'] (NbColdConf.trace_mask) */
+NB_FN void nbc_trace(NbCtx &c, int type, int ce, int t, int a, int b)
+{
+    const NbColdConf *cold = (const NbColdConf *)&((const NbCtaConst *)c.ctrl)->cold;
+    nbiot_trace_rec_t *tr = cold->trace_base + (size_t)(c.occ - cold->occ_base) * (size_t)cold->trace_cap;
+    nbiot_trace_rec_t r; r.t = t; r.a = a; r.b = b; r.type = (uint8_t)type; r.ce = (uint8_t)ce; r.pad = 0;
+    tr[c.occ->trace_n % cold->trace_cap] = r;
+    c.occ->trace_n += 1;
+}
+#define NB_TRACE(c, type, ce, t, a, b) do { if (((const NbCtaConst *)(c).ctrl)->cold.trace_mask & (type)) nbc_trace(c, type, ce, t, a, b); } while (0)
+
 /* ------------------------------------------------------------------ scalar draws */
 NB_DEV double nbc_u01(NbCtx &c) { return nb_rng_u01(nbc_hdr(c)->seed, nbc_hdr(c)->draws++, NBIOT_STREAM_ENV); }
 NB_DEV double nbc_normal(NbCtx &c, double mu, double sigma)
@@ -836,6 +849,7 @@ NB_FN1 void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
     int rep = 0; while (rep < 7 && nb_nprach_nsf_list[rep] != N_sf) ++rep;      /* N_sf_to_N_rep (carrier.py:25-26) */
     int counter = h->RAR_counter[ce];
     h->NPRACH_resources += (int64_t)N_sc * N_sf;
+    NB_TRACE(c, NBIOT_TR_RES_NPRACH, ce, t, N_sc * N_sf, 0);
     if (h->gen_t < t) { nbc_new_arrivals(c, t); if (NB_FATAL(c)) return; }
     NbRaEntry *L = c.ra[ce];
     int n = h->ra_n[ce];
@@ -881,6 +895,7 @@ NB_FN1 void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
         });
         ctr += (uint64_t)n_ues;
         h->NPRACH_resources += (int64_t)Na_sc * N_sf;
+        NB_TRACE(c, NBIOT_TR_RES_NPRACH, ce, t, Na_sc * N_sf, 0);
     }
     NB_NOUNROLL
     for (int w = 0; w < 8; ++w) { h->pre_once[w] = 0; h->pre_twice[w] = 0; }
@@ -949,6 +964,7 @@ NB_FN1S void nbc_NPRACH_end(NbCtx &c, int ce, int t)
     int counter = h->RAR_counter[ce];
     int n_ues = h->contenders[ce];
     int detections = h->detected_pre[ce];
+    NB_TRACE(c, NBIOT_TR_NPRACH, ce, t, n_ues, detections);          /* perf_monitor.nprach_sample (access_procedure.py:105) */
     if (n_ues > 0) {
         if (h->rar_n[ce] >= NB_RAR_WIN) { NB_FAULT(c, NBIOT_FAULT_EVENT_SLOTS); return; }
         h->RAR_UEs[ce][h->rar_n[ce]] = detections; h->rar_tot[ce] += detections;
@@ -958,6 +974,7 @@ NB_FN1S void nbc_NPRACH_end(NbCtx &c, int ce, int t)
         int RAR_in = h->RAR_in[ce], RAR_det = h->RAR_ids[ce];
         h->m3_cnt[ce] += 1; h->m3_sent_sum[ce] += h->RAR_sent[ce]; h->m3_recv_sum[ce] += RAR_det;
         h->m3_eff_sum[ce] = NB_ADD(h->m3_eff_sum[ce], NB_DIV((double)RAR_det, (double)(RAR_in > 1 ? RAR_in : 1)));
+        NB_TRACE(c, NBIOT_TR_RARWIN, ce, t, RAR_in | (h->RAR_attmp[ce] << 16), h->RAR_sent[ce] | (RAR_det << 16));   /* rar_window_sample (node_b.py:543) */
         h->RAR_in[ce] = detections; h->RAR_ids[ce] = 0; h->RAR_attmp[ce] = 0; h->RAR_sent[ce] = 0;
         nbc_pool_push(c, NB_KEY(t + h->RAR_window_size[ce], h->seq), NB_EV_RAR_END, ce, counter);
         h->seq += 1;
@@ -1256,6 +1273,7 @@ NB_FN1 void nbc_msg3_event(NbCtx &c, int slot, int t)
         u->state = NB_UE_RAR;
         h->RAR_UEs[uce][i_] += 1; h->rar_tot[uce] += 1;
     }
+    NB_TRACE(c, NBIOT_TR_MSG3, uce, t, connected, connected ? 0 : 1);   /* perf_monitor.rar_sample (rx_procedure.py:41-51): one contender */
     nbc_update_state(c);
 }
 
@@ -1300,6 +1318,7 @@ NB_FN1 void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
             int deps = h->ue_departures[0] + h->ue_departures[1] + h->ue_departures[2];
             h->av_delay = NB_ADD(h->av_delay, NB_DIV(NB_SUB((double)delay, h->av_delay), (double)deps));
             if (nbc_cold(c)->stat_cap > 0) nbc_stat_append(c, delay, service_time, u->t_connection - u->t_arrival, u->acked_data);
+            NB_TRACE(c, NBIOT_TR_DEPART, u->CE_level, t, 0, 0);        /* npusch_delivered (perf_monitor.py:164-168) */
             if (c.conf.random_traffic) { if (nbc_bernoulli(c, h->gen_p) > 0) h->M_beta += 1; else h->M_uniform += 1; }   /* ue_generator.departure */
             else if (u->beta && h->M_beta < h->M_beta_max) h->M_beta += 1;
             else h->M_uniform += 1;
@@ -1394,6 +1413,7 @@ NB_FN1 void nbc_step_RAR_window(NbCtx &c, const uint8_t *a)      /* node_b.py:45
         NB_NOUNROLL
         for (int i = 0; i < h->rar_n[CE_level]; ++i) if (h->RAR_UEs[CE_level][i] > 0) { h->RAR_UEs[CE_level][i] -= 1; h->rar_tot[CE_level] -= 1; break; }
         h->msg3_resources += (int64_t)N_sc * n_sf;
+        NB_TRACE(c, NBIOT_TR_RES_MSG3, CE_level, h->time, N_sc * n_sf, 0);
     } else h->valid_CE_control = 0;
     nbc_schedule_NPDCCH(c, NPDCCH_sf);
     nbc_update_state(c);
@@ -1483,6 +1503,7 @@ NB_FN1 void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:58
         nbc_pool_push(c, NB_KEY(t_ul_end, h->seq), NB_EV_NPUSCH_END, CE_level, slot);
         h->seq += 1;
         h->NPUSCH_resources += (int64_t)N_sc * n_sf;
+        NB_TRACE(c, NBIOT_TR_RES_NPUSCH, CE_level, h->time, N_sc * n_sf, 0);
     } else if (new_data) {
         if (h->n_unfit < NBIOT_STEP_LIST) h->unfit_id[h->n_unfit] = u->id;
         h->n_unfit += 1;
@@ -1783,6 +1804,7 @@ NB_FN void nbc_construct(NbCtx &c, uint64_t seed, const NbCtrlDev *ctrl)
     });
     h->seed = seed;
     c.occ->cluster_count = 0; c.occ->stat_n = 0; c.occ->cluster_cx = 0.0; c.occ->cluster_cy = 0.0;   /* Population.__init__ (:57-63): not reset() */
+    c.occ->trace_n = 0; c.occ->pad_t = 0;
     h->NPDCCH_sf_left = NB_NPDCCH_SF;
     NB_NOUNROLL
     for (int i = 0; i < 16; ++i) h->nprach_conf[i] = nb_nprach_default_conf[i];
@@ -1834,7 +1856,7 @@ NB_FN void nbc_reset(NbCtx &c)
     NB_NOUNROLL
     for (int i = 0; i < 3; ++i) { h->ue_arrivals[i] = 0; h->ue_departures[i] = 0; h->backoffs[i] = 0; }
     h->ue_connections = 0; h->av_delay = 0.0; h->msg3_resources = 0; h->NPUSCH_resources = 0; h->NPRACH_resources = 0;
-    c.occ->stat_n = 0;                                         /* the histories restart (perf_monitor.py:61-84) */
+    c.occ->stat_n = 0; c.occ->trace_n = 0;                     /* the histories restart (perf_monitor.py:61-84) */
     nbc_clear_info(c);
     /* ue_generator.reset (ue_generator.py:38-42) */
     double ratio = c.conf.ratio < 1.0 ? c.conf.ratio : 1.0;

@@ -126,6 +126,13 @@ __global__ void nbiot_stat_count_kernel(const NbOccHist *occ, int n_inst, int32_
     if (i < n_inst) out[i] = occ[i].stat_n;
 }
 
+/* sample ring (conf['traces'] / conf['statistics']): samples recorded per instance */
+__global__ void nbiot_trace_count_kernel(const NbOccHist *occ, int n_inst, int32_t *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_inst) out[i] = occ[i].trace_n;
+}
+
 /* histogram over the whole batch of one history (0 delay, 1 connection, 2 access, 3 acked bits): one warp per instance
  * streams its ring (coalesced int32 reads), bins of `bin_width` with the last bin open-ended; HBM-bound, one pass */
 __global__ void nbiot_stat_hist_kernel(const NbOccHist *occ, const int32_t *stat, int cap, int n_inst, int which, int bin_width, int n_bins,
@@ -239,7 +246,7 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     CK(cudaMemcpyAsync(h->conf_dev, conf, sizeof(nbiot_conf_t), cudaMemcpyHostToDevice, st));
     static_assert(sizeof(NbCtaConst) % 4 == 0, "NbCtaConst is staged word by word");
     NbCtaConst cd; memset(&cd, 0, sizeof cd);
-    cd.ctrl = nb_make_ctrl_dev(ctrl); cd.cold = nb_make_cold(conf, h->state, L.off_occ, L.off_stat);
+    cd.ctrl = nb_make_ctrl_dev(ctrl); cd.cold = nb_make_cold(conf, h->state, L.off_occ, L.off_stat, L.off_trace);
     CK(cudaMemcpyAsync(h->ctrl_dev, &cd, sizeof(NbCtaConst), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->lut2_dev, lut2, NB_LUT_CURVES * NB_LUT_SNR_PTS * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->mcs_dev, mcs, NB_MCS_LOSS_ROWS * NB_N_TBS * 3, cudaMemcpyHostToDevice, st));
@@ -458,6 +465,24 @@ int nbiot_stat_ptrs(nbiot_handle_t *h, void **stat_dev, int *stat_cap)
     if (!h) return set_err(NBIOT_E_INVALID, "nbiot_stat_ptrs: null handle");
     if (stat_dev) *stat_dev = h->L.stat_cap > 0 ? (void *)(h->state + h->L.off_stat) : nullptr;
     if (stat_cap) *stat_cap = h->L.stat_cap;
+    return 0;
+}
+
+int nbiot_trace_ptrs(nbiot_handle_t *h, void **trace_dev, int *trace_cap)
+{
+    if (!h) return set_err(NBIOT_E_INVALID, "nbiot_trace_ptrs: null handle");
+    if (trace_dev) *trace_dev = h->L.trace_cap > 0 ? (void *)(h->state + h->L.off_trace) : nullptr;
+    if (trace_cap) *trace_cap = h->L.trace_cap;
+    return 0;
+}
+
+int nbiot_trace_counts(nbiot_handle_t *h, int32_t *counts_dev, void *stream)
+{
+    if (!h || !counts_dev) return set_err(NBIOT_E_INVALID, "nbiot_trace_counts: null argument");
+    CK(cudaSetDevice(h->device));
+    nbiot_trace_count_kernel<<<(h->n_inst + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const NbOccHist *)(h->state + h->L.off_occ), h->n_inst, counts_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
     return 0;
 }
 

@@ -104,6 +104,8 @@ typedef struct {            /* cold per-instance block in HBM: per-occasion NPRA
     int32_t cluster_count;  /* UEs still to be placed around the current cluster centre */
     int32_t stat_n;         /* departures recorded in the statistics histories since reset */
     double cluster_cx, cluster_cy;
+    int32_t trace_n;        /* samples recorded in the sample ring since reset */
+    int32_t pad_t;
 } NbOccHist;
 
 typedef struct __attribute__((aligned(16))) NbHdr {
@@ -200,6 +202,8 @@ typedef struct {
     double cluster_prob, cluster_range;   /* cluster_range already divided by the cell range (population.py:62) */
     NbOccHist *occ_base;                  /* instance index = c.occ - occ_base */
     int32_t *stat_base;                   /* int32[n_inst][4][stat_cap]: delay, connection, access, acked bits */
+    nbiot_trace_rec_t *trace_base;        /* [n_inst][trace_cap] */
+    int32_t trace_cap, trace_mask;
 } NbColdConf;
 
 /* per-CTA constants in shared memory: NbCtx.ctrl points at the first member */
@@ -221,20 +225,22 @@ static inline NbCtrlDev nb_make_ctrl_dev(const nbiot_ctrl_t *c)
 
 /* byte offsets of the per-instance arrays inside the caller-owned state buffer */
 typedef struct {
-    int32_t n_inst, ue_cap, grid_w, hist_cap, n_carriers, ra_cap, stat_cap, pad1;
+    int32_t n_inst, ue_cap, grid_w, hist_cap, n_carriers, ra_cap, stat_cap, trace_cap;
     uint64_t off_hdr, off_grid, off_ra, off_conn, off_cont, off_ue, off_free, off_occ;
-    uint64_t off_incoming, off_delays, off_service, off_rec, off_scratch, off_stat, total;
+    uint64_t off_incoming, off_delays, off_service, off_rec, off_scratch, off_stat, off_trace, total;
 } NbLayout;
 
 static inline uint64_t nb_align256(uint64_t x) { return (x + 255u) & ~(uint64_t)255u; }
 
-static inline NbColdConf nb_make_cold(const nbiot_conf_t *c, uint8_t *state, uint64_t off_occ, uint64_t off_stat)
+static inline NbColdConf nb_make_cold(const nbiot_conf_t *c, uint8_t *state, uint64_t off_occ, uint64_t off_stat, uint64_t off_trace)
 {
     NbColdConf k;
     double range = c->max_d > 0 ? c->max_d : NB_MAX_RANGE;      /* channel.py:128-131 */
     k.stat_cap = c->stat_cap > 0 ? c->stat_cap : 0; k.clustered = c->clustered; k.cluster_lo = c->cluster_lo; k.cluster_hi = c->cluster_hi;
     k.cluster_prob = c->cluster_prob; k.cluster_range = c->cluster_range / range;
     k.occ_base = (NbOccHist *)(state + off_occ); k.stat_base = (int32_t *)(state + off_stat);
+    k.trace_base = (nbiot_trace_rec_t *)(state + off_trace);
+    k.trace_cap = c->trace_cap > 0 ? c->trace_cap : 0; k.trace_mask = k.trace_cap ? c->trace_mask : 0;
     return k;
 }
 
@@ -242,7 +248,7 @@ static inline NbLayout nb_make_layout(const nbiot_conf_t *c, int n)
 {
     NbLayout L;
     L.n_inst = n; L.ue_cap = c->ue_cap; L.grid_w = c->grid_w; L.hist_cap = c->hist_cap;
-    L.n_carriers = c->n_carriers >= 2 ? 2 : 1; L.ra_cap = c->ue_cap + NB_RA_SLACK; L.stat_cap = c->stat_cap > 0 ? c->stat_cap : 0; L.pad1 = 0;
+    L.n_carriers = c->n_carriers >= 2 ? 2 : 1; L.ra_cap = c->ue_cap + NB_RA_SLACK; L.stat_cap = c->stat_cap > 0 ? c->stat_cap : 0; L.trace_cap = c->trace_cap > 0 ? c->trace_cap : 0;
     uint64_t o = 0, N = (uint64_t)n;
     L.off_hdr = o;      o = nb_align256(o + N * sizeof(NbHdr));
     L.off_grid = o;     o = nb_align256(o + N * (uint64_t)L.n_carriers * (uint64_t)L.grid_w * 2u);
@@ -258,6 +264,7 @@ static inline NbLayout nb_make_layout(const nbiot_conf_t *c, int n)
     L.off_rec = o;      o = nb_align256(o + N * sizeof(nbiot_record_t));
     L.off_scratch = o;  o = nb_align256(o + N * (uint64_t)L.ra_cap * 2u);
     L.off_stat = o;     o = nb_align256(o + N * 4u * (uint64_t)L.stat_cap * 4u);
+    L.off_trace = o;    o = nb_align256(o + N * (uint64_t)L.trace_cap * sizeof(nbiot_trace_rec_t));
     L.total = o;
     return L;
 }

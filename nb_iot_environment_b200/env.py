@@ -18,7 +18,7 @@ import torch
 from . import _cabi
 from . import parameters as par
 from .controller import ControllerTables
-from .record import RECORD_DTYPE, STATE_IDS, FAULT_FATAL_MASK, make_conf, record_to_info
+from .record import RECORD_DTYPE, TRACE_DTYPE, STATE_IDS, FAULT_FATAL_MASK, make_conf, record_to_info, samples_to_lists
 
 _ALL = 0xF
 _SCHED = (1 << STATE_IDS['Scheduling']) | (1 << STATE_IDS['RAR_window_end'])
@@ -108,7 +108,7 @@ class BatchedNBIoTEnv:
     that is driven from outside (-1: none, the cells run on their internal agents)."""
 
     def __init__(self, conf, agents_conf=None, ext_agent=-1, num_envs=1, seeds=None, n_carriers=1, device=0,
-                 ue_cap=None, grid_w=1024, hist_cap=256, all_states_external=False, stat_cap=None):
+                 ue_cap=None, grid_w=1024, hist_cap=256, all_states_external=False, stat_cap=None, trace_cap=None):
         if not torch.cuda.is_available():
             raise _cabi.NbiotError('BatchedNBIoTEnv needs a CUDA device: there is no CPU fallback')
         self.L = _cabi.load()
@@ -116,7 +116,7 @@ class BatchedNBIoTEnv:
         self.device = torch.device('cuda', device)
         self.conf = dict(conf)
         self.n_carriers = n_carriers
-        self.cconf = make_conf(conf, n_carriers=n_carriers, ue_cap=ue_cap, grid_w=grid_w, hist_cap=hist_cap, stat_cap=stat_cap)
+        self.cconf = make_conf(conf, n_carriers=n_carriers, ue_cap=ue_cap, grid_w=grid_w, hist_cap=hist_cap, stat_cap=stat_cap, trace_cap=trace_cap)
         self.tables = ControllerTables(agents_conf, ext_agent, n_carriers)
         self.all_states_external = bool(all_states_external)
         self.ctrl = self.tables.build(all_states_external=self.all_states_external)
@@ -152,6 +152,10 @@ class BatchedNBIoTEnv:
         _cabi.check(self.L.nbiot_stat_ptrs(self._h, ctypes.byref(stp), ctypes.byref(scap)))
         self.stat_cap = scap.value
         self._stat_off = (stp.value - base) if stp.value else None
+        trp, tcap = ctypes.c_void_p(), ctypes.c_int()
+        _cabi.check(self.L.nbiot_trace_ptrs(self._h, ctypes.byref(trp), ctypes.byref(tcap)))
+        self.trace_cap = tcap.value
+        self._trace_off = (trp.value - base) if trp.value else None
 
     # ------------------------------------------------------------------ spaces (controller.py:77-103)
     def _set_obs_items(self):
@@ -323,9 +327,39 @@ class BatchedNBIoTEnv:
             _cabi.check(self.L.nbiot_stat_counts(self._h, out.data_ptr(), self._stream()))
         return out
 
+    def samples(self):
+        """the sample ring of every cell in order of occurrence: a list of (TRACE_DTYPE array, samples since reset); a cell with more
+        samples than trace_cap keeps the last trace_cap of them"""
+        if not self.trace_cap:
+            raise _cabi.NbiotError("the batch was created without sample lists: pass conf['traces']=True and / or conf['statistics']=True")
+        N, cap = self.num_envs, self.trace_cap
+        cnt = torch.zeros(N, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.L.nbiot_trace_counts(self._h, cnt.data_ptr(), self._stream()))
+        cnt = cnt.cpu().numpy()
+        raw = self.state[self._trace_off:self._trace_off + N * cap * TRACE_DTYPE.itemsize].cpu().numpy().view(TRACE_DTYPE).reshape(N, cap)
+        return [(raw[i, :n].copy() if n <= cap else np.roll(raw[i], -(n % cap)).copy(), int(n)) for i, n in enumerate(cnt)]
+
+    def traces(self):
+        """PerfMonitor's `traces` lists (perf_monitor.py:61-69, :111-140) of every cell under the reference's attribute names:
+        rar_detections / rar_errors / rar_collisions / nprach_arrivals / nprach_detections per CE level and the t_* lists over all levels,
+        each a list of (value, t). Needs conf['traces']."""
+        if not self.cconf.trace_mask & 3:
+            raise _cabi.NbiotError("the batch was created without traces: pass conf['traces']=True")
+        out = []
+        for rec, n in self.samples():
+            d = samples_to_lists(rec)
+            d = {k: d[k] for k in ('rar_detections', 'rar_errors', 'rar_collisions', 't_rar_detections', 'nprach_arrivals', 'nprach_detections',
+                                   't_nprach_arrivals', 't_nprach_detections')}
+            d['truncated'] = n > self.trace_cap
+            out.append(d)
+        return out
+
     def histories(self):
         """PerfMonitor.delay_history / connection_history / access_history / th_history (perf_monitor.py:61-84, :161-171) of every cell:
-        a list of dicts of numpy arrays, in departure order (what experiments_RL.py:139-140 saves as `delay` and `connection`).
+        a list of dicts of numpy arrays, in departure order (what experiments_RL.py:139-140 saves as `delay` and `connection`), plus the
+        other `statistics` lists: RAR_in / RAR_attmp / RAR_sent / RAR_detected and npusch_delivered per CE level, msg3 / NPUSCH /
+        NPRACH_resources_history (:71-79, :125-129, :164-168, :185-202).
         A cell with more departures than stat_cap keeps the last stat_cap of them ('truncated': True)."""
         if not self.stat_cap:
             raise _cabi.NbiotError("the batch was created without statistics: pass conf['statistics']=True or stat_cap")
@@ -341,6 +375,12 @@ class BatchedNBIoTEnv:
                 v = np.roll(raw[i], -(n % cap), axis=1)
             out.append({'delay': v[0].copy(), 'connection': v[1].copy(), 'access': v[2].copy(),
                         'th': v[3].astype(np.float64) / v[0].astype(np.float64), 'served_users': n, 'truncated': n > cap})
+        if self.trace_cap and self.cconf.trace_mask & 0x7C:
+            for h, (rec, n) in zip(out, self.samples()):
+                d = samples_to_lists(rec)
+                h.update({k: d[k] for k in ('RAR_in', 'RAR_attmp', 'RAR_sent', 'RAR_detected', 'npusch_delivered', 'msg3_resources_history',
+                                            'NPUSCH_resources_history', 'NPRACH_resources_history')})
+                h['samples_truncated'] = n > self.trace_cap
         return out
 
     def save_results(self, path, i=0):

@@ -63,10 +63,54 @@ class NbiotConf(ctypes.Structure):
                 ('random_traffic', ctypes.c_int32), ('n_carriers', ctypes.c_int32),
                 ('ue_cap', ctypes.c_int32), ('grid_w', ctypes.c_int32), ('hist_cap', ctypes.c_int32),
                 ('stat_cap', ctypes.c_int32), ('clustered', ctypes.c_int32), ('cluster_lo', ctypes.c_int32), ('cluster_hi', ctypes.c_int32),
-                ('cluster_prob', ctypes.c_double), ('cluster_range', ctypes.c_double)]
+                ('cluster_prob', ctypes.c_double), ('cluster_range', ctypes.c_double),
+                ('trace_cap', ctypes.c_int32), ('trace_mask', ctypes.c_int32)]
 
 
-_UNSUPPORTED_TRUE = ('animate_carrier', 'animate_stats', 'traces', 'resource_monitor')
+# nbiot_trace_rec_t (include/nbiot_conf.h): one sample of PerfMonitor's lists
+TRACE_DTYPE = np.dtype([('t', '<i4'), ('a', '<i4'), ('b', '<i4'), ('type', 'u1'), ('ce', 'u1'), ('pad', '<u2')])
+assert TRACE_DTYPE.itemsize == 16
+TR_NPRACH, TR_MSG3, TR_RARWIN, TR_RES_MSG3, TR_RES_NPUSCH, TR_RES_NPRACH, TR_DEPART = 1, 2, 4, 8, 16, 32, 64
+TRACE_MASK_TRACES = TR_NPRACH | TR_MSG3                                            # conf['traces'] (perf_monitor.py:61-69)
+TRACE_MASK_STATISTICS = TR_RARWIN | TR_RES_MSG3 | TR_RES_NPUSCH | TR_RES_NPRACH | TR_DEPART   # conf['statistics'] (:71-79)
+DEFAULT_TRACE_CAP = 8192
+
+
+def samples_to_lists(samples):
+    """samples of one cell in order of occurrence (TRACE_DTYPE) -> PerfMonitor's lists under the reference's attribute names
+    (perf_monitor.py:61-79): `traces` lists hold (value, t) tuples, the RAR / resource histories plain values, npusch_delivered
+    (count, t) with the departures of one subframe and CE level merged (:164-168)."""
+    out = {k: [[], [], []] for k in ('rar_detections', 'rar_errors', 'rar_collisions', 'nprach_arrivals', 'nprach_detections',
+                                     'RAR_in', 'RAR_attmp', 'RAR_sent', 'RAR_detected', 'npusch_delivered')}
+    out.update({k: [] for k in ('t_rar_detections', 't_nprach_arrivals', 't_nprach_detections',
+                                'msg3_resources_history', 'NPUSCH_resources_history', 'NPRACH_resources_history')})
+    for r in samples:
+        ty, ce, t, a, b = int(r['type']), int(r['ce']), int(r['t']), int(r['a']), int(r['b'])
+        if ty == TR_NPRACH:
+            out['nprach_arrivals'][ce].append((a, t)); out['nprach_detections'][ce].append((b, t))
+            out['t_nprach_arrivals'].append((a, t)); out['t_nprach_detections'].append((b, t))
+        elif ty == TR_MSG3:
+            out['rar_detections'][ce].append((a, t)); out['rar_errors'][ce].append((b & 1, t)); out['rar_collisions'][ce].append((b >> 1, t))
+            out['t_rar_detections'].append((a, t))
+        elif ty == TR_RARWIN:
+            out['RAR_in'][ce].append(a & 0xFFFF); out['RAR_attmp'][ce].append(a >> 16)
+            out['RAR_sent'][ce].append(b & 0xFFFF); out['RAR_detected'][ce].append(b >> 16)
+        elif ty == TR_RES_MSG3:
+            out['msg3_resources_history'].append(a)
+        elif ty == TR_RES_NPUSCH:
+            out['NPUSCH_resources_history'].append(a)
+        elif ty == TR_RES_NPRACH:
+            out['NPRACH_resources_history'].append(a)
+        elif ty == TR_DEPART:
+            lst = out['npusch_delivered'][ce]
+            if lst and lst[-1][1] == t:
+                lst[-1] = (lst[-1][0] + 1, t)
+            else:
+                lst.append((1, t))
+    return out
+
+
+_UNSUPPORTED_TRUE = ('animate_carrier', 'animate_stats', 'resource_monitor')
 _KNOWN = {'ratio', 'M', 'buffer_range', 'reward_criteria', 'sort_criterium', 'levels', 'max_d', 'sc_adjustment',
           'mcs_automatic', 'ce_mcs_automatic', 'tx_all_buffer', 'animate_carrier', 'statistics', 'animate_stats',
           'traces', 'resource_monitor', 'random', 'clustered', 'cluster_ues', 'cluster_prob', 'cluster_range'}
@@ -75,7 +119,7 @@ _KNOWN = {'ratio', 'M', 'buffer_range', 'reward_criteria', 'sort_criterium', 'le
 DEFAULT_STAT_CAP = 2048
 
 
-def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_cap=None):
+def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_cap=None, trace_cap=None):
     """conf dict with the reference's keys and defaults (system_creator.py:24-44) -> NbiotConf."""
     unknown = set(conf) - _KNOWN
     if unknown:
@@ -114,6 +158,13 @@ def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_c
     c.stat_cap = int(stat_cap) if stat_cap is not None else (DEFAULT_STAT_CAP if conf.get('statistics', False) else 0)
     if c.stat_cap < 0:
         raise ValueError('stat_cap must be >= 0')
+    # conf['traces'] / conf['statistics']: PerfMonitor's sample lists (perf_monitor.py:61-79) as a ring of trace_cap samples per cell
+    c.trace_mask = (TRACE_MASK_TRACES if conf.get('traces', False) else 0) | (TRACE_MASK_STATISTICS if conf.get('statistics', False) else 0)
+    c.trace_cap = (int(trace_cap) if trace_cap is not None else DEFAULT_TRACE_CAP) if c.trace_mask else 0
+    if c.trace_cap < 0:
+        raise ValueError('trace_cap must be >= 0')
+    if not c.trace_cap:
+        c.trace_mask = 0
     # clustered placement (system_creator.py:41-44, population.py:57-63)
     c.clustered = int(bool(conf.get('clustered', False)))
     lo, hi = conf.get('cluster_ues', [10, 30])

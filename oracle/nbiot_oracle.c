@@ -142,6 +142,7 @@ typedef struct Oracle {
     long long msg3_resources, NPUSCH_resources, NPRACH_resources;
     ivec rx_id, rx_delay, err_id, unfit_id, acc_id, acc_delay;
     ivec access_history, connection_history, delay_history, bits_history;   /* statistics (perf_monitor.py:61-84); th = bits / delay */
+    VEC(nbiot_trace_rec_t) samples;   /* nprach_sample / rar_sample / rar_window_sample / register_*_resources / npusch_delivered (perf_monitor.py:61-79) */
 
     int fault;
     /* last NPRACH_update info lists (copied out on request) */
@@ -201,6 +202,7 @@ static void perf_reset(Oracle *o)
     for (int i = 0; i < 3; ++i) o->ue_arrivals[i] = o->ue_departures[i] = o->backoffs[i] = 0;
     o->ue_connections = 0; o->av_delay = 0; o->msg3_resources = o->NPUSCH_resources = o->NPRACH_resources = 0;
     VCLEAR(o->access_history); VCLEAR(o->connection_history); VCLEAR(o->delay_history); VCLEAR(o->bits_history);
+    VCLEAR(o->samples);
 }
 static void perf_clear_info(Oracle *o)
 { VCLEAR(o->rx_id); VCLEAR(o->rx_delay); VCLEAR(o->err_id); VCLEAR(o->unfit_id); VCLEAR(o->acc_id); VCLEAR(o->acc_delay); }
@@ -729,6 +731,14 @@ static void population_MAC_timeout(Oracle *o, Event *ev)              /* populat
     }
 }
 
+/* PerfMonitor's sample lists, in append order (perf_monitor.py:61-79, :111-140, :185-202); which lists are kept: conf.trace_mask */
+static void perf_sample(Oracle *o, int type, int ce, int t, int a, int b)
+{
+    if (!(o->conf.trace_cap > 0 && (o->conf.trace_mask & type))) return;
+    nbiot_trace_rec_t r; r.t = t; r.a = a; r.b = b; r.type = (uint8_t)type; r.ce = (uint8_t)ce; r.pad = 0;
+    VPUSH(o->samples, r);
+}
+
 /* ------------------------------------------------------------------ access procedure */
 static void access_NPRACH_start(Oracle *o, Event *ev)                 /* access_procedure.py:37-91 */
 {
@@ -736,6 +746,7 @@ static void access_NPRACH_start(Oracle *o, Event *ev)                 /* access_
     int counter = o->RAR_counter[CE_level];
     double p = o->probability_anchor;
     o->NPRACH_resources += (long long)N_sc * N_sf;
+    perf_sample(o, NBIOT_TR_RES_NPRACH, CE_level, t, N_sc * N_sf, 0);
     /* population.NPRACH_start :168-188 */
     if (o->gen_t < t) get_new_arrivals(o, t);
     uvec *l = &o->ra_lists[CE_level];
@@ -754,6 +765,7 @@ static void access_NPRACH_start(Oracle *o, Event *ev)                 /* access_
             na_ues = rng_binomial(o, n_ues, p);
             for (int i = 0; i < na_ues; ++i) ra.d[k++]->preamble = rng_integers(o, N_pream, N_pream + 4 * Na_sc);
             o->NPRACH_resources += (long long)Na_sc * N_sf;
+            perf_sample(o, NBIOT_TR_RES_NPRACH, CE_level, t, Na_sc * N_sf, 0);
         }
         int a_ues = n_ues - na_ues;
         for (int i = 0; i < a_ues; ++i) ra.d[k++]->preamble = rng_integers(o, 0, N_pream);
@@ -785,6 +797,7 @@ static void node_start_RAR_window(Oracle *o, int detections, int CE_level, int t
     VPUSH(o->msg3_sent[CE_level], RAR_sent);
     VPUSH(o->msg3_received[CE_level], RAR_detections);
     VPUSH(o->msg3_efficiency[CE_level], (double)RAR_detections / (double)(RAR_in > 1 ? RAR_in : 1));
+    perf_sample(o, NBIOT_TR_RARWIN, CE_level, time, RAR_in | (o->RAR_attmp[CE_level] << 16), RAR_sent | (RAR_detections << 16));   /* rar_window_sample :543 */
     o->RAR_in[CE_level] = detections; o->RAR_ids[CE_level] = 0; o->RAR_attmp[CE_level] = 0; o->RAR_sent[CE_level] = 0;
     int e_time = time + o->RAR_window_size[CE_level];
     Event e = make_event(EV_RAR_WINDOW_END); e.CE_level = CE_level; e.rar_w_id = rar_w_id;
@@ -796,6 +809,7 @@ static void access_NPRACH_end(Oracle *o, Event *ev)                   /* access_
     int CE_level = ev->CE_level, t = ev->t, counter = o->RAR_counter[CE_level];
     int n_ues = o->contenders_per_CE[CE_level];
     int detected = o->detected_preambles_per_CE[CE_level];
+    perf_sample(o, NBIOT_TR_NPRACH, CE_level, t, n_ues, detected);       /* perf_monitor.nprach_sample :105 */
     if (n_ues > 0) {
         node_start_RAR_window(o, detected, CE_level, t, counter);
         o->detected_preambles_per_CE[CE_level] = 0; o->collided_preambles_per_CE[CE_level] = 0; o->contenders_per_CE[CE_level] = 0;
@@ -849,8 +863,10 @@ static void rx_msg3_event(Oracle *o, Event *ev)                       /* rx_proc
     double bler_256 = get_bler(o, SINR, ue->I_tbs, ue->N_rep);
     double p = nb_pow01(1.0 - bler_256, (double)NB_MSG3_TBS / 256);
     int connected = rng_bernoulli(o, p);
+    int ce = ue->CE_level;
     node_msg3_outcome(o, ue, ev->t, connected);
     if (connected) o->ue_connections += 1;                    /* perf.rar_sample(1,0,0,...) */
+    perf_sample(o, NBIOT_TR_MSG3, ce, ev->t, connected, connected ? 0 : 1);   /* one contender: a failure is an error, not a collision (:49-51) */
 }
 
 static void rx_NPUSCH_end(Oracle *o, Event *ev)                       /* rx_procedure.py:54-61, channel.py:236-256, node_b.py:801-830 */
@@ -881,6 +897,7 @@ static void rx_NPUSCH_end(Oracle *o, Event *ev)                       /* rx_proc
                 VPUSH(o->access_history, ue->t_connection - ue->t_arrival); VPUSH(o->connection_history, service_time);
                 VPUSH(o->delay_history, delay); VPUSH(o->bits_history, ue->acked_data);
             }
+            perf_sample(o, NBIOT_TR_DEPART, ue->CE_level, t, 0, 0);            /* npusch_delivered (perf_monitor.py:164-168) */
             gen_departure(o, ue);
             VPUSH(o->departures, delay);
             o->total_departures += 1;
@@ -962,6 +979,7 @@ static void step_RAR_window(Oracle *o, const int32_t *a)              /* node_b.
         ivec *r = &o->RAR_UEs[CE_level];                      /* subtract_one :59-68 */
         for (int i = 0; i < r->n; ++i) if (r->d[i] > 0) { r->d[i] -= 1; break; }
         o->msg3_resources += (long long)N_sc * n_sf;
+        perf_sample(o, NBIOT_TR_RES_MSG3, CE_level, o->time, N_sc * n_sf, 0);
     } else o->valid_CE_control = 0;
     schedule_NPDCCH_arrival(o, NPDCCH_sf);
     update_state(o);
@@ -1030,6 +1048,7 @@ static void step_data(Oracle *o, const int32_t *a)                    /* node_b.
         Event e = make_event(EV_NPUSCH_END); e.ue = ue; e.ue_id = ue->id;
         schedule_event(o, t_ul_end, e);
         o->NPUSCH_resources += (long long)N_sc * n_sf;
+        perf_sample(o, NBIOT_TR_RES_NPUSCH, CE_level, o->time, N_sc * n_sf, 0);
     } else if (new_data) VPUSH(o->unfit_id, ue->id);
     schedule_NPDCCH_arrival(o, NPDCCH_sf);
     update_state(o);
@@ -1299,6 +1318,7 @@ void orc_destroy(Oracle *o)
     VFREE(o->sc_log); VFREE(o->rx_id); VFREE(o->rx_delay); VFREE(o->err_id); VFREE(o->unfit_id); VFREE(o->acc_id); VFREE(o->acc_delay);
     VFREE(o->info_incoming); VFREE(o->info_delays); VFREE(o->info_service);
     VFREE(o->access_history); VFREE(o->connection_history); VFREE(o->delay_history); VFREE(o->bits_history);
+    VFREE(o->samples);
     free(o);
 }
 
@@ -1309,6 +1329,13 @@ int orc_get_stats(Oracle *o, int which, int32_t *out, int cap)
     ivec *v = which == 0 ? &o->delay_history : which == 1 ? &o->connection_history : which == 2 ? &o->access_history : &o->bits_history;
     for (int i = 0; i < v->n && i < cap; ++i) out[i] = v->d[i];
     return v->n;
+}
+
+/* the sample lists since the last reset, in append order; returns the true length, copies at most cap samples */
+int orc_get_samples(Oracle *o, nbiot_trace_rec_t *out, int cap)
+{
+    for (int i = 0; i < o->samples.n && i < cap; ++i) out[i] = o->samples.d[i];
+    return o->samples.n;
 }
 
 /* lists of the last NPRACH_update info: returns the true lengths, copies at most cap entries */

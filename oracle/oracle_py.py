@@ -7,7 +7,7 @@ import subprocess
 
 import numpy as np
 
-from nb_iot_environment_b200.record import RECORD_DTYPE, NbiotConf, make_conf
+from nb_iot_environment_b200.record import RECORD_DTYPE, TRACE_DTYPE, NbiotConf, make_conf
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -31,6 +31,8 @@ def lib():
         L.orc_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_get_stats.restype = ctypes.c_int
         L.orc_get_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.orc_get_samples.restype = ctypes.c_int
+        L.orc_get_samples.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.orc_get_hist.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 2
         L.orc_get_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_set_event_log.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
@@ -114,6 +116,13 @@ class OracleCell:
             out[name] = buf[:n].copy()
         out['th'] = out['bits'].astype(np.float64) / out['delay'].astype(np.float64)      # acked_data / delay (perf_monitor.py:169)
         return out
+
+    def samples(self, cap=1 << 18):
+        """PerfMonitor's sample lists since reset, in append order (TRACE_DTYPE)"""
+        buf = np.zeros(cap, dtype=TRACE_DTYPE)
+        n = self.L.orc_get_samples(self.h, buf.ctypes.data, cap)
+        assert n <= cap
+        return buf[:n].copy()
 
     def counters(self):
         out = np.zeros(16, dtype=np.int64); av = ctypes.c_double()

@@ -38,7 +38,7 @@ struct Staged {
         c->service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
         c->scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
         c->rec = (nbiot_record_t *)(s + L.off_rec) + i;
-        c->lut2 = e->lut2; c->mcs = e->mcs; c->conf = *(const nbiot_conf_hot_t *)&e->conf; c->ctrl = &e->cc.ctrl;
+        c->lut2 = e->lut2; c->mcs = e->mcs; memcpy(&c->conf, &e->conf, sizeof(nbiot_conf_hot_t)); c->ctrl = &e->cc.ctrl;
         c->W = L.grid_w; c->ue_cap = L.ue_cap; c->ra_cap = L.ra_cap; c->hist_cap = L.hist_cap; c->C = L.n_carriers;
         c->evlog = (e->evlog && i == 0) ? e->evlog : NULL; c->evlog_cap = e->evlog_cap;
         c->grid = (uint16_t *)(buf + sizeof(NbCtx) + sizeof(NbHdr));
@@ -83,7 +83,7 @@ void *emu_create(const nbiot_conf_t *conf, int n_inst, const uint64_t *seeds, co
     e->conf = *conf; e->cc.ctrl = nb_make_ctrl_dev(ctrl); e->lut2 = lut2; e->mcs = mcs;
     e->L = nb_make_layout(conf, n_inst);
     e->state = (uint8_t *)calloc(1, e->L.total);
-    e->cc.cold = nb_make_cold(conf, e->state, e->L.off_occ, e->L.off_stat);
+    e->cc.cold = nb_make_cold(conf, e->state, e->L.off_occ, e->L.off_stat, e->L.off_trace);
     for (int i = 0; i < n_inst; ++i) { Staged st(e, i, false); nbc_construct(*st.c, seeds[i], &e->cc.ctrl); }
     return e;
 }
@@ -132,6 +132,17 @@ int emu_stats(void *p, int i, int which, int32_t *out, int cap)
     int n = ((NbOccHist *)(e->state + e->L.off_occ))[i].stat_n, sc = e->L.stat_cap;
     const int32_t *v = (const int32_t *)(e->state + e->L.off_stat) + ((size_t)i * 4 + which) * sc;
     for (int k = 0; k < n && k < cap && k < sc; ++k) out[k] = v[k];
+    return n;
+}
+
+// sample ring of instance i (conf['traces'] / conf['statistics']): copies up to cap samples in order of occurrence, returns the number recorded
+int emu_trace(void *p, int i, nbiot_trace_rec_t *out, int cap)
+{
+    Emu *e = (Emu *)p;
+    int n = ((NbOccHist *)(e->state + e->L.off_occ))[i].trace_n, tc = e->L.trace_cap;
+    const nbiot_trace_rec_t *v = (const nbiot_trace_rec_t *)(e->state + e->L.off_trace) + (size_t)i * tc;
+    int first = n > tc ? n - tc : 0;
+    for (int k = first, j = 0; k < n && j < cap; ++k, ++j) out[j] = v[k % tc];
     return n;
 }
 

@@ -53,6 +53,29 @@ class Golden:
         return {'delay': self.z[f'stat_delay_{si}'], 'connection': self.z[f'stat_conn_{si}'], 'access': self.z[f'stat_access_{si}'], 'th': self.z[f'stat_th_{si}']}
 
 
+    def pm_lists(self, si):
+        """PerfMonitor's sample lists of a traces / statistics case as the reference holds them (lists of tuples / values), or None"""
+        pre, suf = 'pm_', f'_{si}'
+        keys = [k for k in self.z.files if k.startswith(pre) and k.endswith(suf)]
+        if not any(k.startswith('pm_RAR_in') or k.startswith('pm_rar_detections') for k in keys):
+            return None
+        out = {}
+        for k in keys:
+            name, v = k[len(pre):-len(suf)], self.z[k]
+            vals = [tuple(int(x) for x in row) for row in v] if v.ndim == 2 else [int(x) for x in v]
+            if name[-2:] in ('_0', '_1', '_2') and not name.endswith('history'):
+                out.setdefault(name[:-2], [None, None, None])[int(name[-1])] = vals
+            else:
+                out[name] = vals
+        return out
+
+
+def assert_pm_lists(got, want, what=''):
+    """got: samples_to_lists(...) of a cell; want: Golden.pm_lists(si). Every list the golden holds must be equal."""
+    for k, v in want.items():
+        assert got[k] == v, f'{what} PerfMonitor.{k} differs'
+
+
 def record_diff(a, b, rtol=0.0, skip=NON_PARITY_FIELDS):
     """list of (field, a, b) that differ: integers exactly, floats exactly (rtol=0) or within rtol"""
     out = []

@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 from nb_iot_environment_b200.controller import ControllerTables, NbiotCtrl
-from nb_iot_environment_b200.record import RECORD_DTYPE, NbiotConf, make_conf
+from nb_iot_environment_b200.record import RECORD_DTYPE, TRACE_DTYPE, NbiotConf, make_conf
 from oracle.oracle_py import tables
 
 _HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_hostemu')
@@ -28,6 +28,8 @@ def lib(lanes):
         L.emu_stats.restype = ctypes.c_int
         L.emu_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.emu_records.argtypes = [ctypes.c_void_p]
+        L.emu_trace.restype = ctypes.c_int
+        L.emu_trace.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.emu_counters.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         assert L.emu_lanes() == {'1t': 1, '1tg': 1, '32h': 32}.get(lanes, lanes) and L.emu_tasks() == (1 if lanes in ('1t', '1tg') else 0)
         _LIBS[lanes] = L
@@ -82,6 +84,11 @@ class EmuBatch:
             out[name] = buf[:min(n, cap, self.cconf.stat_cap)].copy()
             out['n'] = n
         return out
+
+    def samples(self, i, cap=1 << 16):
+        buf = np.zeros(cap, dtype=TRACE_DTYPE)
+        n = self.L.emu_trace(self.h, i, buf.ctypes.data, cap)
+        return buf[:min(n, cap, self.cconf.trace_cap)].copy(), n
 
     def counters(self, i):
         out = np.zeros(16, dtype=np.int64); av = ctypes.c_double()

@@ -93,8 +93,12 @@ def test_conf_validation():
     assert make_conf(base).stat_cap == 0 and make_conf(base, stat_cap=64).stat_cap == 64
     with pytest.raises(ValueError):
         make_conf(dict(base, clustered=True, cluster_ues=[5, 5]))
+    c = make_conf(dict(base, traces=True))                          # perf_monitor.py:61-69: the NPRACH and msg3 sample lists
+    assert (c.trace_mask, c.trace_cap, c.stat_cap) == (3, 8192, 0)
+    c = make_conf(dict(base, statistics=True), trace_cap=100)
+    assert (c.trace_mask, c.trace_cap, c.stat_cap) == (0x7C, 100, 2048) and make_conf(base).trace_cap == 0
     with pytest.raises(NotImplementedError):
-        make_conf(dict(base, traces=True))
+        make_conf(dict(base, animate_stats=True))
     with pytest.raises(NotImplementedError):
         make_conf(dict(base, reward_criteria='average_total_delay'))
     with pytest.raises(KeyError):

@@ -5,7 +5,7 @@ the unmodified Python reference. Integer fields bit-exact; float fields bit-exac
 import numpy as np
 import pytest
 
-from golden_util import CASES, Golden, record_diff, REF_RTOL
+from golden_util import CASES, Golden, record_diff, assert_pm_lists, REF_RTOL
 
 pytestmark = pytest.mark.gpu
 
@@ -81,6 +81,13 @@ def test_golden_traces_and_oracle(case, kernel):
                 assert np.array_equal(lists[1][si, :len(gdl)], gdl) and np.array_equal(lists[2][si, :len(gsv)], gsv)
                 assert np.allclose(lists[0][si, :len(ginc)], ginc, rtol=REF_RTOL, atol=0)
     assert not (recs['fault'] & 0x1F).any()
+    if g.pm_lists(0) is not None:
+        # conf['traces'] / conf['statistics']: PerfMonitor's sample lists (perf_monitor.py:61-79) through env.traces() / env.histories()
+        tr, hs = env.traces(), env.histories()
+        for si in range(len(g.seeds)):
+            got = dict(tr[si]); got.update(hs[si])
+            assert not tr[si]['truncated'] and not hs[si]['samples_truncated']
+            assert_pm_lists(got, g.pm_lists(si), f'{case} seed {g.seeds[si]}')
     if g.stats(0) is not None:
         # conf['statistics']: the per-departure histories (perf_monitor.py:61-84) and the batch histogram computed on the device
         hs = env.histories()
@@ -543,8 +550,8 @@ def test_parity_beyond_4gib_config3_setup():
     assert env.state.numel() > 4 * (1 << 32)
     ra_cap = caps['ue_cap'] + 64
     arrays = [3504, 2 * caps['grid_w'], 3 * ra_cap * 16, caps['ue_cap'] * 16, caps['ue_cap'] * 64, caps['ue_cap'] * 2, RECORD_DTYPE.itemsize, ra_cap * 2]
-    idx = _sample_cells(N, arrays)
-    assert len(idx) >= 200
+    idx = _sample_cells(N, arrays, n_random=260)
+    assert len(idx) >= 256
     g = torch.Generator(device='cuda'); g.manual_seed(11)
     nvec = torch.tensor(env.action_nvec, device='cuda')
     env.reset()
@@ -574,7 +581,7 @@ def test_parity_beyond_4gib_two_carriers():
     env = BatchedNBIoTEnv(CFG4, num_envs=N, n_carriers=2, all_states_external=True, **caps)
     assert env.state.numel() > 2 * (1 << 32)
     ra_cap = caps['ue_cap'] + 64
-    idx = _sample_cells(N, [2 * 2 * caps['grid_w'], 3 * ra_cap * 16, caps['ue_cap'] * 16, caps['ue_cap'] * 64, caps['ue_cap'] * 2], n_random=200)
+    idx = _sample_cells(N, [2 * 2 * caps['grid_w'], 3 * ra_cap * 16, caps['ue_cap'] * 16, caps['ue_cap'] * 64, caps['ue_cap'] * 2], n_random=260)
     mx = torch.tensor([1, 3, 6, 7, 3, 3, 4, 11, 7, 7, 10, 15, 5, 7, 7, 5, 7, 7, 5, 7, 7, 14, 14], device='cuda') + 1
     g = torch.Generator(device='cuda'); g.manual_seed(12)
     env.reset()

@@ -5,7 +5,7 @@ shorter prefix. The GPU itself is checked in test_gpu_parity.py."""
 import numpy as np
 import pytest
 
-from golden_util import CASES, Golden, record_diff, REF_RTOL
+from golden_util import CASES, Golden, record_diff, assert_pm_lists, REF_RTOL
 
 CAPS = {'manual_branches': dict(grid_w=4096), 'cfg3_npusch_random_policy': dict(grid_w=2048), 'cfg2_random_policy': dict(grid_w=2048),
         'cfg4_two_carriers_bursty': dict(grid_w=2048)}
@@ -35,6 +35,12 @@ def _replay(case, lanes, decisions):
                     assert c[k] == pytest.approx(v, rel=REF_RTOL)
                 else:
                     assert c[k] == v, k
+            gl = g.pm_lists(si)
+            if gl is not None:                                   # traces / statistics sample lists (perf_monitor.py:61-79)
+                from nb_iot_environment_b200.record import samples_to_lists
+                rec_, n_ = b.samples(si)
+                assert n_ == len(rec_)
+                assert_pm_lists(samples_to_lists(rec_), gl, f'{case} seed {g.seeds[si]}')
             gs = g.stats(si)
             if gs is not None:                                   # statistics histories (perf_monitor.py:161-171)
                 st = b.stats(si)

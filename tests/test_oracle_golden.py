@@ -3,7 +3,7 @@ reference: integer fields bit-exact, float fields to 1e-9 relative, same number 
 import numpy as np
 import pytest
 
-from golden_util import CASES, Golden, record_diff, REF_RTOL
+from golden_util import CASES, Golden, record_diff, assert_pm_lists, REF_RTOL
 
 
 @pytest.mark.parametrize('case', CASES)
@@ -40,5 +40,9 @@ def test_oracle_replays_reference_trace(case, oracle_lib):
                 assert np.array_equal(st[k], gs[k]), k
             assert np.array_equal(st['th'], gs['th'])           # acked bits / delay: one IEEE division of the same integers
             assert len(gs['delay']) == sum(gc['ue_departures'])
+        gl = g.pm_lists(si)
+        if gl is not None:                                       # traces / statistics: PerfMonitor's sample lists (perf_monitor.py:61-79)
+            from nb_iot_environment_b200.record import samples_to_lists
+            assert_pm_lists(samples_to_lists(cell.samples()), gl, f'{case} seed {seed}')
         ev = g.events(si)
         assert np.array_equal(cell.event_log()[:len(ev)], ev)   # same pops in the same (time, seq) order

@@ -54,6 +54,10 @@ CASES = {
     'clustered_statistics': dict(conf=dict(CFG1, ratio=0.5, clustered=True, statistics=True), nc=1, policy='fixed', seeds=[80, 81], decisions=1400),
     'clustered_tight_small_cell': dict(conf=dict(CFG1, clustered=True, cluster_ues=[3, 8], cluster_prob=0.9, cluster_range=2.0, max_d=5.0, statistics=True),
                                        nc=1, policy='random', seeds=[85], decisions=1400),
+    # SURVEY 8(f) rank 3, the rest: PerfMonitor's `traces` lists and the remaining `statistics` lists (perf_monitor.py:61-79, :111-140, :185-202)
+    'traces_statistics': dict(conf=dict(CFG1, ratio=0.5, traces=True, statistics=True), nc=1, policy='random', seeds=[90, 91], decisions=1200),
+    'traces_two_carriers': dict(conf={'M': 3000, 'ratio': 0.5, 'buffer_range': [100, 600], 'reward_criteria': 'throughput', 'random': True,
+                                      'traces': True, 'statistics': True}, nc=2, policy='random', seeds=[95], decisions=800),
     'invd_reward_small_cell': dict(conf=dict(CFG1, reward_criteria='invd_users', max_d=3.0, M=600), nc=1, policy='random', seeds=[70], decisions=800),
 }
 
@@ -80,7 +84,7 @@ def run_case(name):
     S, D = len(case['seeds']), case['decisions']
     records = np.zeros((S, D + 1), dtype=RECORD_DTYPE)
     actions = np.zeros((S, D, 23), dtype=np.int8)
-    counters, hists, events, stats = [], [], [], []
+    counters, hists, events, stats, pmlists = [], [], [], [], []
     for si, seed in enumerate(case['seeds']):
         cell = RefCell(case['conf'], seed, n_carriers=case['nc'], log_events=True)
         prng = np.random.default_rng(1000 + seed)
@@ -96,6 +100,23 @@ def run_case(name):
             pm = cell.perf
             stats.append((np.asarray(pm.delay_history, np.int32), np.asarray(pm.connection_history, np.int32),
                           np.asarray(pm.access_history, np.int32), np.asarray(pm.th_history, np.float64)))
+        pl = {}
+        pm = cell.perf
+        if case['conf'].get('traces'):
+            for k in ('rar_detections', 'rar_errors', 'rar_collisions', 'nprach_arrivals', 'nprach_detections'):
+                for ce in range(3):
+                    pl[f'{k}_{ce}'] = np.asarray(getattr(pm, k)[ce], dtype=np.int64).reshape(-1, 2)
+            for k in ('t_rar_detections', 't_nprach_arrivals', 't_nprach_detections'):
+                pl[k] = np.asarray(getattr(pm, k), dtype=np.int64).reshape(-1, 2)
+        if case['conf'].get('statistics'):
+            for k in ('RAR_in', 'RAR_attmp', 'RAR_sent', 'RAR_detected'):
+                for ce in range(3):
+                    pl[f'{k}_{ce}'] = np.asarray(getattr(pm, k)[ce], dtype=np.int64)
+            for ce in range(3):
+                pl[f'npusch_delivered_{ce}'] = np.asarray(pm.npusch_delivered[ce], dtype=np.int64).reshape(-1, 2)
+            for k in ('msg3_resources_history', 'NPUSCH_resources_history', 'NPRACH_resources_history'):
+                pl[k] = np.asarray(getattr(pm, k), dtype=np.int64)
+        pmlists.append(pl)
         hists.append(cell.hists)
         events.append(np.asarray(cell.events, dtype=np.int32))
         cell.close()
@@ -114,6 +135,8 @@ def run_case(name):
         flat[f'events_{si}'] = events[si][:20000]
         if stats:
             flat[f'stat_delay_{si}'], flat[f'stat_conn_{si}'], flat[f'stat_access_{si}'], flat[f'stat_th_{si}'] = stats[si]
+        for k, v in pmlists[si].items():
+            flat[f'pm_{k}_{si}'] = v
     meta = {'name': name, 'conf': case['conf'], 'n_carriers': case['nc'], 'seeds': case['seeds'], 'policy': case['policy'],
             'decisions': D, 'counters': counters, 'record_itemsize': RECORD_DTYPE.itemsize,
             'record_descr': str(RECORD_DTYPE.descr)}
