@@ -243,7 +243,7 @@ def block_config5(job, local, K, W):
     from nb_iot_environment_b200 import BatchedNBIoTEnv
     from nb_iot_environment_b200.sharding import shard_seeds
     N = int(os.environ.get('NBIOT_BENCH_N5', '131072'))
-    env = BatchedNBIoTEnv(CFG1, num_envs=N, seeds=shard_seeds(N * job.world, job.rank, job.world), device=local, ue_cap=256, grid_w=1024, hist_cap=64)
+    env = BatchedNBIoTEnv(CFG1, num_envs=N, seeds=shard_seeds(N * job.world, job.rank, job.world), device=local, ue_cap=256, grid_w=1024, hist_cap=512)
     env.reset()
     for s in range(W):
         env.run_until(SF_PER_STEP * (s + 1))
@@ -275,9 +275,11 @@ def block_config2(job, local, K, W):
     N = int(os.environ.get('NBIOT_BENCH_N2', '65536'))
     K, W = 10 * K, 50
     env = BatchedNBIoTEnv(CFG3, agents_conf=NPUSCH_AGENTS, ext_agent=0, num_envs=N, seeds=shard_seeds(N * job.world, job.rank, job.world), device=local,
-                          ue_cap=CFG3['M'], grid_w=2048, hist_cap=64)
-    nvec = env.action_nvec
-    acts = torch.from_numpy(np.stack([uniform_actions(77, s, job.rank * N, N, nvec) for s in range(W + K)])).to(job.dev)
+                          ue_cap=CFG3['M'], grid_w=2048, hist_cap=1024)
+    # uniform-random actions from a device generator seeded per rank: step s draws the same values whatever --steps is
+    g = torch.Generator(device=job.dev); g.manual_seed(7700 + job.rank)
+    nvec = torch.tensor(env.action_nvec, device=job.dev)
+    acts = (torch.rand((W + K, N, 3), device=job.dev, generator=g) * nvec).to(torch.uint8)
     env.reset()
     for s in range(W):
         env.step(acts[s])
@@ -309,12 +311,14 @@ def block_config3(job, local, K, W):
     N = int(os.environ.get('NBIOT_BENCH_N3', '0')) or (65536 if job.world == 1 else 262144 // job.world)
     K, W = 10 * K, 50
     env = BatchedNBIoTEnv(CFG4, num_envs=N, seeds=shard_seeds(N * job.world, job.rank, job.world), n_carriers=2, device=local, all_states_external=True,
-                          ue_cap=CFG4['M'], grid_w=2048, hist_cap=64)
-    # uniform over control_max_values for 2 carriers minus what the reference raises on (tools/gen_golden.py policy_action)
-    mx = [2, 4, 7, 8, 4, 4, 5, 12, 8, 8, 11, 16, 6, 8, 8, 6, 8, 8, 6, 8, 8, 15, 15]
+                          ue_cap=CFG4['M'], grid_w=2048, hist_cap=2048)
+    # uniform over control_max_values for 2 carriers minus what the reference raises on (tools/gen_golden.py policy_action), from a device
+    # generator seeded per rank (step s draws the same values whatever --steps is)
+    mx = torch.tensor([2, 4, 7, 8, 4, 4, 5, 12, 8, 8, 11, 16, 6, 8, 8, 6, 8, 8, 6, 8, 8, 15, 15], device=job.dev)
+    g = torch.Generator(device=job.dev); g.manual_seed(7800 + job.rank)
 
     def actions(s):
-        a = torch.from_numpy(uniform_actions(78, s, job.rank * N, N, mx)).to(job.dev)
+        a = (torch.rand((N, 23), device=job.dev, generator=g) * mx).to(torch.uint8)
         a[:, 5] = torch.where(a[:, 5] == 2, torch.full_like(a[:, 5], 3), a[:, 5])          # sc = 2 is invalid
         rar = env.record_field('state') == 2                                              # RAR_window: ce_level / rar_Imcs share items 1 / 2
         a[:, 1] = torch.where(rar, a[:, 1] % 3, a[:, 1]); a[:, 2] = torch.where(rar, a[:, 2] % 3, a[:, 2])

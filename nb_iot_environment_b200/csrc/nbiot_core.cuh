@@ -55,6 +55,9 @@ struct __attribute__((aligned(16))) NbCtx {
     int32_t *evlog;           /* optional (t, type) pop log for debugging */
     int W, ue_cap, ra_cap, hist_cap, C, evlog_cap;
     uint16_t *grid;           /* the look-ahead ring: staged in shared memory behind the header, or in place in HBM (short launches) */
+#if NB_LANES == 1
+    uint16_t *blk;            /* [C][W / 32] block summaries of the ring (thread-per-cell kernel; NULL: plain column scans) */
+#endif
 #ifdef NB_TASKS
     int tk_until, tk_max_steps;   /* bounds of this launch (see "tasks" at the end of the file) */
     int tk_internal;              /* the launch has no external action: every agent of a state acts, no state hands control back */
@@ -187,14 +190,16 @@ NB_DEV uint32_t nbc_scan_chunks(NbCtx &c, int carrier, int a, int n)
 }
 
 #if NB_LANES == 1
-/* one lane owns the cell (thread-per-cell kernel, 1-lane CPU build): four columns per 8-byte word, ragged ends one by one.
- * The ring is 8-byte aligned and W is a multiple of 4, so a word whose first column index is a multiple of 4 never wraps. */
+/* One lane owns the cell (thread-per-cell kernel, 1-lane CPU build): four columns per 8-byte word, ragged ends one by one. The ring
+ * is 8-byte aligned and W is a multiple of 4, so a word whose first column index is a multiple of 4 never wraps.
+ * Long windows -- a high-CE transmission is hundreds to thousands of subframes -- would keep ONE lane of a warp scanning while the
+ * other 31 cells wait (19 % of the executed instructions at 1.4 active lanes, profiles/r02d_*), so the thread-per-cell kernel keeps
+ * BLOCK SUMMARIES next to the ring: c.blk[carrier][b] = OR of the 32 columns of ring block b. They are derived data: rebuilt from the
+ * ring at the start of a launch (nbc_blk_rebuild), maintained by every fill, never part of the state (the warp-per-cell kernel, which
+ * scans 32 columns per step, does not know them). A window then costs its two ragged ends plus one summary per whole block. */
 typedef uint64_t __attribute__((may_alias)) nb_u64a;
-NB_FN1S uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
+NB_DEV uint32_t nbc_cols_or(const uint16_t *g, int wm, int k, int e)
 {
-    const uint16_t *g = nbc_col(c, carrier, 0);
-    const int wm = c.W - 1;
-    int k = a, e = a + n;
     uint32_t v = 0; uint64_t v8 = 0;
     NB_NOUNROLL
     while (k < e && (k & 3)) { v |= g[k & wm]; ++k; }
@@ -204,6 +209,18 @@ NB_FN1S uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
     while (k < e) { v |= g[k & wm]; ++k; }
     v8 |= v8 >> 32;
     v |= (uint32_t)v8 | ((uint32_t)v8 >> 16);
+    return v & 0xFFFFu;
+}
+NB_FN1S uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)
+{
+    const uint16_t *g = nbc_col(c, carrier, 0);
+    const int wm = c.W - 1, e = a + n;
+    if (!c.blk || n < 64) return nbc_cols_or(g, wm, a, e);
+    const uint16_t *B = c.blk + carrier * (c.W >> 5);
+    const int bm = (c.W >> 5) - 1, hb = (a + 31) & ~31, te = e & ~31;      /* n >= 64: at least one whole block, hb < te */
+    uint32_t v = nbc_cols_or(g, wm, a, hb) | nbc_cols_or(g, wm, te, e);
+    NB_NOUNROLL
+    for (int b = hb >> 5; b < (te >> 5); ++b) v |= B[b & bm];
     return v & 0xFFFFu;
 }
 NB_FNM3 void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask, int set)
@@ -223,6 +240,37 @@ NB_FNM3 void nbc_grid_update(NbCtx &c, int carrier, int a, int n, uint32_t mask,
     }
     NB_NOUNROLL
     while (k < e) { g[k & wm] = set ? (uint16_t)(g[k & wm] | mask) : (uint16_t)0; ++k; }
+    if (c.blk && n > 0) {
+        uint16_t *B = c.blk + carrier * (c.W >> 5);
+        const int bm = (c.W >> 5) - 1;
+        if (set) {                                             /* every block the fill touches gains the mask */
+            NB_NOUNROLL
+            for (int b = a >> 5; b <= ((e - 1) >> 5); ++b) B[b & bm] = (uint16_t)(B[b & bm] | mask);
+        } else {                                               /* freshly generated columns: a block restarts when its first column does */
+            NB_NOUNROLL
+            for (int b = (a + 31) >> 5; b <= ((e - 1) >> 5); ++b) B[b & bm] = (uint16_t)0;
+        }
+    }
+}
+/* block summaries of the live part of the ring, [t_now, t_ahead): oldest block first, so that when the live range wraps onto the slot
+ * of its own first (partial, never whole inside a window) block the newer one wins */
+NB_FN void nbc_blk_rebuild(NbCtx &c)
+{
+    NbHdr *h = nbc_hdr(c);
+    if (!c.blk || h->t_ahead <= h->t_now) return;
+    const int wm = c.W - 1, bm = (c.W >> 5) - 1;
+    NB_NOUNROLL
+    for (int cc = 0; cc < NB_NC(c); ++cc) {
+        const uint16_t *g = nbc_col(c, cc, 0);
+        uint16_t *B = c.blk + cc * (c.W >> 5);
+        NB_NOUNROLL
+        for (int b = h->t_now >> 5; b <= ((h->t_ahead - 1) >> 5); ++b) {
+            int lo = b << 5, hi = lo + 32;
+            if (lo < h->t_now) lo = h->t_now;
+            if (hi > h->t_ahead) hi = h->t_ahead;
+            B[b & bm] = (uint16_t)nbc_cols_or(g, wm, lo, hi);
+        }
+    }
 }
 #elif NB_GRID_MODE == 0
 NB_FN1S uint32_t nbc_grid_busy(NbCtx &c, int carrier, int a, int n)

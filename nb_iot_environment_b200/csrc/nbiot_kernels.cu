@@ -41,6 +41,7 @@ struct nbiot_handle {
     uint64_t *seeds_dev;
     unsigned int *counter_dev;
     unsigned long long *prof_dev;   /* NBIOT_PROF_INST=1: per-instance timing of the last launch */
+    uint16_t *blk_dev;              /* thread-per-cell kernel: block summaries of the look-ahead rings (derived data) */
     int blocks, smem_bytes, sim_hi;
     int blocks_short, smem_short, sim_hi_short, stage_policy;     /* geometry of launches that leave the grid in HBM */
     NbSimVariant k_gen, k_c1, k_gs, k_c1s;   /* builds of the warp-per-instance kernels (nbiot_simk.cuh): generic / single carrier, ring anywhere / staged */
@@ -157,7 +158,7 @@ static NbKernelArgs make_args(nbiot_handle_t *h, int stage_grid = 1)
     A.counter = h->counter_dev; A.prof = h->prof_dev; A.evlog = h->evlog; A.evlog_cap = h->evlog_cap;
     A.hdr_bytes16 = (int)(sizeof(NbHdr) / 16);
     A.grid_bytes16 = (int)((size_t)h->L.n_carriers * h->L.grid_w * 2 / 16);
-    A.stage_grid = stage_grid;
+    A.stage_grid = stage_grid; A.blk = h->blk_dev;
     A.smem_per_warp = (int)sizeof(NbCtx) + A.hdr_bytes16 * 16 + (stage_grid ? A.grid_bytes16 * 16 : 0);
     return A;
 }
@@ -264,6 +265,8 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
      * lanes; one thread per cell shares every common instruction between 32 cells but needs the cells to fill the machine
      * (148 SMs x 16 warps x 32 lanes = 75 776) -- DESIGN.md section 6c has the measured crossover. */
     h->use_tpc = n_inst >= NB_TPC_MIN_CELLS ? 2 : 0;
+    if (getenv("NBIOT_TPC_BLK") && !atoi(getenv("NBIOT_TPC_BLK"))) h->blk_dev = nullptr;       /* measurement knob: plain column scans */
+    else CK(cudaMalloc(&h->blk_dev, sizeof(uint16_t) * (size_t)n_inst * L.n_carriers * (L.grid_w >> 5)));
     if (const char *e = getenv("NBIOT_KERNEL")) {
         if (!strcmp(e, "tpc")) { h->use_tpc = 1; h->tpc_forced = 1; }
         else if (!strcmp(e, "tpcv")) { h->use_tpc = 2; h->tpc_forced = 1; }
@@ -319,7 +322,7 @@ int nbiot_destroy(nbiot_handle_t *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->conf_dev); cudaFree(h->ctrl_dev); cudaFree(h->lut2_dev); cudaFree(h->mcs_dev); cudaFree(h->seeds_dev); cudaFree(h->counter_dev); cudaFree(h->prof_dev);
+    cudaFree(h->conf_dev); cudaFree(h->ctrl_dev); cudaFree(h->lut2_dev); cudaFree(h->mcs_dev); cudaFree(h->seeds_dev); cudaFree(h->counter_dev); cudaFree(h->prof_dev); cudaFree(h->blk_dev);
     cudaFree(h->act_dev); cudaFree(h->obs_dev); cudaFree(h->rew_dev); cudaFree(h->items_dev);
     cudaFreeHost(h->act_pin); cudaFreeHost(h->obs_pin); cudaFreeHost(h->rew_pin);
     delete h;

@@ -21,6 +21,7 @@ struct NbKernelArgs {
     int32_t *evlog; int evlog_cap;
     int smem_per_warp, hdr_bytes16, grid_bytes16;
     int stage_grid;              /* 1: the look-ahead ring is staged in shared memory; 0: used in place in HBM (short launches) */
+    uint16_t *blk;               /* thread-per-cell kernel: [n_inst][C][W / 32] block summaries of the rings (derived data, rebuilt every launch) */
 };
 
 
@@ -57,6 +58,9 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
     c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
     c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
     c.evlog = i == 0 ? A.evlog : nullptr;
+#if NB_LANES == 1
+    c.blk = A.blk ? A.blk + (size_t)i * A.L.n_carriers * (A.L.grid_w >> 5) : nullptr;
+#endif
     c.grid = A.stage_grid ? (uint16_t *)((unsigned char *)&c + sizeof(NbCtx) + sizeof(NbHdr))
                           : (uint16_t *)(A.state + A.L.off_grid) + (size_t)i * A.L.n_carriers * A.L.grid_w;
 }

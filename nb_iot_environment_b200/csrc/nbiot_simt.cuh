@@ -28,8 +28,11 @@
 #ifndef NB_TPC_THREADS
 #define NB_TPC_THREADS 128
 #endif
+/* 8 CTAs of 128 threads = 32 warps per SM at 64 registers: the kernel waits on memory (local-memory headers and scattered list
+ * accesses miss L1), so resident warps count for more than registers: +26 % over 16 warps at 115 registers; 40 and 48 warps are
+ * no better (profiles/r02_tpc_variants.txt) */
 #ifndef NB_TPC_MIN_CTAS
-#define NB_TPC_MIN_CTAS 4
+#define NB_TPC_MIN_CTAS 8
 #endif
 
 #define NB_CAT2(a, b) a##b
@@ -53,6 +56,7 @@ nbiot_simt_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *act
     uint4 *hg = (uint4 *)((NbHdr *)(A.state + A.L.off_hdr) + i), *hl = (uint4 *)&L.h;
     NB_NOUNROLL
     for (int k = 0; k < (int)(sizeof(NbHdr) / 16); ++k) hl[k] = hg[k];
+    nbc_blk_rebuild(L.c);
     unsigned long long t0 = 0;
     if (A.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     nbc_controller_advance(L.c, L.c.ctrl, ext_actions ? ext_actions + (size_t)i * L.c.ctrl->ext_k : nullptr, until_time, max_steps);
@@ -89,6 +93,7 @@ nbiot_simtv_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *ac
         nb_fill_ctx(L.c, A, i);
         NB_NOUNROLL
         for (int w = 0; w < (int)(sizeof(NbHdr) / 16); ++w) hl[w] = hg[w];
+        nbc_blk_rebuild(L.c);
         L.c.tk_until = until_time; L.c.tk_max_steps = max_steps; L.c.tk_internal = ext_actions ? 0 : 1;
         k = nbc_task_begin(L.c, ext_actions ? ext_actions + (size_t)i * L.c.ctrl->ext_k : nullptr);
     }

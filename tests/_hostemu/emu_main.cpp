@@ -19,7 +19,7 @@ struct Emu {
 
 // mirrors the kernel's staging: [NbCtx | NbHdr | grid] in one scratch slice, copied in and out
 struct Staged {
-    Emu *e; int i; unsigned char *buf; NbCtx *c;
+    Emu *e; int i; unsigned char *buf; NbCtx *c; uint16_t *blkbuf = NULL;
     Staged(Emu *e_, int i_, bool load) : e(e_), i(i_)
     {
         const NbLayout &L = e->L;
@@ -42,9 +42,19 @@ struct Staged {
         c->W = L.grid_w; c->ue_cap = L.ue_cap; c->ra_cap = L.ra_cap; c->hist_cap = L.hist_cap; c->C = L.n_carriers;
         c->evlog = (e->evlog && i == 0) ? e->evlog : NULL; c->evlog_cap = e->evlog_cap;
         c->grid = (uint16_t *)(buf + sizeof(NbCtx) + sizeof(NbHdr));
+#if NB_LANES == 1
+        c->blk = NULL;
+#endif
         if (load) {
             memcpy(buf + sizeof(NbCtx), (NbHdr *)(s + L.off_hdr) + i, sizeof(NbHdr));
             memcpy(buf + sizeof(NbCtx) + sizeof(NbHdr), (uint16_t *)(s + L.off_grid) + (size_t)i * L.n_carriers * L.grid_w, gbytes);
+#if defined(NBIOT_EMU_BLK) && NB_LANES == 1
+            // the thread-per-cell kernel's block summaries: derived data, filled with garbage and rebuilt whenever a cell is loaded
+            blkbuf = (uint16_t *)malloc(sizeof(uint16_t) * L.n_carriers * (L.grid_w >> 5));
+            memset(blkbuf, 0xA5, sizeof(uint16_t) * L.n_carriers * (L.grid_w >> 5));
+            c->blk = blkbuf;
+            nbc_blk_rebuild(*c);
+#endif
         }
     }
     ~Staged()
@@ -53,7 +63,7 @@ struct Staged {
         size_t gbytes = (size_t)L.n_carriers * L.grid_w * 2;
         memcpy((NbHdr *)(e->state + L.off_hdr) + i, buf + sizeof(NbCtx), sizeof(NbHdr));
         memcpy((uint16_t *)(e->state + L.off_grid) + (size_t)i * L.n_carriers * L.grid_w, buf + sizeof(NbCtx) + sizeof(NbHdr), gbytes);
-        free(buf);
+        free(buf); free(blkbuf);
     }
 };
 

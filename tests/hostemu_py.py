@@ -31,7 +31,7 @@ def lib(lanes):
         L.emu_trace.restype = ctypes.c_int
         L.emu_trace.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.emu_counters.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
-        assert L.emu_lanes() == {'1t': 1, '1tg': 1, '32h': 32}.get(lanes, lanes) and L.emu_tasks() == (1 if lanes in ('1t', '1tg') else 0)
+        assert L.emu_lanes() == {'1t': 1, '1tg': 1, '1b': 1, '32h': 32}.get(lanes, lanes) and L.emu_tasks() == (1 if lanes in ('1t', '1tg') else 0)
         _LIBS[lanes] = L
     return _LIBS[lanes]
 

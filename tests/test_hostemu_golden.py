@@ -74,6 +74,13 @@ def test_core_task_chain_fine_grained(case, oracle_lib):
     _replay(case, '1tg', 10 ** 9)
 
 
+@pytest.mark.parametrize('case', CASES)
+def test_core_with_block_summaries(case, oracle_lib):
+    """The one-lane core with the thread-per-cell kernel's block summaries of the look-ahead ring (window scans read one summary per
+    whole 32-column block): rebuilt from the ring at every decision here, maintained by every fill in between."""
+    _replay(case, '1b', 10 ** 9)
+
+
 @pytest.mark.parametrize('case', ['cfg1_default', 'cfg3_npusch_random_policy'])
 def test_event_selection_second_pass(case, oracle_lib):
     """The event selection looks at 32 keys per pass and takes a second pass only when pool entries above the first 22 are in use
@@ -81,7 +88,7 @@ def test_event_selection_second_pass(case, oracle_lib):
     _replay(case, '32h', 300)
 
 
-@pytest.mark.parametrize('lanes', [1, '1tg'])
+@pytest.mark.parametrize('lanes', [1, '1tg', '1b'])
 def test_run_until_with_an_external_agent_registered(lanes, oracle_lib):
     """Controller.run_until (controller.py:156-195) with an external agent registered: every agent of a state acts with its fixed
     action and the cells run to the horizon (the core used to hand control back at the external agent's first decision)."""
@@ -93,10 +100,11 @@ def test_run_until_with_an_external_agent_registered(lanes, oracle_lib):
     seeds = [3, 4]
     b = EmuBatch(conf, seeds, lanes=lanes, ctrl=ControllerTables(NPRACH_AGENTS, 3).build(), ue_cap=1000, grid_w=2048, hist_cap=1024)
     b.reset()
-    recs, steps = b.advance(None, until_time=7000)
-    assert (recs['time'] >= 7000).all() and (steps > 100).all()
+    T = 20000 if lanes == '1b' else 7000          # one long advance: the block summaries are built once and maintained for thousands of fills
+    recs, steps = b.advance(None, until_time=T)
+    assert (recs['time'] >= T).all() and (steps > 100).all()
     for i, s in enumerate(seeds):
         c = OracleController(conf, s, agents_conf=NPRACH_AGENTS, ext_agent=3)
         c.reset()
-        c.run_until(7000)
+        c.run_until(T)
         assert not record_diff(c.rec, recs[i], rtol=0.0)
