@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 #include "nbiot.h"
 #include "nbiot_core.cuh"
@@ -56,6 +57,7 @@ struct nbiot_handle {
     uint8_t *act_dev; double *obs_dev, *rew_dev; nbiot_obs_item_t *items_dev;
     uint8_t *act_pin; double *obs_pin, *rew_pin;
     size_t act_cap, obs_cap, items_cap;
+    std::vector<nbiot_obs_item_t> items_host;    /* what items_dev holds */
 };
 
 static thread_local char g_err[512] = "";
@@ -233,8 +235,7 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     NbLayout L = nb_make_layout(conf, n_inst);
     if (state_bytes < L.total) return set_err(NBIOT_E_SIZE, "nbiot_create: state buffer smaller than nbiot_state_bytes()");
     cudaStream_t st = (cudaStream_t)stream;
-    nbiot_handle_t *h = new nbiot_handle_t();
-    memset(h, 0, sizeof *h);
+    nbiot_handle_t *h = new nbiot_handle_t();      /* value-initialised: every scalar member is zero */
     struct Guard { nbiot_handle_t *h; ~Guard() { if (h) nbiot_destroy(h); } } guard{ h };     /* every error return below frees what was allocated */
     h->conf = *conf; h->ctrl = *ctrl; h->L = L; h->device = device; h->n_inst = n_inst; h->state = (uint8_t *)state_dev;
     CK(cudaMalloc(&h->conf_dev, sizeof(nbiot_conf_t)));
@@ -384,11 +385,15 @@ static int ensure_items(nbiot_handle_t *h, const nbiot_obs_item_t *items, int n_
     *obs_dim = d;
     if (n_items <= 0) return 0;
     if ((size_t)n_items > h->items_cap) {
-        cudaFree(h->items_dev); h->items_dev = nullptr; h->items_cap = 0;
+        cudaFree(h->items_dev); h->items_dev = nullptr; h->items_cap = 0; h->items_host.clear();
         CK(cudaMalloc(&h->items_dev, sizeof(nbiot_obs_item_t) * (size_t)n_items));
         h->items_cap = (size_t)n_items;
     }
-    CK(cudaMemcpyAsync(h->items_dev, items, sizeof(nbiot_obs_item_t) * (size_t)n_items, cudaMemcpyHostToDevice, st));
+    /* the table only changes when the external agent does: upload it when it differs from what the device already holds */
+    if (h->items_host.size() != (size_t)n_items || memcmp(h->items_host.data(), items, sizeof(nbiot_obs_item_t) * (size_t)n_items) != 0) {
+        h->items_host.assign(items, items + n_items);
+        CK(cudaMemcpyAsync(h->items_dev, h->items_host.data(), sizeof(nbiot_obs_item_t) * (size_t)n_items, cudaMemcpyHostToDevice, st));
+    }
     return 0;
 }
 

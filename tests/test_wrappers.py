@@ -59,6 +59,23 @@ def _check_npusch(make_env):
     assert n_impossible > 0       # ... and the answer-without-stepping branch
 
 
+def _check_rar(make_env):
+    """RAR_wrapper of the reference (wrappers.py:366-421) on its own environment, both reward criteria, against RARWrapper"""
+    from nb_iot_environment_b200.wrappers import RARWrapper
+    z = np.load(os.path.join(GOLDEN_DIR, 'wrappers_rar.npz'))
+    meta = json.loads(bytes(z['meta']).decode())
+    seen = set()
+    for si, (seed, crit) in enumerate(zip(meta['seeds'], meta['criteria'])):
+        env = RARWrapper(make_env(meta['conf'], NPRACH_AGENTS, 1, [seed]), reward_criteria=crit)
+        env.reset()
+        acts, rew = z[f'acts_{si}'], z[f'rew_{si}']
+        for k in range(acts.shape[0]):
+            _, r, _, _, _ = env.step(acts[k][None, :])
+            assert float(r[0]) == rew[k], (crit, k)
+            seen.add(float(rew[k]))
+    assert -1.0 in seen and 1.0 in seen and len(seen) >= 5      # penalties, saturated and fractional rewards all occur
+
+
 def _oracle_env(conf, agents, ext, seeds):
     from oracle_vector_env import OracleVectorEnv
     return OracleVectorEnv(conf, agents, ext, seeds)
@@ -87,6 +104,15 @@ def test_nprach_wrapper_on_oracle(oracle_lib):
 
 def test_scheduler_wrapper_on_oracle(oracle_lib):
     _check_npusch(_oracle_env)
+
+
+def test_rar_wrapper_on_oracle(oracle_lib):
+    _check_rar(_oracle_env)
+
+
+@pytest.mark.gpu
+def test_rar_wrapper_on_cuda():
+    _check_rar(_cuda_env)
 
 
 @pytest.mark.gpu

@@ -4,6 +4,7 @@ driven by random wrapper-level actions: tests/golden/wrappers_*.npz.  Build cont
 
   nprach : scripts/nprach set-up (evaluate_RL.py:46-131): NPRACH_wrapper over agent 3, MultiDiscrete([105,4,4,4,6,6,6])
   npusch : scripts/npusch set-up (experiments_RL.py:40-131): BasicSchedulerWrapper + DiscreteActions over agent 0
+  rar    : RAR_wrapper (wrappers.py:366-421) over agent 1 of the scripts/nprach agent set, reward criteria 'msg3' and 'departures'
 """
 import json, os, sys
 import numpy as np
@@ -56,6 +57,22 @@ def main():
             acts.append(a); obs.append(np.asarray(o, float)); rew.append(float(r))
         res[f'acts_{si}'] = np.asarray(acts, np.int64); res[f'obs_{si}'] = np.asarray(obs); res[f'rew_{si}'] = np.asarray(rew)
     np.savez_compressed(os.path.join(out, 'wrappers_npusch.npz'), meta=np.frombuffer(json.dumps({'conf': CFG3, 'seeds': [510, 511]}).encode(), dtype=np.uint8), **res)
+    # ---- RAR wrapper (reference wrappers.py:366-421) over agent 1 (RAR_window: ce_level, rar_Imcs, Nrep), both reward criteria
+    conf = dict(CFG1, ratio=0.5, ce_mcs_automatic=False)
+    res = {}
+    seeds, criteria = [520, 521], ['msg3', 'departures']
+    for si, (seed, crit) in enumerate(zip(seeds, criteria)):
+        env = W.RAR_wrapper(make_env(m, conf, NPRACH_AGENTS, 1, seed), reward_criteria=crit)
+        rng = np.random.default_rng(seed)
+        obs0, _ = env.reset()
+        acts, obs, rew = [], [np.asarray(obs0, float)], []
+        for _ in range(400):
+            a = [int(rng.integers(0, 3)), int(rng.integers(0, 3)), int(rng.integers(0, 5))]
+            o, r, _, _, info = env.step(list(a))
+            acts.append(a); obs.append(np.asarray(o, float)); rew.append(float(r))
+        res[f'acts_{si}'] = np.asarray(acts, np.int64); res[f'obs_{si}'] = np.asarray(obs).reshape(len(obs), -1); res[f'rew_{si}'] = np.asarray(rew)
+    np.savez_compressed(os.path.join(out, 'wrappers_rar.npz'),
+                        meta=np.frombuffer(json.dumps({'conf': conf, 'seeds': seeds, 'criteria': criteria}).encode(), dtype=np.uint8), **res)
     print('wrote wrapper goldens')
 
 
