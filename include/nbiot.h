@@ -109,6 +109,10 @@ int nbiot_hist_ptrs(nbiot_handle_t *h, void **incoming_dev, void **delays_dev, v
  * register_*_resources, npusch_delivered; perf_monitor.py:61-79, :111-140, :161-202): trace_dev = nbiot_trace_rec_t[n_inst][trace_cap]
  * inside the state buffer (NULL when off), entry k of an instance at k % trace_cap; counts_dev = int32[n_inst] samples since reset */
 int nbiot_trace_ptrs(nbiot_handle_t *h, void **trace_dev, int *trace_cap);
+/* the per-epoch info lists (info['receptions'], ['errors'], ['unfit'], ['access']; perf_monitor.py:92-103) beyond the list_cap = 16 entries
+ * the record holds: spill_dev = int32[n_inst][6][spill_cap] inside the state buffer, rows = rx id, rx delay, error id, unfit id, access id,
+ * access delay; entry k >= list_cap of a list at column k - list_cap (the record's n_* fields are the true lengths) */
+int nbiot_spill_ptr(nbiot_handle_t *h, void **spill_dev, int *list_cap, int *spill_cap);
 int nbiot_trace_counts(nbiot_handle_t *h, int32_t *counts_dev, void *stream);
 /* conf.stat_cap > 0 (conf['statistics']): the per-departure histories of PerfMonitor (perf_monitor.py:61-84, :161-171; the arrays
  * experiments_RL.py:139-140 / experiments_MAMBRL.py:121-122 save) as rings in HBM.

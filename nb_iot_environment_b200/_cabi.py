@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('NBIOT_LIB') or os.path.join(_HERE, 'libnbiot_b200.so'
 # every symbol include/nbiot.h declares
 SYMBOLS = ['nbiot_abi_version', 'nbiot_last_error', 'nbiot_state_bytes', 'nbiot_hdr_bytes', 'nbiot_hdr_task_bytes', 'nbiot_create', 'nbiot_destroy',
            'nbiot_set_controller', 'nbiot_reset', 'nbiot_advance', 'nbiot_advance_masked', 'nbiot_records_ptr', 'nbiot_hist_ptrs', 'nbiot_gather_obs',
-           'nbiot_reduce_stats', 'nbiot_step_host', 'nbiot_stat_ptrs', 'nbiot_trace_ptrs', 'nbiot_trace_counts', 'nbiot_stat_counts', 'nbiot_stat_histogram', 'nbiot_set_event_log', 'nbiot_launch_count', 'nbiot_launch_geometry', 'nbiot_kernel_name', 'nbiot_instance_times',
+           'nbiot_reduce_stats', 'nbiot_step_host', 'nbiot_stat_ptrs', 'nbiot_trace_ptrs', 'nbiot_spill_ptr', 'nbiot_trace_counts', 'nbiot_stat_counts', 'nbiot_stat_histogram', 'nbiot_set_event_log', 'nbiot_launch_count', 'nbiot_launch_geometry', 'nbiot_kernel_name', 'nbiot_instance_times',
            'nbiot_rng_u01', 'nbiot_rng_pair', 'nbiot_rng_normal', 'nbiot_rng_bounded',
            # include/nbiot_agent.h
            'nbiot_mb_agent_create', 'nbiot_mb_agent_destroy', 'nbiot_mb_agent_act', 'nbiot_mb_agent_faults']
@@ -75,6 +75,7 @@ def load():
     L.nbiot_stat_counts.argtypes = [vp, vp, vp]
     L.nbiot_trace_ptrs.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i32)]
     L.nbiot_trace_counts.argtypes = [vp, vp, vp]
+    L.nbiot_spill_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.nbiot_stat_histogram.argtypes = [vp, i32, i32, i32, vp, vp]
     L.nbiot_gather_obs.argtypes = [vp, ctypes.POINTER(ObsItem), i32, vp, vp, vp]
     L.nbiot_reduce_stats.argtypes = [vp, vp, vp]

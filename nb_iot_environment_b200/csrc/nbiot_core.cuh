@@ -48,6 +48,7 @@ struct __attribute__((aligned(16))) NbCtx {
     int32_t *delays, *service;
     uint16_t *scratch;
     nbiot_record_t *rec;
+    int32_t *spill;           /* [6][NBIOT_STEP_SPILL]: entries 16.. of the per-epoch info lists (rx id / delay, errors, unfit, access id / delay) */
     const uint16_t *lut2;
     const uint8_t *mcs;
     nbiot_conf_hot_t conf;    /* by value: one shared-memory load per use instead of a pointer chase into HBM */
@@ -124,6 +125,13 @@ NB_FN void nbc_trace(NbCtx &c, int type, int ce, int t, int a, int b)
     c.occ->trace_n += 1;
 }
 #define NB_TRACE(c, type, ce, t, a, b) do { if (((const NbCtaConst *)(c).ctrl)->cold.trace_mask & (type)) nbc_trace(c, type, ce, t, a, b); } while (0)
+
+/* entry k >= NBIOT_STEP_LIST of a per-epoch info list (0 rx id, 1 rx delay, 2 errors, 3 unfit, 4 access id, 5 access delay): the header
+ * and the record hold the first 16, the rest goes to the side buffer in HBM (rare: only loaded cells between two scheduling decisions) */
+NB_FN void nbc_step_spill(NbCtx &c, int list, int k, int v)
+{
+    if (k - NBIOT_STEP_LIST < NBIOT_STEP_SPILL) c.spill[list * NBIOT_STEP_SPILL + (k - NBIOT_STEP_LIST)] = v;
+}
 
 /* ------------------------------------------------------------------ scalar draws */
 NB_DEV double nbc_u01(NbCtx &c) { return nb_rng_u01(nbc_hdr(c)->seed, nbc_hdr(c)->draws++, NBIOT_STREAM_ENV); }
@@ -1310,6 +1318,7 @@ NB_FN1 void nbc_msg3_event(NbCtx &c, int slot, int t)
         nbc_conn_insert(c, slot);
         u->timestamp = t;                                      /* perf.register_ue (perf_monitor.py:224-229) */
         if (h->n_acc < NBIOT_STEP_LIST) { h->acc_id[h->n_acc] = u->id; h->acc_delay[h->n_acc] = t - u->t_arrival; }
+        else { nbc_step_spill(c, 4, h->n_acc, u->id); nbc_step_spill(c, 5, h->n_acc, t - u->t_arrival); }
         h->n_acc += 1;
         h->RAR_ids[uce] += 1; h->RAR_detected[uce] += 1;
         double sample = NB_MUL(-1.0, u->loss);
@@ -1354,6 +1363,7 @@ NB_FN1 void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
         u->acked_data += u->bits; u->retx_buffer = 0; u->bits = 0; u->new_data = 1;
         int d = t - u->timestamp;
         if (h->n_rx < NBIOT_STEP_LIST) { h->rx_id[h->n_rx] = u->id; h->rx_delay[h->n_rx] = d; }
+        else { nbc_step_spill(c, 0, h->n_rx, u->id); nbc_step_spill(c, 1, h->n_rx, d); }
         h->n_rx += 1;
         h->rx_sum = NB_ADD(h->rx_sum, (double)d);
         if (c.conf.reward_criteria == NB_RW_INVD_USERS) h->rx_inv_sum = NB_ADD(h->rx_inv_sum, NB_DIV(1.0, NB_DIV((double)d, 1000.0)));
@@ -1380,7 +1390,7 @@ NB_FN1 void nbc_NPUSCH_end(NbCtx &c, int slot, int t)
         } else nbc_conn_insert(c, slot);
     } else {
         u->new_data = 0; u->retx_buffer = u->bits;
-        if (h->n_err < NBIOT_STEP_LIST) h->err_id[h->n_err] = u->id;
+        if (h->n_err < NBIOT_STEP_LIST) h->err_id[h->n_err] = u->id; else nbc_step_spill(c, 2, h->n_err, u->id);
         h->n_err += 1; h->error_count += 1; h->attempts_count += 1;
         nbc_conn_insert(c, slot);
     }
@@ -1553,7 +1563,7 @@ NB_FN1 void nbc_step_data(NbCtx &c, const uint8_t *a)            /* node_b.py:58
         h->NPUSCH_resources += (int64_t)N_sc * n_sf;
         NB_TRACE(c, NBIOT_TR_RES_NPUSCH, CE_level, h->time, N_sc * n_sf, 0);
     } else if (new_data) {
-        if (h->n_unfit < NBIOT_STEP_LIST) h->unfit_id[h->n_unfit] = u->id;
+        if (h->n_unfit < NBIOT_STEP_LIST) h->unfit_id[h->n_unfit] = u->id; else nbc_step_spill(c, 3, h->n_unfit, u->id);
         h->n_unfit += 1;
     }
     nbc_schedule_NPDCCH(c, NPDCCH_sf);
@@ -1750,7 +1760,8 @@ NB_FN1 void nbc_write_record(NbCtx &c, double reward, double occ_nprach, double 
             if (!u->new_data) { double v = u->sinr; if (!(v > -40.0)) v = -40.0; if (!(v < 30.0)) v = 30.0; r->sinr[i] = NB_ADD(v, 40.0); }
         }
         r->n_rx = h->n_rx; r->n_err = h->n_err; r->n_unfit = h->n_unfit; r->n_acc = h->n_acc;
-        if (h->n_rx > NBIOT_STEP_LIST || h->n_err > NBIOT_STEP_LIST || h->n_unfit > NBIOT_STEP_LIST || h->n_acc > NBIOT_STEP_LIST)
+        const int lim = NBIOT_STEP_LIST + NBIOT_STEP_SPILL;                 /* 16 in the record, 48 more in the side buffer */
+        if (h->n_rx > lim || h->n_err > lim || h->n_unfit > lim || h->n_acc > lim)
             NB_FAULT(c, NBIOT_FAULT_LIST_TRUNC);
         nbw_run([&]() -> int {                                  /* one list position per lane */
             NB_NOUNROLL

@@ -476,6 +476,15 @@ int nbiot_stat_ptrs(nbiot_handle_t *h, void **stat_dev, int *stat_cap)
     return 0;
 }
 
+int nbiot_spill_ptr(nbiot_handle_t *h, void **spill_dev, int *list_cap, int *spill_cap)
+{
+    if (!h) return set_err(NBIOT_E_INVALID, "nbiot_spill_ptr: null handle");
+    if (spill_dev) *spill_dev = h->state + h->L.off_spill;
+    if (list_cap) *list_cap = NBIOT_STEP_LIST;
+    if (spill_cap) *spill_cap = NBIOT_STEP_SPILL;
+    return 0;
+}
+
 int nbiot_trace_ptrs(nbiot_handle_t *h, void **trace_dev, int *trace_cap)
 {
     if (!h) return set_err(NBIOT_E_INVALID, "nbiot_trace_ptrs: null handle");

@@ -227,7 +227,7 @@ static inline NbCtrlDev nb_make_ctrl_dev(const nbiot_ctrl_t *c)
 typedef struct {
     int32_t n_inst, ue_cap, grid_w, hist_cap, n_carriers, ra_cap, stat_cap, trace_cap;
     uint64_t off_hdr, off_grid, off_ra, off_conn, off_cont, off_ue, off_free, off_occ;
-    uint64_t off_incoming, off_delays, off_service, off_rec, off_scratch, off_stat, off_trace, total;
+    uint64_t off_incoming, off_delays, off_service, off_rec, off_scratch, off_stat, off_trace, off_spill, total;
 } NbLayout;
 
 static inline uint64_t nb_align256(uint64_t x) { return (x + 255u) & ~(uint64_t)255u; }
@@ -265,6 +265,7 @@ static inline NbLayout nb_make_layout(const nbiot_conf_t *c, int n)
     L.off_scratch = o;  o = nb_align256(o + N * (uint64_t)L.ra_cap * 2u);
     L.off_stat = o;     o = nb_align256(o + N * 4u * (uint64_t)L.stat_cap * 4u);
     L.off_trace = o;    o = nb_align256(o + N * (uint64_t)L.trace_cap * sizeof(nbiot_trace_rec_t));
+    L.off_spill = o;    o = nb_align256(o + N * 6u * (uint64_t)NBIOT_STEP_SPILL * 4u);
     L.total = o;
     return L;
 }

@@ -65,6 +65,7 @@ class LazyInfos:
         self._env = env
         self._records = None
         self._hist = None
+        self._spill = None
         self._epoch = env._epoch          # the step this view belongs to: the records live in the state buffer and move on with it
 
     def _check_fresh(self):
@@ -88,15 +89,24 @@ class LazyInfos:
     def __len__(self):
         return self._env.num_envs
 
+    def _spills(self):
+        if self._spill is None:
+            self._check_fresh()
+            self._spill = self._env.step_list_spill()
+        return self._spill
+
     def __getitem__(self, i):
         rec = self.records[i]
         hist = None
+        spill = None
+        if max(int(rec['n_rx']), int(rec['n_err']), int(rec['n_unfit']), int(rec['n_acc'])) > 16:
+            spill = self._spills()[i]              # a per-epoch list longer than the record's 16 entries: the rest is in the side buffer
         if rec['state'] == STATE_IDS['NPRACH_update']:
             inc, dl, sv = self._hists()
             cap = inc.shape[1]
             ni, nd = min(int(rec['n_incoming']), cap), min(int(rec['departures']), cap)
             hist = (inc[i, :ni].tolist(), dl[i, :nd].tolist(), sv[i, :nd].tolist())
-        return record_to_info(rec, hist)
+        return record_to_info(rec, hist, spill)
 
     def field(self, name):
         return self.records[name]
@@ -152,6 +162,9 @@ class BatchedNBIoTEnv:
         _cabi.check(self.L.nbiot_stat_ptrs(self._h, ctypes.byref(stp), ctypes.byref(scap)))
         self.stat_cap = scap.value
         self._stat_off = (stp.value - base) if stp.value else None
+        spp, lcap, scap2 = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int()
+        _cabi.check(self.L.nbiot_spill_ptr(self._h, ctypes.byref(spp), ctypes.byref(lcap), ctypes.byref(scap2)))
+        self._spill_off, self._spill_cap = spp.value - base, scap2.value
         trp, tcap = ctypes.c_void_p(), ctypes.c_int()
         _cabi.check(self.L.nbiot_trace_ptrs(self._h, ctypes.byref(trp), ctypes.byref(tcap)))
         self.trace_cap = tcap.value
@@ -395,6 +408,11 @@ class BatchedNBIoTEnv:
         with torch.cuda.device(self.device):
             _cabi.check(self.L.nbiot_stat_histogram(self._h, idx, int(bin_width), int(n_bins), out.data_ptr(), self._stream()))
         return out
+
+    def step_list_spill(self):
+        """int32[N, 6, 48] (host): entries 16.. of the per-epoch info lists (rx id / delay, errors, unfit, access id / delay) of every cell"""
+        N, cap = self.num_envs, self._spill_cap
+        return self.state[self._spill_off:self._spill_off + N * 6 * cap * 4].cpu().numpy().view(np.int32).reshape(N, 6, cap)
 
     def period_lists(self):
         """(incoming float64[N, cap], delays int32[N, cap], service_times int32[N, cap]) of the update period

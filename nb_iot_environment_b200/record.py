@@ -176,7 +176,10 @@ def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_c
     return c
 
 
-def record_to_info(rec, hist=None):
+STEP_SPILL = 48
+
+
+def record_to_info(rec, hist=None, spill=None):
     """One record -> the reference's `info` dict (same keys and value types as node_b.py:299-408)."""
     state = STATE_NAMES[int(rec['state'])]
     info = {'time': int(rec['time']), 'state': state, 'total_ues': int(rec['total_ues']),
@@ -188,12 +191,17 @@ def record_to_info(rec, hist=None):
         info['loss'] = [float(v) for v in rec['loss']]
         info['sinr'] = [float(v) for v in rec['sinr']]
         info['buffer'] = [int(v) if i < n else 0.0 for i, v in enumerate(rec['buffer'])]
-        k = min(int(rec['n_rx']), STEP_LIST)
-        info['receptions'] = {int(a): int(b) for a, b in zip(rec['rx_id'][:k], rec['rx_delay'][:k])}
-        info['errors'] = [int(v) for v in rec['err_id'][:min(int(rec['n_err']), STEP_LIST)]]
-        info['unfit'] = [int(v) for v in rec['unfit_id'][:min(int(rec['n_unfit']), STEP_LIST)]]
-        k = min(int(rec['n_acc']), STEP_LIST)
-        info['access'] = {int(a): int(b) for a, b in zip(rec['acc_id'][:k], rec['acc_delay'][:k])}
+        def full(field, count, row):
+            """the record's 16 entries, then the side buffer's (spill: int32[6][STEP_SPILL] of this cell) when the list is longer"""
+            n_ = int(rec[count])
+            v = [int(x) for x in rec[field][:min(n_, STEP_LIST)]]
+            if n_ > STEP_LIST and spill is not None:
+                v += [int(x) for x in spill[row][:min(n_ - STEP_LIST, STEP_SPILL)]]
+            return v
+        info['receptions'] = dict(zip(full('rx_id', 'n_rx', 0), full('rx_delay', 'n_rx', 1)))
+        info['errors'] = full('err_id', 'n_err', 2)
+        info['unfit'] = full('unfit_id', 'n_unfit', 3)
+        info['access'] = dict(zip(full('acc_id', 'n_acc', 4), full('acc_delay', 'n_acc', 5)))
     elif state == 'RAR_window':
         for key in ('ues_per_CE', 'RAR_in', 'RAR_sent', 'RAR_ids', 'RAR_detected', 'RAR_failed'):
             info[key] = [int(v) for v in rec[key]]

@@ -1121,7 +1121,8 @@ static void advance_fel(Oracle *o)                                    /* node_b.
 static void fill_list(int32_t *dst, const ivec *src, Oracle *o)
 {
     int n = src->n;
-    if (n > NBIOT_STEP_LIST) { n = NBIOT_STEP_LIST; o->fault |= NBIOT_FAULT_LIST_TRUNC; }
+    if (n > NBIOT_STEP_LIST + NBIOT_STEP_SPILL) o->fault |= NBIOT_FAULT_LIST_TRUNC;      /* the CUDA path keeps 16 + 48 entries */
+    if (n > NBIOT_STEP_LIST) n = NBIOT_STEP_LIST;
     for (int i = 0; i < n; ++i) dst[i] = src->d[i];
 }
 
@@ -1327,6 +1328,15 @@ void orc_destroy(Oracle *o)
 int orc_get_stats(Oracle *o, int which, int32_t *out, int cap)
 {
     ivec *v = which == 0 ? &o->delay_history : which == 1 ? &o->connection_history : which == 2 ? &o->access_history : &o->bits_history;
+    for (int i = 0; i < v->n && i < cap; ++i) out[i] = v->d[i];
+    return v->n;
+}
+
+/* the per-epoch info lists in full (perf_monitor.py:92-103): which = 0 rx id, 1 rx delay, 2 errors, 3 unfit, 4 access id, 5 access delay;
+ * returns the true length, copies at most cap entries */
+int orc_get_step_list(Oracle *o, int which, int32_t *out, int cap)
+{
+    ivec *v = which == 0 ? &o->rx_id : which == 1 ? &o->rx_delay : which == 2 ? &o->err_id : which == 3 ? &o->unfit_id : which == 4 ? &o->acc_id : &o->acc_delay;
     for (int i = 0; i < v->n && i < cap; ++i) out[i] = v->d[i];
     return v->n;
 }

@@ -31,6 +31,8 @@ def lib():
         L.orc_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_get_stats.restype = ctypes.c_int
         L.orc_get_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.orc_get_step_list.restype = ctypes.c_int
+        L.orc_get_step_list.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.orc_get_samples.restype = ctypes.c_int
         L.orc_get_samples.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.orc_get_hist.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 2
@@ -116,6 +118,15 @@ class OracleCell:
             out[name] = buf[:n].copy()
         out['th'] = out['bits'].astype(np.float64) / out['delay'].astype(np.float64)      # acked_data / delay (perf_monitor.py:169)
         return out
+
+    def step_lists(self, cap=4096):
+        """the per-epoch info lists in full: (receptions dict, errors, unfit, access dict) as the reference's info holds them"""
+        out = []
+        buf = np.zeros(cap, dtype=np.int32)
+        for which in range(6):
+            n = self.L.orc_get_step_list(self.h, which, buf.ctypes.data, cap)
+            out.append(buf[:n].tolist())
+        return dict(zip(out[0], out[1])), out[2], out[3], dict(zip(out[4], out[5]))
 
     def samples(self, cap=1 << 18):
         """PerfMonitor's sample lists since reset, in append order (TRACE_DTYPE)"""

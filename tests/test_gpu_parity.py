@@ -601,3 +601,43 @@ def test_parity_beyond_4gib_two_carriers():
     bad = [int(i) for k, i in enumerate(idx) if record_diff(orecs[k], recs[i], rtol=0.0)]
     assert not bad, f'{len(bad)} of {len(idx)} sampled cells differ from the oracle, first: {bad[:5]}'
     env.close()
+
+
+def test_info_lists_longer_than_the_record():
+    """info['receptions'] / ['errors'] / ['access'] accumulate between two Scheduling decisions (perf_monitor.py:92-103, cleared at
+    node_b.py:589); in a loaded two-carrier cell that stays in RAR windows for a while they outgrow the record's 16 entries. The rest
+    lives in the side buffer: infos returns the complete lists, equal to the oracle's, and nothing is flagged as truncated."""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from oracle.oracle_py import OracleCell
+    CFG4 = {'M': 3000, 'ratio': 0.5, 'buffer_range': [100, 600], 'reward_criteria': 'throughput', 'random': True}
+    N, STEPS = 1024, 700
+    env = BatchedNBIoTEnv(CFG4, num_envs=N, n_carriers=2, all_states_external=True, ue_cap=3000, grid_w=2048, hist_cap=2048)
+    mx = torch.tensor([1, 3, 6, 7, 3, 3, 4, 11, 7, 7, 10, 15, 5, 7, 7, 5, 7, 7, 5, 7, 7, 14, 14], device='cuda') + 1
+    g = torch.Generator(device='cuda'); g.manual_seed(12)
+    env.reset()
+    acts, found = [], None
+    for s in range(STEPS):
+        a = (torch.rand((N, 23), device='cuda', generator=g) * mx).to(torch.uint8)
+        a[:, 5] = torch.where(a[:, 5] == 2, torch.full_like(a[:, 5], 3), a[:, 5])
+        rar = env.record_field('state') == 2
+        a[:, 1] = torch.where(rar, a[:, 1] % 3, a[:, 1]); a[:, 2] = torch.where(rar, a[:, 2] % 3, a[:, 2])
+        env.node_step(a)
+        acts.append(a.cpu().numpy())
+        if s > 300 and s % 20 == 0:
+            long_ = (env.record_field('n_rx') > 16) & (env.record_field('state') == 0)
+            if bool(long_.any()):
+                found = int(torch.nonzero(long_)[0])
+                break
+    assert found is not None, 'no cell accumulated more than 16 receptions: make the scenario heavier'
+    from nb_iot_environment_b200.env import LazyInfos
+    info = LazyInfos(env)[found]
+    assert len(info['receptions']) == int(env.records()[found]['n_rx']) > 16
+    cell = OracleCell(CFG4, found, n_carriers=2)
+    cell.reset()
+    for a in acts:
+        cell.step(a[found])
+    rx, err, unfit, acc = cell.step_lists()
+    assert info['receptions'] == rx and info['errors'] == err and info['unfit'] == unfit and info['access'] == acc
+    assert env.stats()['truncated'] == 0 and env.stats()['faulted'] == 0
+    env.close()
