@@ -112,7 +112,7 @@ int nbiot_trace_ptrs(nbiot_handle_t *h, void **trace_dev, int *trace_cap);
 /* the per-epoch info lists (info['receptions'], ['errors'], ['unfit'], ['access']; perf_monitor.py:92-103) beyond the list_cap = 16 entries
  * the record holds: spill_dev = int32[n_inst][6][spill_cap] inside the state buffer, rows = rx id, rx delay, error id, unfit id, access id,
  * access delay; entry k >= list_cap of a list at column k - list_cap (the record's n_* fields are the true lengths) */
-int nbiot_spill_ptr(nbiot_handle_t *h, void **spill_dev, int *list_cap, int *spill_cap);
+int nbiot_spill_ptr(nbiot_handle_t *h, void **spill_dev, int *list_cap, int *spill_cap);   /* spill_cap = max(NBIOT_STEP_SPILL, hist_cap) */
 int nbiot_trace_counts(nbiot_handle_t *h, int32_t *counts_dev, void *stream);
 /* conf.stat_cap > 0 (conf['statistics']): the per-departure histories of PerfMonitor (perf_monitor.py:61-84, :161-171; the arrays
  * experiments_RL.py:139-140 / experiments_MAMBRL.py:121-122 save) as rings in HBM.

@@ -18,8 +18,10 @@
 
 #define NBIOT_MAX_OCC 48    /* NPRACH occasions per CE per 3000-sf update period (<= 3000/80 + 1) */
 #define NBIOT_STEP_LIST 16  /* receptions / errors / unfit / access entries per scheduling epoch  */
-#define NBIOT_STEP_SPILL 48 /* further entries of each of those lists kept in a side buffer of the state (nbiot_spill_ptr): a list is only
-                               cut -- and NBIOT_FAULT_LIST_TRUNC raised -- beyond NBIOT_STEP_LIST + NBIOT_STEP_SPILL entries */
+#define NBIOT_STEP_SPILL 48 /* further entries of each of those lists kept in a side buffer of the state (nbiot_spill_ptr): at least this many,
+                               hist_cap when that is larger (info['access'] grows by one per connection for as long as a cell stays in
+                               RAR windows: hundreds of entries under RA congestion). A list is only cut -- and NBIOT_FAULT_LIST_TRUNC
+                               raised -- beyond NBIOT_STEP_LIST + that */
 
 /* per-instance fault bits: a faulted instance is frozen (time stops advancing) */
 #define NBIOT_FAULT_UE_SLOTS 0x1u     /* more live UEs than ue_cap                          */

@@ -48,7 +48,7 @@ struct __attribute__((aligned(16))) NbCtx {
     int32_t *delays, *service;
     uint16_t *scratch;
     nbiot_record_t *rec;
-    int32_t *spill;           /* [6][NBIOT_STEP_SPILL]: entries 16.. of the per-epoch info lists (rx id / delay, errors, unfit, access id / delay) */
+    int32_t *spill;           /* [6][spill cap]: entries 16.. of the per-epoch info lists (rx id / delay, errors, unfit, access id / delay) */
     const uint16_t *lut2;
     const uint8_t *mcs;
     nbiot_conf_hot_t conf;    /* by value: one shared-memory load per use instead of a pointer chase into HBM */
@@ -130,7 +130,8 @@ NB_FN void nbc_trace(NbCtx &c, int type, int ce, int t, int a, int b)
  * and the record hold the first 16, the rest goes to the side buffer in HBM (rare: only loaded cells between two scheduling decisions) */
 NB_FN void nbc_step_spill(NbCtx &c, int list, int k, int v)
 {
-    if (k - NBIOT_STEP_LIST < NBIOT_STEP_SPILL) c.spill[list * NBIOT_STEP_SPILL + (k - NBIOT_STEP_LIST)] = v;
+    const int cap = nb_spill_cap(c.hist_cap);
+    if (k - NBIOT_STEP_LIST < cap) c.spill[list * cap + (k - NBIOT_STEP_LIST)] = v;
 }
 
 /* ------------------------------------------------------------------ scalar draws */
@@ -1760,7 +1761,7 @@ NB_FN1 void nbc_write_record(NbCtx &c, double reward, double occ_nprach, double 
             if (!u->new_data) { double v = u->sinr; if (!(v > -40.0)) v = -40.0; if (!(v < 30.0)) v = 30.0; r->sinr[i] = NB_ADD(v, 40.0); }
         }
         r->n_rx = h->n_rx; r->n_err = h->n_err; r->n_unfit = h->n_unfit; r->n_acc = h->n_acc;
-        const int lim = NBIOT_STEP_LIST + NBIOT_STEP_SPILL;                 /* 16 in the record, 48 more in the side buffer */
+        const int lim = NBIOT_STEP_LIST + nb_spill_cap(c.hist_cap);         /* 16 in the record, the rest in the side buffer */
         if (h->n_rx > lim || h->n_err > lim || h->n_unfit > lim || h->n_acc > lim)
             NB_FAULT(c, NBIOT_FAULT_LIST_TRUNC);
         nbw_run([&]() -> int {                                  /* one list position per lane */

@@ -266,8 +266,10 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
      * lanes; one thread per cell shares every common instruction between 32 cells but needs the cells to fill the machine
      * (148 SMs x 16 warps x 32 lanes = 75 776) -- DESIGN.md section 6c has the measured crossover. */
     h->use_tpc = n_inst >= NB_TPC_MIN_CELLS ? 2 : 0;
-    if (getenv("NBIOT_TPC_BLK") && !atoi(getenv("NBIOT_TPC_BLK"))) h->blk_dev = nullptr;       /* measurement knob: plain column scans */
-    else CK(cudaMalloc(&h->blk_dev, sizeof(uint16_t) * (size_t)n_inst * L.n_carriers * (L.grid_w >> 5)));
+    /* block summaries of the look-ahead ring for the thread-per-cell kernel (nbiot_core.cuh): 8 % fewer executed instructions and 3-4 %
+     * SLOWER on the sweep configuration (the kernel waits on memory, and the summaries are one more scattered region per cell):
+     * off unless NBIOT_TPC_BLK=1 (profiles/r02_tpc_variants.txt) */
+    if (getenv("NBIOT_TPC_BLK") && atoi(getenv("NBIOT_TPC_BLK"))) CK(cudaMalloc(&h->blk_dev, sizeof(uint16_t) * (size_t)n_inst * L.n_carriers * (L.grid_w >> 5)));
     if (const char *e = getenv("NBIOT_KERNEL")) {
         if (!strcmp(e, "tpc")) { h->use_tpc = 1; h->tpc_forced = 1; }
         else if (!strcmp(e, "tpcv")) { h->use_tpc = 2; h->tpc_forced = 1; }
@@ -481,7 +483,7 @@ int nbiot_spill_ptr(nbiot_handle_t *h, void **spill_dev, int *list_cap, int *spi
     if (!h) return set_err(NBIOT_E_INVALID, "nbiot_spill_ptr: null handle");
     if (spill_dev) *spill_dev = h->state + h->L.off_spill;
     if (list_cap) *list_cap = NBIOT_STEP_LIST;
-    if (spill_cap) *spill_cap = NBIOT_STEP_SPILL;
+    if (spill_cap) *spill_cap = nb_spill_cap(h->L.hist_cap);
     return 0;
 }
 

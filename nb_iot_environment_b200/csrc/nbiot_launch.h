@@ -57,7 +57,7 @@ __device__ __forceinline__ void nb_fill_ctx(NbCtx &c, const NbKernelArgs &A, int
     c.service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
     c.scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
     c.rec = (nbiot_record_t *)(s + L.off_rec) + i;
-    c.spill = (int32_t *)(s + L.off_spill) + (size_t)i * 6u * NBIOT_STEP_SPILL;
+    c.spill = (int32_t *)(s + L.off_spill) + (size_t)i * 6u * nb_spill_cap(L.hist_cap);
     c.evlog = i == 0 ? A.evlog : nullptr;
 #if NB_LANES == 1
     c.blk = A.blk ? A.blk + (size_t)i * A.L.n_carriers * (A.L.grid_w >> 5) : nullptr;

@@ -231,6 +231,7 @@ typedef struct {
 } NbLayout;
 
 static inline uint64_t nb_align256(uint64_t x) { return (x + 255u) & ~(uint64_t)255u; }
+#define nb_spill_cap(hist_cap) ((hist_cap) > NBIOT_STEP_SPILL ? (hist_cap) : NBIOT_STEP_SPILL)   /* entries per spilled info list (host and device) */
 
 static inline NbColdConf nb_make_cold(const nbiot_conf_t *c, uint8_t *state, uint64_t off_occ, uint64_t off_stat, uint64_t off_trace)
 {
@@ -265,7 +266,7 @@ static inline NbLayout nb_make_layout(const nbiot_conf_t *c, int n)
     L.off_scratch = o;  o = nb_align256(o + N * (uint64_t)L.ra_cap * 2u);
     L.off_stat = o;     o = nb_align256(o + N * 4u * (uint64_t)L.stat_cap * 4u);
     L.off_trace = o;    o = nb_align256(o + N * (uint64_t)L.trace_cap * sizeof(nbiot_trace_rec_t));
-    L.off_spill = o;    o = nb_align256(o + N * 6u * (uint64_t)NBIOT_STEP_SPILL * 4u);
+    L.off_spill = o;    o = nb_align256(o + N * 6u * (uint64_t)nb_spill_cap(L.hist_cap) * 4u);
     L.total = o;
     return L;
 }

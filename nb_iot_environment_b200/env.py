@@ -410,7 +410,7 @@ class BatchedNBIoTEnv:
         return out
 
     def step_list_spill(self):
-        """int32[N, 6, 48] (host): entries 16.. of the per-epoch info lists (rx id / delay, errors, unfit, access id / delay) of every cell"""
+        """int32[N, 6, max(48, hist_cap)] (host): entries 16.. of the per-epoch info lists (rx id / delay, errors, unfit, access id / delay) of every cell"""
         N, cap = self.num_envs, self._spill_cap
         return self.state[self._spill_off:self._spill_off + N * 6 * cap * 4].cpu().numpy().view(np.int32).reshape(N, 6, cap)
 

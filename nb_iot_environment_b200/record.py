@@ -176,7 +176,6 @@ def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_c
     return c
 
 
-STEP_SPILL = 48
 
 
 def record_to_info(rec, hist=None, spill=None):
@@ -192,11 +191,11 @@ def record_to_info(rec, hist=None, spill=None):
         info['sinr'] = [float(v) for v in rec['sinr']]
         info['buffer'] = [int(v) if i < n else 0.0 for i, v in enumerate(rec['buffer'])]
         def full(field, count, row):
-            """the record's 16 entries, then the side buffer's (spill: int32[6][STEP_SPILL] of this cell) when the list is longer"""
+            """the record's 16 entries, then the side buffer's (spill: int32[6][spill cap] of this cell) when the list is longer"""
             n_ = int(rec[count])
             v = [int(x) for x in rec[field][:min(n_, STEP_LIST)]]
             if n_ > STEP_LIST and spill is not None:
-                v += [int(x) for x in spill[row][:min(n_ - STEP_LIST, STEP_SPILL)]]
+                v += [int(x) for x in spill[row][:n_ - STEP_LIST]]
             return v
         info['receptions'] = dict(zip(full('rx_id', 'n_rx', 0), full('rx_delay', 'n_rx', 1)))
         info['errors'] = full('err_id', 'n_err', 2)

@@ -1121,7 +1121,8 @@ static void advance_fel(Oracle *o)                                    /* node_b.
 static void fill_list(int32_t *dst, const ivec *src, Oracle *o)
 {
     int n = src->n;
-    if (n > NBIOT_STEP_LIST + NBIOT_STEP_SPILL) o->fault |= NBIOT_FAULT_LIST_TRUNC;      /* the CUDA path keeps 16 + 48 entries */
+    int spill = o->conf.hist_cap > NBIOT_STEP_SPILL ? o->conf.hist_cap : NBIOT_STEP_SPILL;
+    if (n > NBIOT_STEP_LIST + spill) o->fault |= NBIOT_FAULT_LIST_TRUNC;      /* the CUDA path keeps 16 + max(48, hist_cap) entries */
     if (n > NBIOT_STEP_LIST) n = NBIOT_STEP_LIST;
     for (int i = 0; i < n; ++i) dst[i] = src->d[i];
 }

@@ -38,7 +38,7 @@ struct Staged {
         c->service = (int32_t *)(s + L.off_service) + (size_t)i * L.hist_cap;
         c->scratch = (uint16_t *)(s + L.off_scratch) + (size_t)i * L.ra_cap;
         c->rec = (nbiot_record_t *)(s + L.off_rec) + i;
-        c->spill = (int32_t *)(s + L.off_spill) + (size_t)i * 6u * NBIOT_STEP_SPILL;
+        c->spill = (int32_t *)(s + L.off_spill) + (size_t)i * 6u * nb_spill_cap(L.hist_cap);
         c->lut2 = e->lut2; c->mcs = e->mcs; memcpy(&c->conf, &e->conf, sizeof(nbiot_conf_hot_t)); c->ctrl = &e->cc.ctrl;
         c->W = L.grid_w; c->ue_cap = L.ue_cap; c->ra_cap = L.ra_cap; c->hist_cap = L.hist_cap; c->C = L.n_carriers;
         c->evlog = (e->evlog && i == 0) ? e->evlog : NULL; c->evlog_cap = e->evlog_cap;
