@@ -47,6 +47,10 @@ typedef struct nbiot_conf {
                                  (PerfMonitor.nprach_sample / rar_sample, perf_monitor.py:61-69, :111-140), conf['statistics'] the
                                  RAR-window samples, the three resource histories and the departures
                                  (rar_window_sample, register_*_resources, npusch_delivered; :71-79, :125-129, :161-202)  */
+    int32_t capture_effect;   /* Channel(capture_effect=True) (channel.py:124-126, :158-159, :200-219): a preamble chosen by several UEs
+                                 can still be detected (states CAPTURE / COLLIDED), msg3 grants then carry several contenders.
+                                 Not reachable through create_system (system_creator.py:51); a constructor argument here.     */
+    int32_t pad_conf;
 } nbiot_conf_t;
 
 /* one sample of the ring (16 bytes), in the order the reference appends to its lists */

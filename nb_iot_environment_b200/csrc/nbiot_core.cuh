@@ -896,6 +896,154 @@ NB_FN1 void nbc_new_arrivals(NbCtx &c, int t)
     }
 }
 
+#ifndef NB_NO_CAPTURE
+/* ------------------------------------------------------------------ capture effect (Channel(capture_effect=True); generic builds only)
+ * Plain scalar code, out of line and off the hot path: every lane of a warp-per-cell build walks it with the same values. */
+/* Channel.sinr_estimation (channel.py:178-198) over the UEs in slots[0..n): one shadow-fading draw each, the strongest signal against
+ * noise + the others; returns the SINR in dB and the index of the strongest */
+NB_FN double nbc_sinr_estimation(NbCtx &c, const uint16_t *slots, int n, int *max_i)
+{
+    double sum = 0.0, max_rx = -1.0;                           /* powers are positive */
+    *max_i = 0;
+    NB_NOUNROLL
+    for (int i = 0; i < n; ++i) {
+        double LogF = nbc_normal(c, 0.0, NB_SIGMA_F);
+        double rx_pw = nb_exp10(NB_DIV(NB_SUB(NB_SUB(NB_TX_PW, c.ue[slots[i]].loss), LogF), 10.0));
+        sum = NB_ADD(sum, rx_pw);
+        if (rx_pw > max_rx) { max_rx = rx_pw; *max_i = i; }
+    }
+    double ni = NB_SUB(NB_ADD(NB_NOISE_MW, sum), max_rx);
+    return NB_MUL(10.0, nb_log10(NB_DIV(max_rx, ni)));
+}
+
+/* the detection pass of AccessProcedure.NPRACH_start (access_procedure.py:76-91) with Channel.preamble_detection /
+ * multiple_preamble_detection (channel.py:156-176, :200-219): preamble groups in first-occurrence order; a shared preamble is detected
+ * when its strongest signal is (state CAPTURE for all its UEs, else COLLIDED). c.scratch[r] = list position of contender r, its
+ * preamble in the entry's wake_t. */
+NB_FN void nbc_nprach_detect_capture(NbCtx &c, int ce, int n_ues, int rep)
+{
+    NbHdr *h = nbc_hdr(c);
+    NbRaEntry *L = c.ra[ce];
+    const double x0 = nb_nprach_x0[rep], kk = nb_nprach_k[rep];
+    uint32_t seen[8] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u };
+    int detected = 0, signals = 0;
+    NB_NOUNROLL
+    for (int r = 0; r < n_ues; ++r) {
+        const int pre = (int)L[c.scratch[r]].wake_t;
+        const uint32_t bit = 1u << (pre & 31);
+        if (seen[(pre >> 5) & 7] & bit) continue;
+        seen[(pre >> 5) & 7] |= bit;
+        if (!((h->pre_twice[(pre >> 5) & 7] >> (pre & 31)) & 1u)) {                    /* alone on its preamble */
+            NbRaEntry *e = &L[c.scratch[r]];
+            double LogF = nbc_normal(c, 0.0, NB_SIGMA_F);
+            double SINR = NB_SUB(NB_SUB(NB_SUB(NB_SUB(NB_TX_PW, c.ue[e->slot].loss), LogF), NB_NOISE_DBM), NB_NOISE_FIG);
+            double p = NB_DIV(1.0, NB_ADD(1.0, nb_exp(NB_MUL(-kk, NB_SUB(SINR, x0)))));
+            int det = nbc_bernoulli(c, p);
+            if (det) e->st_ce = (uint8_t)((e->st_ce & 0xF0u) | NB_UE_RAR);
+            detected += det; signals += det;
+            continue;
+        }
+        /* several UEs on this preamble: one draw each in list order, then one detection draw for the strongest */
+        double sum = 0.0, max_rx = -1.0;
+        NB_NOUNROLL
+        for (int q = r; q < n_ues; ++q) {
+            const NbRaEntry *e = &L[c.scratch[q]];
+            if ((int)e->wake_t != pre) continue;
+            double LogF = nbc_normal(c, 0.0, NB_SIGMA_F);
+            double rx_pw = nb_exp10(NB_DIV(NB_SUB(NB_SUB(NB_TX_PW, c.ue[e->slot].loss), LogF), 10.0));
+            sum = NB_ADD(sum, rx_pw);
+            if (rx_pw > max_rx) max_rx = rx_pw;
+        }
+        double SINR = NB_MUL(10.0, nb_log10(NB_DIV(max_rx, NB_SUB(NB_ADD(NB_NOISE_MW, sum), max_rx))));
+        double p = NB_DIV(1.0, NB_ADD(1.0, nb_exp(NB_MUL(-kk, NB_SUB(SINR, x0)))));
+        int det = nbc_bernoulli(c, p);
+        NB_NOUNROLL
+        for (int q = r; q < n_ues; ++q) {
+            NbRaEntry *e = &L[c.scratch[q]];
+            if ((int)e->wake_t == pre) e->st_ce = (uint8_t)((e->st_ce & 0xF0u) | (det ? NB_UE_CAPTURE : NB_UE_COLLIDED));
+        }
+        detected += det; signals += 1;
+    }
+    int collided = signals - detected;
+    h->detected_pre[ce] = detected;
+    h->collided_pre[ce] = collided;
+    if (h->occ_n[ce] < NBIOT_MAX_OCC) { c.occ->det[ce][h->occ_n[ce]] = (int16_t)detected; c.occ->col[ce][h->occ_n[ce]] = (int16_t)collided; }
+    else NB_FAULT(c, NBIOT_FAULT_LIST_TRUNC);
+    h->occ_n[ce] += 1; h->det_sum[ce] += detected; h->col_sum[ce] += collided;
+}
+
+/* Population.msg3_grant (population.py:201-256) in full: the first UE of the list in RAR or CAPTURE state; when it was captured,
+ * every later RAR / CAPTURE UE of the list on the same preamble answers the grant too (one Msg3 event, one MAC timer for all) */
+NB_FN void nbc_msg3_grant_capture(NbCtx &c, int ce, int t, int t_msg3_end, int I_tbs, int N_rep)
+{
+    NbHdr *h = nbc_hdr(c);
+    NbRaEntry *L = c.ra[ce];
+    const int n = h->ra_n[ce];
+    int first = -1, preamble = -1, members = 0, alone = 0;
+    const uint32_t seq_msg3 = h->seq, seq_timer = h->seq + 1u;
+    const int t_exp = t + h->MAC_timer > t_msg3_end + 1 ? t + h->MAC_timer : t_msg3_end + 1;
+    NB_NOUNROLL
+    for (int i = 0; i < n && !alone; ++i) {
+        NbRaEntry e = L[i];
+        if (e.st_ce == NB_RA_TOMB) continue;
+        const uint32_t st = NB_STATE(e);
+        if (st != NB_UE_RAR && st != NB_UE_CAPTURE) continue;
+        if (first < 0) { first = i; preamble = (int)e.wake_t; alone = st == NB_UE_RAR; }
+        else if ((int)e.wake_t != preamble) continue;
+        L[i].st_ce = NB_RA_TOMB;
+        NbUe *u = &c.ue[e.slot];
+        u->state = (uint8_t)(st == NB_UE_RAR && members == 0 ? NB_UE_CONREQ : st);    /* only an uncollided first UE becomes CONREQ (:232-234) */
+        u->I_tbs = (uint8_t)I_tbs; u->N_rep = (uint8_t)N_rep; u->rar_w_id = e.rar_w_id;
+        u->attempts = e.attempts; u->CE_level = (uint8_t)NB_CE(e); u->where = NB_IN_CONTENTION;
+        if (members == 0) nbc_pool_push(c, NB_KEY(t_msg3_end, seq_msg3), NB_EV_MSG3, ce, e.slot);
+        if (h->cont_n >= c.ue_cap) { NB_FAULT(c, NBIOT_FAULT_UE_SLOTS); return; }
+        NbContEntry ce_; ce_.key = NB_KEY(t_exp, seq_timer); ce_.ue_id = u->id; ce_.slot = e.slot; ce_.ord = (uint16_t)members;
+        c.cont[h->cont_n] = ce_;
+        if (h->mac_valid && ce_.key < h->next_mac) { h->next_mac = ce_.key; h->next_mac_idx = h->cont_n; }
+        h->cont_n += 1;
+        members += 1;
+    }
+    if (members) h->seq += 2;
+}
+
+/* the contention list of the Msg3 event whose first UE sits in `slot`, in grant order: the entries of the contention set that share its
+ * MAC-timer key. Returns their number (written to c.scratch as UE slots). */
+NB_FN int nbc_msg3_contenders(NbCtx &c, int slot)
+{
+    NbHdr *h = nbc_hdr(c);
+    uint64_t key = NB_KEY_NONE;
+    NB_NOUNROLL
+    for (int i = 0; i < h->cont_n; ++i) if (c.cont[i].slot == (uint16_t)slot) { key = c.cont[i].key; break; }
+    int n = 0;
+    NB_NOUNROLL
+    for (int i = 0; i < h->cont_n; ++i) if (c.cont[i].key == key) n += 1;
+    NB_NOUNROLL
+    for (int i = 0; i < h->cont_n; ++i) if (c.cont[i].key == key) c.scratch[c.cont[i].ord] = c.cont[i].slot;
+    return n;
+}
+
+/* Population.MAC_timeout (population.py:151-163) for a timer that covers several UEs: those still in contention time out in the
+ * order of the grant's list */
+NB_FN void nbc_MAC_timeout_group(NbCtx &c, uint64_t key)
+{
+    NbHdr *h = nbc_hdr(c);
+    for (;;) {
+        int best = -1;
+        NB_NOUNROLL
+        for (int i = 0; i < h->cont_n; ++i) if (c.cont[i].key == key && (best < 0 || c.cont[i].ord < c.cont[best].ord)) best = i;
+        if (best < 0) break;
+        NbContEntry e = c.cont[best];
+        h->cont_n -= 1;
+        if (best != h->cont_n) c.cont[best] = c.cont[h->cont_n];
+        NbUe *u = &c.ue[e.slot];
+        u->state = NB_UE_RAO; u->where = NB_IN_RA;
+        nbc_ra_append(c, u->CE_level, e.slot, NB_UE_RAO, u->CE_level, u->attempts, u->rar_w_id);
+        if (NB_FATAL(c)) break;
+    }
+    h->mac_valid = 0;
+}
+#endif /* NB_NO_CAPTURE */
+
 /* ------------------------------------------------------------------ NPRACH pass */
 /* AccessProcedure.NPRACH_start (access_procedure.py:37-91), Population.NPRACH_start (population.py:168-188),
  * Channel.preamble_detection (channel.py:156-176) */
@@ -972,6 +1120,13 @@ NB_FN1 void nbc_NPRACH_start(NbCtx &c, int ce, NbOccasion occ)
         return 0;
     });
     ctr += (uint64_t)n_ues;
+#ifndef NB_NO_CAPTURE
+    if (nbc_cold(c)->capture_effect) {                         /* every preamble group in first-occurrence order, the shared ones included */
+        h->draws = ctr;
+        nbc_nprach_detect_capture(c, ce, n_ues, rep);
+        return;
+    }
+#endif
     /* pass 3: singleton preambles are detected with a sigmoid(SINR) Bernoulli draw, in list order;
      * a preamble chosen twice or more is a certain failure and consumes no draw */
     double x0 = nb_nprach_x0[rep], kk = nb_nprach_k[rep];
@@ -1071,6 +1226,9 @@ NB_DEV void nbc_cont_remove(NbCtx &c, int idx)
 NB_FN1S void nbc_msg3_grant(NbCtx &c, int ce, int t, int t_msg3_end, int I_tbs, int N_rep)
 {
     NbHdr *h = nbc_hdr(c);
+#ifndef NB_NO_CAPTURE
+    if (nbc_cold(c)->capture_effect) { nbc_msg3_grant_capture(c, ce, t, t_msg3_end, I_tbs, N_rep); return; }
+#endif
     NbRaEntry *L = c.ra[ce];
     int n = h->ra_n[ce];
     int idx = nbw_run([&]() -> int {
@@ -1092,7 +1250,7 @@ NB_FN1S void nbc_msg3_grant(NbCtx &c, int ce, int t, int t_msg3_end, int I_tbs, 
     nbc_pool_push(c, NB_KEY(t_msg3_end, h->seq), NB_EV_MSG3, ce, e.slot);
     h->seq += 1;
     int t_exp = t + h->MAC_timer > t_msg3_end + 1 ? t + h->MAC_timer : t_msg3_end + 1;
-    NbContEntry ce_; ce_.key = NB_KEY(t_exp, h->seq); ce_.ue_id = u->id; ce_.slot = e.slot; ce_.pad = 0;
+    NbContEntry ce_; ce_.key = NB_KEY(t_exp, h->seq); ce_.ue_id = u->id; ce_.slot = e.slot; ce_.ord = 0;
     h->seq += 1;
     c.cont[h->cont_n] = ce_;
     if (h->mac_valid && ce_.key < h->next_mac) { h->next_mac = ce_.key; h->next_mac_idx = h->cont_n; }
@@ -1102,6 +1260,9 @@ NB_FN1S void nbc_msg3_grant(NbCtx &c, int ce, int t, int t_msg3_end, int I_tbs, 
 /* Population.MAC_timeout (population.py:151-163) */
 NB_FN1S void nbc_MAC_timeout(NbCtx &c, int idx)
 {
+#ifndef NB_NO_CAPTURE
+    if (nbc_cold(c)->capture_effect) { nbc_MAC_timeout_group(c, c.cont[idx].key); return; }
+#endif
     NbContEntry e = c.cont[idx];
     nbc_cont_remove(c, idx);
     NbUe *u = &c.ue[e.slot];
@@ -1292,12 +1453,24 @@ NB_FN1 void nbc_msg3_event(NbCtx &c, int slot, int t)
 {
     NbHdr *h = nbc_hdr(c);
     NbUe *u = &c.ue[slot];
-    double LogF = nbc_normal(c, 0.0, NB_SIGMA_F);
-    double rx_pw = NB_SUB(NB_SUB(NB_TX_PW, u->loss), LogF);
-    rx_pw = nb_exp10(NB_DIV(rx_pw, 10.0));
-    double ni = NB_SUB(NB_ADD(NB_NOISE_MW, NB_ADD(0.0, rx_pw)), rx_pw);
-    double SINR = NB_MUL(10.0, nb_log10(NB_DIV(rx_pw, ni)));
-    double bler = nbc_get_bler(c, SINR, u->I_tbs, u->N_rep);
+    const int I_tbs = u->I_tbs, N_rep = u->N_rep;              /* of the first UE of the contention list (channel.py:226-227) */
+    int contenders = 1;
+    double SINR;
+#ifndef NB_NO_CAPTURE
+    if (nbc_cold(c)->capture_effect && (contenders = nbc_msg3_contenders(c, slot)) > 1) {
+        int mi;                                                /* several UEs answered the grant: the strongest one is the candidate (channel.py:221-234) */
+        SINR = nbc_sinr_estimation(c, c.scratch, contenders, &mi);
+        slot = c.scratch[mi]; u = &c.ue[slot];
+    } else
+#endif
+    {
+        double LogF = nbc_normal(c, 0.0, NB_SIGMA_F);
+        double rx_pw = NB_SUB(NB_SUB(NB_TX_PW, u->loss), LogF);
+        rx_pw = nb_exp10(NB_DIV(rx_pw, 10.0));
+        double ni = NB_SUB(NB_ADD(NB_NOISE_MW, NB_ADD(0.0, rx_pw)), rx_pw);
+        SINR = NB_MUL(10.0, nb_log10(NB_DIV(rx_pw, ni)));
+    }
+    double bler = nbc_get_bler(c, SINR, I_tbs, N_rep);
     double p = nb_pow01(NB_SUB(1.0, bler), (double)NB_MSG3_TBS / 256.0);
     int connected = nbc_bernoulli(c, p);
     int uce = u->CE_level, i_ = 0, window_active = 0;
@@ -1331,7 +1504,7 @@ NB_FN1 void nbc_msg3_event(NbCtx &c, int slot, int t)
         u->state = NB_UE_RAR;
         h->RAR_UEs[uce][i_] += 1; h->rar_tot[uce] += 1;
     }
-    NB_TRACE(c, NBIOT_TR_MSG3, uce, t, connected, connected ? 0 : 1);   /* perf_monitor.rar_sample (rx_procedure.py:41-51): one contender */
+    NB_TRACE(c, NBIOT_TR_MSG3, uce, t, connected, connected ? 0 : (contenders > 1 ? 2 : 1));   /* perf_monitor.rar_sample (rx_procedure.py:41-51): a failure is an error with one contender, a collision with several */
     nbc_update_state(c);
 }
 

@@ -86,7 +86,7 @@ typedef struct {            /* 16 B: entry of the connected queue, kept sorted b
 typedef struct {            /* 16 B: UE in contention resolution; key = its MAC_timer event */
     uint64_t key;
     int32_t ue_id;
-    uint16_t slot, pad;
+    uint16_t slot, ord;     /* ord: position in the contention list of its msg3 grant (0 unless capture_effect put several UEs on one grant) */
 } NbContEntry;
 
 typedef struct {            /* 64 B: reference system/user.py:35-70 minus never-read fields */
@@ -204,6 +204,7 @@ typedef struct {
     int32_t *stat_base;                   /* int32[n_inst][4][stat_cap]: delay, connection, access, acked bits */
     nbiot_trace_rec_t *trace_base;        /* [n_inst][trace_cap] */
     int32_t trace_cap, trace_mask;
+    int32_t capture_effect, pad_cold;     /* Channel(capture_effect=True), channel.py:124-126 */
 } NbColdConf;
 
 /* per-CTA constants in shared memory: NbCtx.ctrl points at the first member */
@@ -242,6 +243,7 @@ static inline NbColdConf nb_make_cold(const nbiot_conf_t *c, uint8_t *state, uin
     k.occ_base = (NbOccHist *)(state + off_occ); k.stat_base = (int32_t *)(state + off_stat);
     k.trace_base = (nbiot_trace_rec_t *)(state + off_trace);
     k.trace_cap = c->trace_cap > 0 ? c->trace_cap : 0; k.trace_mask = k.trace_cap ? c->trace_mask : 0;
+    k.capture_effect = c->capture_effect ? 1 : 0; k.pad_cold = 0;
     return k;
 }
 

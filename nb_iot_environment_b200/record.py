@@ -64,7 +64,7 @@ class NbiotConf(ctypes.Structure):
                 ('ue_cap', ctypes.c_int32), ('grid_w', ctypes.c_int32), ('hist_cap', ctypes.c_int32),
                 ('stat_cap', ctypes.c_int32), ('clustered', ctypes.c_int32), ('cluster_lo', ctypes.c_int32), ('cluster_hi', ctypes.c_int32),
                 ('cluster_prob', ctypes.c_double), ('cluster_range', ctypes.c_double),
-                ('trace_cap', ctypes.c_int32), ('trace_mask', ctypes.c_int32)]
+                ('trace_cap', ctypes.c_int32), ('trace_mask', ctypes.c_int32), ('capture_effect', ctypes.c_int32), ('pad_conf', ctypes.c_int32)]
 
 
 # nbiot_trace_rec_t (include/nbiot_conf.h): one sample of PerfMonitor's lists
@@ -119,7 +119,7 @@ _KNOWN = {'ratio', 'M', 'buffer_range', 'reward_criteria', 'sort_criterium', 'le
 DEFAULT_STAT_CAP = 2048
 
 
-def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_cap=None, trace_cap=None):
+def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_cap=None, trace_cap=None, capture_effect=False):
     """conf dict with the reference's keys and defaults (system_creator.py:24-44) -> NbiotConf."""
     unknown = set(conf) - _KNOWN
     if unknown:
@@ -165,6 +165,7 @@ def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_c
         raise ValueError('trace_cap must be >= 0')
     if not c.trace_cap:
         c.trace_mask = 0
+    c.capture_effect = int(bool(capture_effect))        # Channel(capture_effect=True), channel.py:124-126
     # clustered placement (system_creator.py:41-44, population.py:57-63)
     c.clustered = int(bool(conf.get('clustered', False)))
     lo, hi = conf.get('cluster_ues', [10, 30])

@@ -66,8 +66,9 @@ enum { EV_NPDCCH_ARRIVAL, EV_NPRACH_UPDATE, EV_RAR_WINDOW_END, EV_NPRACH_START, 
 
 typedef struct {
     int type, t, CE_level, carrier, N_pream, N_rep, N_sf, N_sc, rar_w_id;
-    UE *ue;       /* Msg3 ue_list (one UE: capture_effect is off), NPUSCH_end, Backoff_end */
-    int ue_id;    /* MAC_timer ue_id_list (one id) */
+    UE *ue;       /* Msg3 ue_list[0], NPUSCH_end, Backoff_end */
+    int ue_id;    /* MAC_timer ue_id_list[0] */
+    UE **ue_list; int *id_list; int n_list;   /* Msg3 ue_list / MAC_timer ue_id_list with several contenders (capture effect); NULL / 0 for one */
 } Event;
 
 typedef struct { int time; uint64_t count; Event ev; } HeapEntry;
@@ -348,6 +349,33 @@ static int preamble_detection_single(Oracle *o, UE *ue, int N_rep)   /* channel.
     double p = 1 / (1 + nb_exp(-nb_nprach_k[r] * (SINR - nb_nprach_x0[r])));
     int detected = rng_bernoulli(o, p);
     if (detected) ue->state = NB_UE_RAR;
+    return detected;
+}
+
+static double sinr_estimation(Oracle *o, UE **ues, int n, int *max_i)   /* channel.py:178-198 */
+{
+    double sum = 0, max_rx = -INFINITY;
+    *max_i = 0;
+    for (int i = 0; i < n; ++i) {
+        double LogF = rng_normal(o, 0, NB_SIGMA_F);
+        double rx_pw = NB_TX_PW - ues[i]->loss - LogF;
+        rx_pw = nb_exp10(rx_pw / 10);
+        sum = sum + rx_pw;                                     /* Python sum(pw): left to right from 0 */
+        if (rx_pw > max_rx) { max_rx = rx_pw; *max_i = i; }
+    }
+    double ni = NB_NOISE_MW + sum - max_rx;
+    return 10 * nb_log10(max_rx / ni);
+}
+
+/* Channel.multiple_preamble_detection (channel.py:200-219): the strongest of the colliding signals may still be detected */
+static int multiple_preamble_detection(Oracle *o, UE **ues, int n, int N_rep)
+{
+    int mi;
+    double SINR = sinr_estimation(o, ues, n, &mi);
+    int r = rep_index(N_rep);
+    double p = 1 / (1 + nb_exp(-nb_nprach_k[r] * (SINR - nb_nprach_x0[r])));
+    int detected = rng_bernoulli(o, p);
+    for (int i = 0; i < n; ++i) ues[i]->state = detected ? NB_UE_CAPTURE : NB_UE_COLLIDED;
     return detected;
 }
 
@@ -676,25 +704,34 @@ static void get_new_arrivals(Oracle *o, int t)                        /* populat
 
 static void population_msg3_grant(Oracle *o, int CE_level, int t, int t_msg3_end, int I_tbs, int N_rep)   /* population.py:201-256 */
 {
-    UE *sel = NULL;
     uvec *l = &o->ra_lists[CE_level];
+    uvec cl = { 0 };                                           /* contention_list */
+    int preamble = -1;
     for (int i = 0; i < l->n; ++i) {
         UE *ue = l->d[i];
-        if (ue->state == NB_UE_CAPTURE || ue->state == NB_UE_RAR) {   /* CAPTURE is unreachable (capture_effect off) */
+        if (!(ue->state == NB_UE_CAPTURE || ue->state == NB_UE_RAR)) continue;
+        if (cl.n == 0) {
+            preamble = ue->preamble;
             ue->I_tbs = I_tbs; ue->N_rep = N_rep; ue->t_contention = t;
-            ue->state = NB_UE_CONREQ;
-            sel = ue;
-            break;
+            VPUSH(cl, ue);
+            if (ue->state == NB_UE_RAR) { ue->state = NB_UE_CONREQ; break; }      /* did not collide: the only contender */
+        } else if (ue->preamble == preamble) {                 /* captured preamble: everybody who sent it answers the grant */
+            ue->I_tbs = I_tbs; ue->N_rep = N_rep; ue->t_contention = t;
+            VPUSH(cl, ue);
         }
     }
-    if (!sel) return;
-    uvec_remove(l, sel);
-    VPUSH(o->contention, sel);
-    Event m = make_event(EV_MSG3); m.ue = sel; m.ue_id = sel->id;
+    if (!cl.n) return;
+    for (int i = 0; i < cl.n; ++i) { uvec_remove(l, cl.d[i]); VPUSH(o->contention, cl.d[i]); }
+    Event m = make_event(EV_MSG3); m.ue = cl.d[0]; m.ue_id = cl.d[0]->id;
+    Event tm = make_event(EV_MAC_TIMER); tm.ue_id = cl.d[0]->id;
+    if (cl.n > 1) {
+        m.ue_list = malloc(sizeof(UE *) * (size_t)cl.n); tm.id_list = malloc(sizeof(int) * (size_t)cl.n); m.n_list = tm.n_list = cl.n;
+        for (int i = 0; i < cl.n; ++i) { m.ue_list[i] = cl.d[i]; tm.id_list[i] = cl.d[i]->id; }
+    }
     schedule_event(o, t_msg3_end, m);
-    Event tm = make_event(EV_MAC_TIMER); tm.ue_id = sel->id;
     int t_exp = t + o->MAC_timer > t_msg3_end + 1 ? t + o->MAC_timer : t_msg3_end + 1;
     schedule_event(o, t_exp, tm);
+    VFREE(cl);
 }
 
 static void backoff_end(UE *ue) { ue->state = NB_UE_RAO; ue->backoff_counter += 1; }   /* population.py:143-149 */
@@ -720,15 +757,20 @@ static void population_RAR_window_end(Oracle *o, int t, int CE_level, int backof
 
 static void population_MAC_timeout(Oracle *o, Event *ev)              /* population.py:151-163 */
 {
-    for (int i = 0; i < o->contention.n; ++i) {
-        UE *ue = o->contention.d[i];
-        if (ue->id == ev->ue_id) {
-            VDEL(o->contention, i);
-            ue->state = NB_UE_RAO; ue->timeout_counter += 1;
-            VPUSH(o->ra_lists[ue->CE_level], ue);
-            return;
+    int n = ev->n_list > 1 ? ev->n_list : 1;
+    for (int k = 0; k < n; ++k) {                              /* ue_id_list order; ids that already connected are skipped */
+        int id = ev->n_list > 1 ? ev->id_list[k] : ev->ue_id;
+        for (int i = 0; i < o->contention.n; ++i) {
+            UE *ue = o->contention.d[i];
+            if (ue->id == id) {
+                VDEL(o->contention, i);
+                ue->state = NB_UE_RAO; ue->timeout_counter += 1;
+                VPUSH(o->ra_lists[ue->CE_level], ue);
+                break;
+            }
         }
     }
+    free(ev->id_list); ev->id_list = NULL;
 }
 
 /* PerfMonitor's sample lists, in append order (perf_monitor.py:61-79, :111-140, :185-202); which lists are kept: conf.trace_mask */
@@ -776,7 +818,13 @@ static void access_NPRACH_start(Oracle *o, Event *ev)                 /* access_
             for (int j = 0; j < i; ++j) if (ra.d[j]->preamble == pre) { first = 0; break; }
             if (!first) continue;
             for (int j = i; j < n_ues; ++j) if (ra.d[j]->preamble == pre) cnt++;
-            if (cnt > 1) { detected_signals += 1; }
+            if (cnt > 1 && o->conf.capture_effect) {           /* channel.py:158-159 */
+                UE **grp = malloc(sizeof(UE *) * (size_t)cnt); int g = 0;
+                for (int j = i; j < n_ues; ++j) if (ra.d[j]->preamble == pre) grp[g++] = ra.d[j];
+                detected_preambles += multiple_preamble_detection(o, grp, cnt, N_rep); detected_signals += 1;
+                free(grp);
+            }
+            else if (cnt > 1) { detected_signals += 1; }
             else { int d = preamble_detection_single(o, ra.d[i], N_rep); detected_preambles += d; detected_signals += d; }
         }
         int collided = detected_signals - detected_preambles;
@@ -859,14 +907,20 @@ static void node_msg3_outcome(Oracle *o, UE *ue, int t, int connected)   /* node
 static void rx_msg3_event(Oracle *o, Event *ev)                       /* rx_procedure.py:29-51, channel.py:221-234 */
 {
     UE *ue = ev->ue;
-    double SINR = sinr_estimation_single(o, ue);
-    double bler_256 = get_bler(o, SINR, ue->I_tbs, ue->N_rep);
+    int contenders = ev->n_list > 1 ? ev->n_list : 1;
+    double SINR;
+    int I_tbs = ue->I_tbs, N_rep = ue->N_rep;                  /* of contention_list[0] (channel.py:226-227) */
+    if (contenders > 1) { int mi; SINR = sinr_estimation(o, ev->ue_list, contenders, &mi); ue = ev->ue_list[mi]; }   /* the strongest signal */
+    else SINR = sinr_estimation_single(o, ue);
+    double bler_256 = get_bler(o, SINR, I_tbs, N_rep);
     double p = nb_pow01(1.0 - bler_256, (double)NB_MSG3_TBS / 256);
     int connected = rng_bernoulli(o, p);
     int ce = ue->CE_level;
     node_msg3_outcome(o, ue, ev->t, connected);
     if (connected) o->ue_connections += 1;                    /* perf.rar_sample(1,0,0,...) */
-    perf_sample(o, NBIOT_TR_MSG3, ce, ev->t, connected, connected ? 0 : 1);   /* one contender: a failure is an error, not a collision (:49-51) */
+    /* a failure with one contender is an error, with several a collision (rx_procedure.py:41-51) */
+    perf_sample(o, NBIOT_TR_MSG3, ce, ev->t, connected, connected ? 0 : (contenders > 1 ? 2 : 1));
+    free(ev->ue_list); ev->ue_list = NULL;
 }
 
 static void rx_NPUSCH_end(Oracle *o, Event *ev)                       /* rx_procedure.py:54-61, channel.py:236-256, node_b.py:801-830 */

@@ -74,9 +74,9 @@ def tables():
 class OracleCell:
     """One simulated cell: NodeB-level reset()/step(action23) like reference system/node_b.py:163-245."""
 
-    def __init__(self, conf, seed, n_carriers=1):
+    def __init__(self, conf, seed, n_carriers=1, capture_effect=False):
         self.L = lib()
-        self.cconf = conf if isinstance(conf, NbiotConf) else make_conf(conf, n_carriers=n_carriers)
+        self.cconf = conf if isinstance(conf, NbiotConf) else make_conf(conf, n_carriers=n_carriers, capture_effect=capture_effect)
         lut, mcs = tables()
         self.h = self.L.orc_create(ctypes.byref(self.cconf), ctypes.c_uint64(seed), lut.ctypes.data, mcs.ctypes.data)
         self.rec = np.zeros(1, dtype=RECORD_DTYPE)

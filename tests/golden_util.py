@@ -30,6 +30,7 @@ class Golden:
         self.seeds = self.meta['seeds']
         self.decisions = self.meta['decisions']
         self.counters = self.meta['counters']
+        self.capture_effect = bool(self.meta.get('capture_effect', False))     # Channel(capture_effect=True): a constructor argument, not a conf key
         self.z = z
 
     def hist(self, si):

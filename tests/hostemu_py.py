@@ -37,9 +37,9 @@ def lib(lanes):
 
 
 class EmuBatch:
-    def __init__(self, conf, seeds, n_carriers=1, lanes=1, ctrl=None, **caps):
+    def __init__(self, conf, seeds, n_carriers=1, lanes=1, ctrl=None, capture_effect=False, **caps):
         self.L = lib(lanes)
-        self.cconf = make_conf(conf, n_carriers=n_carriers, **caps)
+        self.cconf = make_conf(conf, n_carriers=n_carriers, capture_effect=capture_effect, **caps)
         self.n = len(seeds)
         self.seeds = np.asarray(seeds, dtype=np.uint64)
         lut, mcs = tables()

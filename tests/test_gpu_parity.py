@@ -10,7 +10,7 @@ from golden_util import CASES, Golden, record_diff, assert_pm_lists, REF_RTOL
 pytestmark = pytest.mark.gpu
 
 CFG1 = {'ratio': 1.0, 'M': 1000, 'buffer_range': [100, 600], 'reward_criteria': 'throughput'}
-CAPS = {'manual_branches': dict(grid_w=4096), 'cfg3_npusch_random_policy': dict(grid_w=2048), 'cfg2_random_policy': dict(grid_w=2048),
+CAPS = {'capture_effect': dict(grid_w=2048), 'capture_effect_two_carriers': dict(grid_w=2048), 'traces_two_carriers': dict(grid_w=2048), 'manual_branches': dict(grid_w=4096), 'cfg3_npusch_random_policy': dict(grid_w=2048), 'cfg2_random_policy': dict(grid_w=2048),
         'cfg4_two_carriers_bursty': dict(grid_w=2048)}
 
 # agent sets of the two shipped scenarios (scripts/nprach/evaluate_RL.py:46-77, scripts/npusch/experiments_RL.py:40-78)
@@ -56,8 +56,8 @@ def test_golden_traces_and_oracle(case, kernel):
     g = Golden(case)
     caps = dict(ue_cap=g.conf['M'], grid_w=1024, hist_cap=1024)
     caps.update(CAPS.get(case, {}))
-    env = BatchedNBIoTEnv(g.conf, num_envs=len(g.seeds), seeds=g.seeds, n_carriers=g.n_carriers, all_states_external=True, **caps)
-    cells = [OracleCell(g.conf, s, n_carriers=g.n_carriers) for s in g.seeds]
+    env = BatchedNBIoTEnv(g.conf, num_envs=len(g.seeds), seeds=g.seeds, n_carriers=g.n_carriers, all_states_external=True, capture_effect=g.capture_effect, **caps)
+    cells = [OracleCell(g.conf, s, n_carriers=g.n_carriers, capture_effect=g.capture_effect) for s in g.seeds]
     env.reset()
     recs = env.records()
     hists = [g.hist(si) for si in range(len(g.seeds))]

@@ -7,7 +7,7 @@ import pytest
 
 from golden_util import CASES, Golden, record_diff, assert_pm_lists, REF_RTOL
 
-CAPS = {'manual_branches': dict(grid_w=4096), 'cfg3_npusch_random_policy': dict(grid_w=2048), 'cfg2_random_policy': dict(grid_w=2048),
+CAPS = {'capture_effect': dict(grid_w=2048), 'capture_effect_two_carriers': dict(grid_w=2048), 'traces_two_carriers': dict(grid_w=2048), 'manual_branches': dict(grid_w=4096), 'cfg3_npusch_random_policy': dict(grid_w=2048), 'cfg2_random_policy': dict(grid_w=2048),
         'cfg4_two_carriers_bursty': dict(grid_w=2048)}
 
 
@@ -16,7 +16,7 @@ def _replay(case, lanes, decisions):
     g = Golden(case)
     caps = dict(ue_cap=g.conf['M'], grid_w=1024, hist_cap=1024)
     caps.update(CAPS.get(case, {}))
-    b = EmuBatch(g.conf, g.seeds, n_carriers=g.n_carriers, lanes=lanes, **caps)
+    b = EmuBatch(g.conf, g.seeds, n_carriers=g.n_carriers, lanes=lanes, capture_effect=g.capture_effect, **caps)
     recs = b.reset()
     D = min(decisions, g.decisions)
     for d in range(-1, D):
@@ -55,7 +55,7 @@ def test_core_scalar_logic(case, oracle_lib):
     _replay(case, 1, 10 ** 9)
 
 
-@pytest.mark.parametrize('case', ['cfg1_default', 'cfg4_two_carriers_bursty', 'overload'])
+@pytest.mark.parametrize('case', ['cfg1_default', 'cfg4_two_carriers_bursty', 'overload', 'capture_effect'])
 def test_core_lane_parallel_sections(case, oracle_lib):
     _replay(case, 32, 400)
 

@@ -11,7 +11,7 @@ def test_oracle_replays_reference_trace(case, oracle_lib):
     from oracle.oracle_py import OracleCell
     g = Golden(case)
     for si, seed in enumerate(g.seeds):
-        cell = OracleCell(g.conf, seed, n_carriers=g.n_carriers)
+        cell = OracleCell(g.conf, seed, n_carriers=g.n_carriers, capture_effect=g.capture_effect)
         cell.enable_event_log()
         rec = cell.reset()
         assert not record_diff(g.records[si, 0], rec, rtol=REF_RTOL)

@@ -58,6 +58,11 @@ CASES = {
     'traces_statistics': dict(conf=dict(CFG1, ratio=0.5, traces=True, statistics=True), nc=1, policy='random', seeds=[90, 91], decisions=1200),
     'traces_two_carriers': dict(conf={'M': 3000, 'ratio': 0.5, 'buffer_range': [100, 600], 'reward_criteria': 'throughput', 'random': True,
                                       'traces': True, 'statistics': True}, nc=2, policy='random', seeds=[95], decisions=800),
+    # Channel(capture_effect=True) (channel.py:158-159, :200-219): CAPTURE / COLLIDED states, msg3 grants with several contenders
+    'capture_effect': dict(conf={'M': 3000, 'ratio': 0.5, 'buffer_range': [100, 600], 'reward_criteria': 'throughput', 'traces': True}, nc=1,
+                           policy='random', seeds=[97, 98], decisions=1400, capture=True),
+    'capture_effect_two_carriers': dict(conf={'M': 3000, 'ratio': 0.5, 'buffer_range': [100, 600], 'reward_criteria': 'users', 'random': True, 'traces': True},
+                                        nc=2, policy='random', seeds=[99], decisions=900, capture=True),
     'invd_reward_small_cell': dict(conf=dict(CFG1, reward_criteria='invd_users', max_d=3.0, M=600), nc=1, policy='random', seeds=[70], decisions=800),
 }
 
@@ -86,7 +91,7 @@ def run_case(name):
     actions = np.zeros((S, D, 23), dtype=np.int8)
     counters, hists, events, stats, pmlists = [], [], [], [], []
     for si, seed in enumerate(case['seeds']):
-        cell = RefCell(case['conf'], seed, n_carriers=case['nc'], log_events=True)
+        cell = RefCell(case['conf'], seed, n_carriers=case['nc'], log_events=True, capture_effect=case.get('capture', False))
         prng = np.random.default_rng(1000 + seed)
         rec = cell.reset()
         records[si, 0] = rec
@@ -138,7 +143,7 @@ def run_case(name):
         for k, v in pmlists[si].items():
             flat[f'pm_{k}_{si}'] = v
     meta = {'name': name, 'conf': case['conf'], 'n_carriers': case['nc'], 'seeds': case['seeds'], 'policy': case['policy'],
-            'decisions': D, 'counters': counters, 'record_itemsize': RECORD_DTYPE.itemsize,
+            'decisions': D, 'counters': counters, 'capture_effect': bool(case.get('capture', False)), 'record_itemsize': RECORD_DTYPE.itemsize,
             'record_descr': str(RECORD_DTYPE.descr)}
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name + '.npz'), records=records.view(np.uint8).reshape(S, D + 1, -1),

@@ -156,11 +156,15 @@ def info_to_record(info, reward, rng=None, hist_out=None):
 class RefCell:
     """NodeB-level driver of one reference cell: reset() / step(action23) -> record."""
 
-    def __init__(self, conf, seed, n_carriers=1, log_events=False):
+    def __init__(self, conf, seed, n_carriers=1, log_events=False, capture_effect=False):
         m = load_reference(n_carriers)
         self.m = m
         self.rng = PhiloxShim(seed)
         self.node, self.perf, self.population, self.carrier = m['create_system'](self.rng, dict(conf))
+        if capture_effect:
+            # create_system never passes capture_effect to Channel (system_creator.py:51); the flag is a plain attribute read at every
+            # preamble detection (channel.py:126, :158), so it is switched on on the constructed channel
+            self.node.m.channel.capture_effect = True
         self.hists = []
         self.events = [] if log_events else None
         if log_events:
