@@ -152,6 +152,48 @@ class NPRACHWrapper(_Wrapper):
         return obs, reward, terminated, truncated, infos
 
 
+class NPRACHWrapperTraces(NPRACHWrapper):
+    """reference NPRACH_wrapper_traces (wrappers.py:210-255), the wrapper scripts/nprach/evaluate_RL.py:141 runs: after every step one
+    sample per metric and cell is kept -- info[metric], or the mean of it when it is a list (0 for an empty one) -- on the device.
+    `samples[metric]` is a list with one float64[N] tensor per step; `samples_array(metric)` stacks them to [steps, N], the per-cell
+    columns being what the reference's evaluator collects per run (evaluate_RL.py:172-177). The log file / flag file of the reference
+    class are host conveniences and are not restated."""
+
+    _PERIOD_LISTS = {'incoming': (0, 'n_incoming'), 'delays': (1, 'departures'), 'service_times': (2, 'departures')}
+
+    def __init__(self, env, metrics, discrete=False, use_default_action=False, norm=100):
+        super().__init__(env, discrete=discrete, use_default_action=use_default_action, norm=norm)
+        self.samples = {m: [] for m in metrics}
+
+    def _period_mean(self, which, count_field):
+        base = self.env
+        off, cap = base._hist_off[which], base._hist_off[3]
+        N = self.num_envs
+        if which == 0:
+            v = base.state[off:off + N * cap * 8].view(torch.float64).view(N, cap)
+        else:
+            v = base.state[off:off + N * cap * 4].view(torch.int32).view(N, cap).double()
+        n = base.record_field(count_field).long().clamp(max=cap)
+        keep = torch.arange(cap, device=self.device)[None, :] < n[:, None]
+        total = torch.where(keep, v, torch.zeros_like(v)).sum(dim=1)
+        return torch.where(n > 0, total / n.clamp(min=1).double(), torch.zeros_like(total))
+
+    def _sample(self, metric):
+        if metric in self._PERIOD_LISTS:
+            return self._period_mean(*self._PERIOD_LISTS[metric])
+        v = self.env.record_field(metric).double()
+        return v.mean(dim=1) if v.dim() == 2 else v            # a fixed-length list of the info (ratios per CE level ...): its mean
+
+    def step(self, action):
+        out = super().step(action)
+        for metric, lst in self.samples.items():
+            lst.append(self._sample(metric).clone())
+        return out
+
+    def samples_array(self, metric):
+        return torch.stack(self.samples[metric]) if self.samples[metric] else torch.zeros((0, self.num_envs), dtype=torch.float64, device=self.device)
+
+
 class BasicSchedulerWrapper(_Wrapper):
     """reference BasicSchedulerWrapper (wrappers.py:84-116); with select_only=True the plain BasicWrapper (:47-82)."""
 

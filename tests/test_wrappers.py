@@ -20,10 +20,11 @@ def _load(name):
     return meta, [z[f'acts_{i}'] for i in range(S)], [z[f'obs_{i}'] for i in range(S)], [z[f'rew_{i}'] for i in range(S)]
 
 
-def _check_nprach(make_env):
-    from nb_iot_environment_b200.wrappers import NPRACHWrapper
+def _check_nprach(make_env, traces=False):
+    from nb_iot_environment_b200.wrappers import NPRACHWrapper, NPRACHWrapperTraces
     meta, acts, obs, rew = _load('wrappers_nprach')
-    env = NPRACHWrapper(make_env(meta['conf'], NPRACH_AGENTS, 3, meta['seeds']))
+    base = make_env(meta['conf'], NPRACH_AGENTS, 3, meta['seeds'])
+    env = NPRACHWrapperTraces(base, meta['metrics']) if traces else NPRACHWrapper(base)
     assert env.action_nvec.tolist() == [105, 4, 4, 4, 6, 6, 6]
     o, _ = env.reset()
     o = o.cpu().numpy()
@@ -39,6 +40,12 @@ def _check_nprach(make_env):
             assert np.allclose(o[i], obs[i][k + 1], rtol=REF_RTOL, atol=1e-12), (k, i)
             assert r[i] == pytest.approx(rew[i][k], rel=1e-12), (k, i)
     assert n_invalid > 0          # the trace exercises the replay-previous-action branch
+    if traces:                    # NPRACH_wrapper_traces.samples (wrappers.py:210-255): info[metric], lists as their mean
+        z = np.load(os.path.join(GOLDEN_DIR, 'wrappers_nprach.npz'))
+        for metric in meta['metrics']:
+            got = env.samples_array(metric).cpu().numpy()
+            for i in range(len(meta['seeds'])):
+                assert np.allclose(got[:, i], z[f'samples_{metric}_{i}'], rtol=REF_RTOL, atol=1e-12), (metric, i)
 
 
 def _check_npusch(make_env):
@@ -118,6 +125,11 @@ def test_rar_wrapper_on_cuda():
 @pytest.mark.gpu
 def test_nprach_wrapper_on_cuda():
     _check_nprach(_cuda_env)
+
+
+@pytest.mark.gpu
+def test_nprach_wrapper_traces_on_cuda():
+    _check_nprach(_cuda_env, traces=True)
 
 
 @pytest.mark.gpu

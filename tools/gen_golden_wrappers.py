@@ -16,6 +16,9 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from test_gpu_parity import NPRACH_AGENTS, NPUSCH_AGENTS, CFG1, CFG3   # noqa: E402  (agent dictionaries of the two scripts)
 
 
+TRACE_METRICS = ['departures', 'NPRACH_occupation', 'service_times', 'delays', 'incoming', 'detection_ratios', 'av_delay']   # evaluate_RL.py:37 + list-valued ones
+
+
 def make_env(m, conf, agents, ext, seed):
     import gymnasium as gym
     node, perf, _, _ = m['create_system'](PhiloxShim(seed), dict(conf))
@@ -34,7 +37,8 @@ def main():
     conf = dict(CFG1, ratio=0.5)
     res = {}
     for si, seed in enumerate([500, 501]):
-        env = W.NPRACH_wrapper(make_env(m, conf, NPRACH_AGENTS, 3, seed))
+        # the subclass evaluate_RL.py:141 uses: same observations and rewards as NPRACH_wrapper, plus one sample per metric and step
+        env = W.NPRACH_wrapper_traces(make_env(m, conf, NPRACH_AGENTS, 3, seed), TRACE_METRICS)
         rng = np.random.default_rng(seed)
         obs0, _ = env.reset()
         acts, obs, rew = [], [np.asarray(obs0, float)], []
@@ -43,7 +47,10 @@ def main():
             o, r, _, _, info = env.step(list(a))
             acts.append(a); obs.append(np.asarray(o, float)); rew.append(float(r))
         res[f'acts_{si}'] = np.asarray(acts, np.int64); res[f'obs_{si}'] = np.asarray(obs); res[f'rew_{si}'] = np.asarray(rew)
-    np.savez_compressed(os.path.join(out, 'wrappers_nprach.npz'), meta=np.frombuffer(json.dumps({'conf': conf, 'seeds': [500, 501]}).encode(), dtype=np.uint8), **res)
+        for metric in TRACE_METRICS:
+            res[f'samples_{metric}_{si}'] = np.asarray(env.samples[metric], dtype=np.float64)
+    np.savez_compressed(os.path.join(out, 'wrappers_nprach.npz'),
+                        meta=np.frombuffer(json.dumps({'conf': conf, 'seeds': [500, 501], 'metrics': TRACE_METRICS}).encode(), dtype=np.uint8), **res)
     # ---- scheduler wrapper + discrete actions
     res = {}
     for si, seed in enumerate([510, 511]):
