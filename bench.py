@@ -233,6 +233,20 @@ class _Job:
                'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                             'b_alg_bytes_per_subframe_instance': balg, 'lbar_live_ues': lbar, 'rho_events_per_subframe': rho}}
         out.update(extra)
+        tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+        key = extra.get('traffic_key')
+        if key and os.path.exists(tp) and key in json.load(open(tp)):
+            # DRAM bytes and warp instructions of ONE launch of this block's kernel from ncu (same build, same workload, scaled by the cells of
+            # this run); time and counters are this run's
+            tj = json.load(open(tp))[key]
+            scale = N / float(tj.get('cells', N))
+            out['roofline']['traffic'] = tj['dram_bytes_per_launch'] * scale
+            wi = float(tj['warp_inst_per_launch']) * scale
+            sf_launch = sf / self.world / K
+            out['issue'] = {'warp_inst_per_launch': wi, 'inst_per_subframe_instance': wi / max(sf_launch, 1.0), 'inst_per_event': wi / max(ev / self.world / K, 1.0),
+                            'ipc_per_sm': wi / ((ms_job / K) * 1e-3 * 1965e6 * 148), 'active_lanes_per_inst': tj.get('active_lanes_per_inst'),
+                            'source': tj.get('source')}
+        out.pop('traffic_key', None)
         return out
 
 
@@ -261,7 +275,7 @@ def block_config5(job, local, K, W):
     d = (env.stats_tensor().clone() - s0).cpu().numpy()
     out = job.finish(env, 'configs[4] sweep point: config-1 traffic (M=1000, ratio 1), default agents on the device, 1 step = 3000 subframes per cell in one launch',
                      N, K, ms, d, float(torch.cat(live).double().sum().item()), 1,
-                     {'l2': f'state {env.state.numel() / 1e9:.1f} GB per GPU, far larger than L2', 'kernel': env.kernel_name()})
+                     {'l2': f'state {env.state.numel() / 1e9:.1f} GB per GPU, far larger than L2', 'kernel': env.kernel_name(), 'traffic_key': 'config5'})
     env.close()
     return out
 

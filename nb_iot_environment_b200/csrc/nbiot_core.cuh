@@ -59,6 +59,9 @@ struct __attribute__((aligned(16))) NbCtx {
 #if NB_LANES == 1
     uint16_t *blk;            /* [C][W / 32] block summaries of the ring (thread-per-cell kernel; NULL: plain column scans) */
 #endif
+#ifdef NB_TPC_GLOBAL_HDR
+    struct NbHdr *hdr_g;
+#endif
 #ifdef NB_TASKS
     int tk_until, tk_max_steps;   /* bounds of this launch (see "tasks" at the end of the file) */
     int tk_internal;              /* the launch has no external action: every agent of a state acts, no state hands control back */
@@ -90,7 +93,11 @@ static long long nb_dbg_count[16];
 #else
 #define NB_ASSUME_SHARED(p) ((void)0)
 #endif
+#ifdef NB_TPC_GLOBAL_HDR   /* experiment: the thread-per-cell kernel reaches the header in place in HBM (no local copy) */
+NB_DEV NbHdr *nbc_hdr(NbCtx &c) { return c.hdr_g; }
+#else
 NB_DEV NbHdr *nbc_hdr(NbCtx &c) { NbHdr *h = (NbHdr *)((char *)&c + sizeof(NbCtx)); NB_ASSUME_SHARED(h); return h; }
+#endif
 NB_DEV const NbColdConf *nbc_cold(NbCtx &c) { return &((const NbCtaConst *)c.ctrl)->cold; }
 /* NB_GRID_STAGED: a build that only runs with the look-ahead ring staged behind the header (long launches): the ring is reached from the
  * context pointer with constant offsets and shared-memory loads, not through a generic pointer that may also point into HBM */

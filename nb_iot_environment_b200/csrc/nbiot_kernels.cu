@@ -262,6 +262,9 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     if ((size_t)h->smem_bytes + sizeof(NbCtaConst) + 64 > prop.sharedMemPerBlockOptin) return set_err(NBIOT_E_INVALID, "grid_w too large for the shared memory of one CTA");
     nb_sim_variant_generic(&h->k_gen); nb_sim_variant_c1(&h->k_c1); nb_sim_variant_gs(&h->k_gs); nb_sim_variant_c1s(&h->k_c1s);
     nb_sim_variant_tpc_gen(&h->k_tpc_gen); nb_sim_variant_tpc_c1(&h->k_tpc_c1);
+    if (const char *e = getenv("NBIOT_TPC_CARVEOUT"))      /* measurement knob: shared-memory carve-out of the thread-per-cell kernels, % */
+        for (const NbSimVariant *v : { &h->k_tpc_gen, &h->k_tpc_c1 })
+            for (const void *f : { v->sim_lo, v->sim_hi }) CK(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     /* Which kernel advances the batch. One warp per cell keeps a cell's latency low but repeats the scalar control logic on 32
      * lanes; one thread per cell shares every common instruction between 32 cells but needs the cells to fill the machine
      * (148 SMs x 16 warps x 32 lanes = 75 776) -- DESIGN.md section 6c has the measured crossover. */

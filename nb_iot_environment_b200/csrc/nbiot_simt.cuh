@@ -54,8 +54,12 @@ nbiot_simt_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *act
     nb_fill_ctx_launch(L.c, A, &s_ctrl);
     nb_fill_ctx(L.c, A, i);
     uint4 *hg = (uint4 *)((NbHdr *)(A.state + A.L.off_hdr) + i), *hl = (uint4 *)&L.h;
+#ifdef NB_TPC_GLOBAL_HDR
+    L.c.hdr_g = (NbHdr *)hg;
+#else
     NB_NOUNROLL
     for (int k = 0; k < (int)(sizeof(NbHdr) / 16); ++k) hl[k] = hg[k];
+#endif
     nbc_blk_rebuild(L.c);
     unsigned long long t0 = 0;
     if (A.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -66,8 +70,10 @@ nbiot_simt_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *act
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         A.prof[4 * (size_t)i] = t0; A.prof[4 * (size_t)i + 1] = t1; A.prof[4 * (size_t)i + 2] = smid; A.prof[4 * (size_t)i + 3] = 0ull;
     }
+#ifndef NB_TPC_GLOBAL_HDR
     NB_NOUNROLL
     for (int k = 0; k < (int)(sizeof(NbHdr) / 16); ++k) hg[k] = hl[k];
+#endif
 }
 
 /* The same with VOTED DISPATCH. Left to themselves the 32 cells of a warp are in as many different event handlers as the event
@@ -91,8 +97,12 @@ nbiot_simtv_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *ac
     if (mine) {
         nb_fill_ctx_launch(L.c, A, &s_ctrl);
         nb_fill_ctx(L.c, A, i);
+#ifdef NB_TPC_GLOBAL_HDR
+        L.c.hdr_g = (NbHdr *)hg;
+#else
         NB_NOUNROLL
         for (int w = 0; w < (int)(sizeof(NbHdr) / 16); ++w) hl[w] = hg[w];
+#endif
         nbc_blk_rebuild(L.c);
         L.c.tk_until = until_time; L.c.tk_max_steps = max_steps; L.c.tk_internal = ext_actions ? 0 : 1;
         k = nbc_task_begin(L.c, ext_actions ? ext_actions + (size_t)i * L.c.ctrl->ext_k : nullptr);
@@ -110,10 +120,12 @@ nbiot_simtv_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *ac
         if (k == best) { k = nbc_task_run(L.c, k); waited = 0; }
         else if (k != NB_TK_DONE) waited += 1;
     }
+#ifndef NB_TPC_GLOBAL_HDR
     if (mine) {
         NB_NOUNROLL
         for (int w = 0; w < (int)(sizeof(NbHdr) / 16); ++w) hg[w] = hl[w];
     }
+#endif
 }
 
 }   /* namespace nbk_<variant> */

@@ -5,6 +5,9 @@
 #include <stdint.h>
 
 #define NB_TPC 1
+#ifdef NB_EXP_TPC_GLOBAL_HDR      /* measurement build: header reached in place in HBM instead of a local-memory copy */
+#define NB_TPC_GLOBAL_HDR 1
+#endif
 #define NB_TASKS 1
 #define NB_FIXED_C 1
 #define NB_NO_EVLOG 1
