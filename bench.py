@@ -310,7 +310,8 @@ def block_config2(job, local, K, W):
     job.barrier()
     d = (env.stats_tensor().clone() - s0).cpu().numpy()
     out = job.finish(env, 'configs[2]: NPUSCH control scenario (M=2000, ratio 1, scheduling agent external, uniform-random actions), 1 step = 1 external decision per cell = 1 launch',
-                     N, K, e0.elapsed_time(e1), d, float(torch.cat(live).double().sum().item()) * 10.0, 1, {'kernel': env.kernel_name()})
+                     N, K, e0.elapsed_time(e1), d, float(torch.cat(live).double().sum().item()) * 10.0, 1,
+                     {'kernel': 'warp-per-cell (launches of one or two NodeB steps run on it whatever the batch size)'})
     out['instance_decisions_per_s'] = N * job.world * K / (out['ms_per_step'] * K / 1e3)
     env.close()
     return out
@@ -354,7 +355,8 @@ def block_config3(job, local, K, W):
     d = (env.stats_tensor().clone() - s0).cpu().numpy()
     out = job.finish(env, 'configs[3]: two carriers, NPRACH + NPUSCH both controlled from outside at every decision, M=3000 bursty (ratio 0.5, random traffic), '
                           '262144 cells over the GPUs of the job (65536 on one GPU), 1 step = 1 NodeB decision per cell = 1 launch (action upload + state-dependent fix-up inside)',
-                     N, K, e0.elapsed_time(e1), d, float(torch.cat(live).double().sum().item()) * 10.0, 2, {'kernel': env.kernel_name()})
+                     N, K, e0.elapsed_time(e1), d, float(torch.cat(live).double().sum().item()) * 10.0, 2,
+                     {'kernel': 'warp-per-cell (launches of one or two NodeB steps run on it whatever the batch size)'})
     out['instance_decisions_per_s'] = N * job.world * K / (out['ms_per_step'] * K / 1e3)
     env.close()
     return out
