@@ -87,6 +87,12 @@ __global__ void __launch_bounds__(NB_TPC_THREADS, NB_TPC_MIN_CTAS)
 nbiot_simtv_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps)
 {
     __shared__ NbCtaConst s_ctrl;
+#ifdef NB_TPC_AFFINITY
+    /* class affinity (measurement build): the class the warps of this CTA picked last gets a bonus in the vote, so that the warps of a CTA tend
+     * to walk the same handler at the same time and share the instruction lines they fetch. A racy hint, never a correctness matter. */
+    __shared__ volatile int s_class;
+    if (threadIdx.x == 0) s_class = 0;
+#endif
     for (int k = threadIdx.x; k < (int)(sizeof(NbCtaConst) / 4); k += blockDim.x) ((uint32_t *)&s_ctrl)[k] = ((const uint32_t *)A.ctrl)[k];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,11 +118,20 @@ nbiot_simtv_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *ac
         __syncwarp(NB_FULL);
         if (!__ballot_sync(NB_FULL, k != NB_TK_DONE)) break;
         int best = 0, best_score = 0;
+#ifdef NB_TPC_AFFINITY
+        const int fav = s_class;
+#endif
 #pragma unroll
         for (int cl = 1; cl < NB_TK_N; ++cl) {
             int sc = __reduce_add_sync(NB_FULL, k == cl ? 4 + waited : 0);
+#ifdef NB_TPC_AFFINITY
+            if (sc > 0 && cl == fav) sc += NB_TPC_AFFINITY;
+#endif
             if (sc > best_score) { best_score = sc; best = cl; }
         }
+#ifdef NB_TPC_AFFINITY
+        if ((threadIdx.x & 31u) == 0 && best) s_class = best;
+#endif
         if (k == best) { k = nbc_task_run(L.c, k); waited = 0; }
         else if (k != NB_TK_DONE) waited += 1;
     }
