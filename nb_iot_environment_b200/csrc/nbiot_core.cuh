@@ -441,7 +441,7 @@ NB_FN void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
     int cursor[2][3];
     NB_NOUNROLL
     for (int cc = 0; cc < NB_NC(c); ++cc)
-        NB_NOUNROLL
+        NB_SMALL_LOOP
         for (int ce = 0; ce < 3; ++ce) {
             NbResource &r = h->res[cc][ce];
             cursor[cc][ce] = a;
@@ -457,7 +457,7 @@ NB_FN void nbc_extend_lookahead(NbCtx &c, int new_t_ahead)
         int best = b, bc = -1, bce = -1;
         NB_NOUNROLL
         for (int cc = 0; cc < NB_NC(c); ++cc)
-            NB_NOUNROLL
+            NB_SMALL_LOOP
             for (int ce = 0; ce < 3; ++ce) {
                 NbResource &r = h->res[cc][ce];
                 if (!r.N_sc || cursor[cc][ce] >= b) continue;
@@ -1796,7 +1796,7 @@ NB_FN1S uint64_t nbc_next_event(NbCtx &c, int *code)
 #if NB_LANES == 1
     /* one lane: the fixed slots, then only the pool entries that hold an event (keys are unique, so no tie to break) */
     {
-        NB_NOUNROLL
+        NB_SMALL_LOOP
         for (int j = 0; j < 9; ++j) { uint64_t kj = h->keys[j]; if (kj < best) { best = kj; bcode = j; } }
         uint64_t used = ~h->pool_free & ((1ULL << NB_EV_POOL) - 1ULL);
         NB_NOUNROLL

@@ -5,6 +5,14 @@
 #include <stdint.h>
 
 #define NB_TPC 1
+/* inlining policy of the thread-per-cell build: single-call-site functions out of line, only the tiny multi-site helpers inlined (+3.5 % on the
+ * sweep against the warp-per-cell kernels' policy; inlining everything costs 11 %: profiles/r02_tpc_variants.txt section 11) */
+#ifndef NB_INLINE_SINGLE
+#define NB_INLINE_SINGLE 0
+#endif
+#ifndef NB_INLINE_MULTI
+#define NB_INLINE_MULTI 1
+#endif
 #ifdef NB_EXP_TPC_GLOBAL_HDR      /* measurement build: header reached in place in HBM instead of a local-memory copy */
 #define NB_TPC_GLOBAL_HDR 1
 #endif

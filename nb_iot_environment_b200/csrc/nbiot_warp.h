@@ -63,7 +63,18 @@
 #define NB_FN1 static __device__ __noinline__
 #endif
 #define NB_FULL 0xFFFFFFFFu
+#if defined(NB_TPC) && defined(NB_TPC_UNROLL_ALL)      /* measurement build: the compiler's own unrolling in the thread-per-cell kernel */
+#define NB_NOUNROLL
+#else
 #define NB_NOUNROLL _Pragma("unroll 1")
+#endif
+/* short fixed-trip loops over header arrays (event keys, NPRACH resources): rolled in the warp-per-cell kernels, which are short of instruction
+ * fetch; unrolled in the thread-per-cell kernel, which waits on memory and wants the independent loads in flight together */
+#if defined(NB_TPC) && defined(NB_TPC_MLP)
+#define NB_SMALL_LOOP _Pragma("unroll")
+#else
+#define NB_SMALL_LOOP NB_NOUNROLL
+#endif
 #ifdef NB_TPC
 /* thread-per-cell build (nbiot_simt.cu): one THREAD owns a cell, a warp carries 32 unrelated cells. The lane-parallel sections
  * degenerate to scalar loops (a "warp" of one lane, exactly the NBIOT_EMU_LANES == 1 build the CPU tests run), nothing is
@@ -106,6 +117,7 @@ NB_DEV int nbw_ffsll(uint64_t v) { return __ffsll((long long)v); }
 #define NB_FNM4 static
 #define NB_LDG(p) (*(p))
 #define NB_NOUNROLL
+#define NB_SMALL_LOOP
 static inline int nbw_popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int nbw_ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int nbw_popcll(uint64_t v) { return __builtin_popcountll(v); }
