@@ -43,6 +43,8 @@ struct nbiot_handle {
     unsigned int *counter_dev;
     unsigned long long *prof_dev;   /* NBIOT_PROF_INST=1: per-instance timing of the last launch */
     uint16_t *blk_dev;              /* thread-per-cell kernel: block summaries of the look-ahead rings (derived data) */
+    uint32_t *dur_dev;              /* per cell: duration of its last long warp-per-cell launch (cost predictor of the dealing) */
+    int32_t *deal_order, *deal_len; unsigned int *deal_cnt; int deal_lists, deal_stride, deal_pad, deal;   /* dealing by predicted cost (one-wave launches) */
     int blocks, smem_bytes, sim_hi;
     int blocks_short, smem_short, sim_hi_short, stage_policy;     /* geometry of launches that leave the grid in HBM */
     NbSimVariant k_gen, k_c1, k_gs, k_c1s;   /* builds of the warp-per-instance kernels (nbiot_simk.cuh): generic / single carrier, ring anywhere / staged */
@@ -152,6 +154,50 @@ __global__ void nbiot_stat_hist_kernel(const NbOccHist *occ, const int32_t *stat
     }
 }
 
+/* Dealing the cells of a ONE-WAVE launch to SMs by predicted cost. With as many warp slots as cells (4096 cells on 148 x 28 slots) every cell
+ * starts at once and the launch ends with the SM that happened to get the heaviest cells (SM finish times 12 % apart, a quarter of the warp-time
+ * idle, profiles/r02_tail.txt). A cell's cost is predictable enough from its own previous duration and the length of its random-access lists
+ * (R2 0.48, tools/cost_model2.py): one CTA sorts the cells by that prediction (bitonic sort in shared memory) and deals them to the SMs in snake
+ * order, so that every SM's list holds the same predicted work; nbiot_sim_kernel then takes a warp's cell from the list of the SM it runs on.
+ * Which warp runs a cell never changes a result. */
+#define NB_DEAL_MAX 8192
+__global__ void __launch_bounds__(1024)
+nbiot_deal_kernel(const NbHdr *hdr, const uint32_t *dur, const uint8_t *active, int n_inst, int n_pad, int n_lists, int stride,
+                  int32_t *order, int32_t *len, unsigned int *cnt)
+{
+    extern __shared__ unsigned long long keys[];          /* (predicted cost << 16) | cell index */
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        unsigned long long k = 0ull;                       /* padding and inactive cells sort last */
+        if (i < n_inst && !(active && !active[i])) {
+            const NbHdr *h = hdr + i;
+            const unsigned long long ra = (unsigned long long)(h->ra_n[0] + h->ra_n[1] + h->ra_n[2]);
+            const unsigned long long cost = 1000000ull + 8690ull * ra + (dur ? (365ull * dur[i]) / 1000ull : 0ull);     /* ns; tools/cost_model2.py */
+            k = (cost << 16) | (unsigned long long)i;
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= n_pad; size <<= 1)
+        for (int stride2 = size >> 1; stride2 > 0; stride2 >>= 1) {
+            for (int t = threadIdx.x; t < n_pad / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride2 - 1)), hi = lo + stride2;
+                const bool desc = (lo & size) == 0;        /* overall descending */
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    for (int s2 = threadIdx.x; s2 < n_lists; s2 += blockDim.x) { len[s2] = 0; cnt[s2] = 0u; }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_pad; p += blockDim.x) {
+        const unsigned long long k = keys[p];
+        if (!k) continue;
+        const int round = p / n_lists, pos = p % n_lists, sm = (round & 1) ? n_lists - 1 - pos : pos;       /* snake: heavy and light alternate */
+        order[(size_t)sm * stride + round] = (int32_t)(k & 0xFFFFull);
+        atomicMax(&len[sm], round + 1);
+    }
+}
+
 /* ------------------------------------------------------------------ host side */
 static NbKernelArgs make_args(nbiot_handle_t *h, int stage_grid = 1)
 {
@@ -161,6 +207,7 @@ static NbKernelArgs make_args(nbiot_handle_t *h, int stage_grid = 1)
     A.hdr_bytes16 = (int)(sizeof(NbHdr) / 16);
     A.grid_bytes16 = (int)((size_t)h->L.n_carriers * h->L.grid_w * 2 / 16);
     A.stage_grid = stage_grid; A.blk = h->blk_dev;
+    A.deal_order = nullptr; A.deal_len = nullptr; A.deal_cnt = nullptr; A.deal_lists = 0; A.deal_stride = 0; A.dur = nullptr;
     A.smem_per_warp = (int)sizeof(NbCtx) + A.hdr_bytes16 * 16 + (stage_grid ? A.grid_bytes16 * 16 : 0);
     return A;
 }
@@ -193,6 +240,14 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
     }
     else if (mode == 2) {
         const NbSimVariant *v = sim_variant(h, stage);
+        if (stage && h->deal && blocks * NB_WPB >= h->n_inst) {     /* a long launch in one wave: deal the cells to the SMs by predicted cost */
+            nbiot_deal_kernel<<<1, 1024, (size_t)h->deal_pad * sizeof(unsigned long long), st>>>((const NbHdr *)(h->state + h->L.off_hdr), h->dur_dev, active, h->n_inst,
+                                                                                                 h->deal_pad, h->deal_lists, h->deal_stride, h->deal_order, h->deal_len, h->deal_cnt);
+            CK(cudaGetLastError());
+            h->launches += 1;
+            A.deal_order = h->deal_order; A.deal_len = h->deal_len; A.deal_cnt = h->deal_cnt; A.deal_lists = h->deal_lists; A.deal_stride = h->deal_stride;
+        }
+        if (stage) A.dur = h->dur_dev;
         void *args[] = { (void *)&A, (void *)&ext_actions, (void *)&active, (void *)&until_time, (void *)&max_steps };
         CK(cudaLaunchKernel(hi ? v->sim_hi : v->sim_lo, dim3(blocks), dim3(NB_WPB * 32), args, (size_t)smem, st));
     } else {
@@ -269,6 +324,22 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
      * lanes; one thread per cell shares every common instruction between 32 cells but needs the cells to fill the machine
      * (148 SMs x 16 warps x 32 lanes = 75 776) -- DESIGN.md section 6c has the measured crossover. */
     h->use_tpc = n_inst >= NB_TPC_MIN_CELLS ? 2 : 0;
+    /* dealing by predicted cost for batches that run their long launches in one wave: measured 1.7 % SLOWER on configs[1] (a cell's
+     * duration in a step is mostly that step's fresh randomness, and the launch ends with its slowest CELL, not its most loaded SM:
+     * profiles/r02_tail.txt), so it is off unless NBIOT_DEAL=1 */
+    h->deal = 0;
+    if (n_inst <= NB_DEAL_MAX && n_inst >= 2 * prop.multiProcessorCount && getenv("NBIOT_DEAL") && atoi(getenv("NBIOT_DEAL"))) {
+        h->deal_lists = prop.multiProcessorCount;
+        h->deal_pad = 2; while (h->deal_pad < n_inst) h->deal_pad <<= 1;
+        h->deal_stride = (h->deal_pad + h->deal_lists - 1) / h->deal_lists + 1;
+        CK(cudaMalloc(&h->dur_dev, sizeof(uint32_t) * (size_t)n_inst));
+        CK(cudaMemsetAsync(h->dur_dev, 0, sizeof(uint32_t) * (size_t)n_inst, st));
+        CK(cudaMalloc(&h->deal_order, sizeof(int32_t) * (size_t)h->deal_lists * h->deal_stride));
+        CK(cudaMalloc(&h->deal_len, sizeof(int32_t) * (size_t)h->deal_lists));
+        CK(cudaMalloc(&h->deal_cnt, sizeof(unsigned int) * (size_t)h->deal_lists));
+        CK(cudaFuncSetAttribute(nbiot_deal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NB_DEAL_MAX * (int)sizeof(unsigned long long)));
+        h->deal = 1;
+    }
     /* block summaries of the look-ahead ring for the thread-per-cell kernel (nbiot_core.cuh): 8 % fewer executed instructions and 3-4 %
      * SLOWER on the sweep configuration (the kernel waits on memory, and the summaries are one more scattered region per cell):
      * off unless NBIOT_TPC_BLK=1 (profiles/r02_tpc_variants.txt) */
@@ -328,7 +399,7 @@ int nbiot_destroy(nbiot_handle_t *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->conf_dev); cudaFree(h->ctrl_dev); cudaFree(h->lut2_dev); cudaFree(h->mcs_dev); cudaFree(h->seeds_dev); cudaFree(h->counter_dev); cudaFree(h->prof_dev); cudaFree(h->blk_dev);
+    cudaFree(h->conf_dev); cudaFree(h->ctrl_dev); cudaFree(h->lut2_dev); cudaFree(h->mcs_dev); cudaFree(h->seeds_dev); cudaFree(h->counter_dev); cudaFree(h->prof_dev); cudaFree(h->blk_dev); cudaFree(h->dur_dev); cudaFree(h->deal_order); cudaFree(h->deal_len); cudaFree(h->deal_cnt);
     cudaFree(h->act_dev); cudaFree(h->obs_dev); cudaFree(h->rew_dev); cudaFree(h->items_dev);
     cudaFreeHost(h->act_pin); cudaFreeHost(h->obs_pin); cudaFreeHost(h->rew_pin);
     delete h;

@@ -22,6 +22,10 @@ struct NbKernelArgs {
     int smem_per_warp, hdr_bytes16, grid_bytes16;
     int stage_grid;              /* 1: the look-ahead ring is staged in shared memory; 0: used in place in HBM (short launches) */
     uint16_t *blk;               /* thread-per-cell kernel: [n_inst][C][W / 32] block summaries of the rings (derived data, rebuilt every launch) */
+    /* one-wave launches of the warp-per-cell kernel: cells dealt to SMs by predicted cost (nbiot_deal_kernel). deal_order[sm][k] = k-th cell of
+     * SM sm's list, deal_len[sm] its length, deal_cnt[sm] the claim counter; NULL: cells are claimed in index order from `counter`. */
+    const int32_t *deal_order; const int32_t *deal_len; unsigned int *deal_cnt; int deal_lists, deal_stride;
+    uint32_t *dur;               /* per cell: duration of its last long launch in ns (the cost predictor's memory); NULL: not recorded */
 };
 
 

@@ -32,6 +32,30 @@
 #define NB_CAT(a, b) NB_CAT2(a, b)
 namespace NB_CAT(nbk_, NB_SIM_VARIANT) {     /* the kernels of this build: nbk_generic::nbiot_sim_kernel<7>, nbk_c1::nbiot_sim_kernel<7>, ... */
 
+/* Dealt launches (nbiot_deal_kernel): cells were dealt to SMs so that every SM holds the same predicted work. Take the next cell of the list
+ * of the SM this warp runs on; a warp whose list is used up (the block scheduler gave its SM more warps than the list has cells) takes what other
+ * lists have left. Returns n_inst when nothing is left anywhere. The loop is WARP-UNIFORM -- lane 0 claims, every lane follows the outcome --
+ * so that no lane leaves a loop the others never entered (a lane-0-only probing loop with a break in it left the warp's convergence state
+ * in a condition the simulation core did not survive: hangs and illegal-instruction faults as soon as a warp had to probe a second list). */
+__device__ __forceinline__ int nb_claim_dealt(const NbKernelArgs &A, int lane, int &probe)
+{
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    _Pragma("unroll 1")
+    while (probe < A.deal_lists) {
+        int got = -1;
+        if (lane == 0) {
+            const unsigned int s2 = (smid + (unsigned int)probe) % (unsigned int)A.deal_lists;
+            const unsigned int slot = atomicAdd(&A.deal_cnt[s2], 1u);
+            if ((int)slot < A.deal_len[s2]) got = A.deal_order[(size_t)s2 * A.deal_stride + slot];
+        }
+        got = __shfl_sync(0xFFFFFFFFu, got, 0);
+        if (got >= 0) return got;
+        probe += 1;
+    }
+    return A.L.n_inst;
+}
+
 /* Claim instances from the work counter; stage [ctx | header | grid] in this warp's shared-memory slice;
  * run `body`; write header and grid back. */
 template <bool LOAD, class Body>
@@ -49,10 +73,14 @@ __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, cons
     uint16_t *grid_g = (uint16_t *)(A.state + A.L.off_grid);
     const size_t grid_elems = (size_t)A.L.n_carriers * A.L.grid_w;
     if (lane == 0) nb_fill_ctx_launch(c, A, &s_ctrl);
+    int probe = 0;                                     /* dealt launches: lists tried so far (own SM's first, then the others') */
     for (;;) {
         int i = 0;
-        if (lane == 0) i = (int)atomicAdd(A.counter, 1u);
-        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (A.deal_order) i = nb_claim_dealt(A, lane, probe);
+        else {
+            if (lane == 0) i = (int)atomicAdd(A.counter, 1u);
+            i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        }
         if (i >= A.L.n_inst) break;
         if (active && !active[i]) continue;
         if (lane == 0) nb_fill_ctx(c, A, i);
@@ -66,8 +94,13 @@ __device__ __forceinline__ void nb_for_each_instance(const NbKernelArgs &A, cons
         }
         __syncwarp();
         unsigned long long t0 = 0;
-        if (A.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        if (A.prof || A.dur) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         body(c, i);
+        if (A.dur && lane == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            A.dur[i] = (uint32_t)(t1 - t0);
+        }
         if (A.prof && lane == 0) {
             unsigned long long t1; unsigned int smid;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));

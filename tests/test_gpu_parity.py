@@ -643,3 +643,31 @@ def test_info_lists_longer_than_the_record():
     assert info['receptions'] == rx and info['errors'] == err and info['unfit'] == unfit and info['access'] == acc
     assert env.stats()['truncated'] == 0 and env.stats()['faulted'] == 0
     env.close()
+
+
+def test_dealing_cells_to_sms_changes_nothing(monkeypatch):
+    """One-wave long launches of the warp-per-cell kernel deal the cells to the SMs by predicted cost (nbiot_deal_kernel: the cell's previous
+    duration + the length of its random-access lists, sorted and dealt in snake order). Which warp of which SM runs a cell never changes
+    a result: same state buffer with the dealing off, masked advances included."""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    N = 1000
+    states = []
+    for deal in ('1', '0'):
+        monkeypatch.setenv('NBIOT_DEAL', deal)
+        monkeypatch.setenv('NBIOT_KERNEL', 'warp')
+        env = BatchedNBIoTEnv(dict(CFG1, ratio=0.5), agents_conf=NPRACH_AGENTS, ext_agent=3, num_envs=N, seeds=list(range(N)), ue_cap=1000, grid_w=2048, hist_cap=512)
+        env.reset()
+        r = np.random.default_rng(33)
+        for k in range(5):
+            a = _random_ext_actions(r, env.action_nvec, N)
+            if k == 3:
+                env.step(a, active=torch.as_tensor(r.integers(0, 2, size=N).astype(bool)))
+            else:
+                env.step(a)
+        env.run_until(18000)
+        torch.cuda.synchronize()
+        states.append(env.state.cpu().numpy().copy()); assert env.stats()['faulted'] == 0
+        assert (env.records()['time'] >= 15000).all()
+        env.close()
+    assert np.array_equal(states[0], states[1])
