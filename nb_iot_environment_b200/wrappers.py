@@ -225,6 +225,13 @@ class BasicSchedulerWrapper(_Wrapper):
         return obs, reward, terminated, truncated, infos
 
 
+class BasicWrapper(BasicSchedulerWrapper):
+    """reference BasicWrapper (wrappers.py:47-82): the agent only selects the UE; no penalty for grants that do not fit"""
+
+    def __init__(self, env):
+        super().__init__(env, select_only=True)
+
+
 class DiscreteActions(_Wrapper):
     """reference DiscreteActions (wrappers.py:355-363)"""
 
@@ -311,3 +318,21 @@ class NPRACHAgentWrapper(_Wrapper):
             self.arrival_history = torch.cat([self.arrival_history[:, 1:], self.agent.lambda_estimate[:, None].clone()], dim=1)
         self.obs = self._reduce(obs)
         return self.obs, self.r, terminated, truncated, infos
+
+
+class NPRACHAgentWrapperTraces(NPRACHAgentWrapper):
+    """reference NPRACH_agent_wrapper_traces (wrappers.py:321-353): the running mean of every metric the agent samples, updated
+    incrementally after each step as the reference does (avg += (sample - avg) / n), one float64[N] tensor per metric on the
+    device. The log file of the reference class is a host convenience and is not restated."""
+
+    def __init__(self, env, agent, **kw):
+        super().__init__(env, agent, **kw)
+        self.averages = {m: torch.zeros(self.num_envs, dtype=torch.float64, device=self.device) for m in self.samples}
+
+    def step(self, action):
+        out = super().step(action)
+        for metric, samples in self.samples.items():
+            if samples:
+                avg = self.averages[metric]
+                self.averages[metric] = avg + self._div(samples[-1] - avg, self.n)
+        return out

@@ -117,7 +117,7 @@ def test_agent_closed_loop_on_device_matches_reference():
     from test_gpu_parity import NPRACH_AGENTS
     from nb_iot_environment_b200 import BatchedNBIoTEnv
     from nb_iot_environment_b200.mb_agent import BatchedNPRACHAgent
-    from nb_iot_environment_b200.wrappers import NPRACHAgentWrapper
+    from nb_iot_environment_b200.wrappers import NPRACHAgentWrapperTraces as NPRACHAgentWrapper       # the plain wrapper + running means
     z, meta = _golden()
     for ci, m in enumerate(meta['loops']):
         p = f'loop_{ci}'
@@ -137,5 +137,9 @@ def test_agent_closed_loop_on_device_matches_reference():
         for name, key in (('departures', 's_departures'), ('NPRACH_occupation', 's_occupation'), ('service_times', 's_service'), ('beta', 's_beta')):
             got = np.asarray([x.cpu().numpy()[0] for x in agent.samples[name]])
             np.testing.assert_allclose(got, z[f'{p}_{key}'], rtol=1e-9, atol=1e-12, err_msg=f'{p} samples {name}')
+            avg = 0.0                                            # NPRACH_agent_wrapper_traces.step (wrappers.py:337-340) on the reference's samples
+            for n, sample in enumerate(z[f'{p}_{key}'], start=1):
+                avg += (float(sample) - avg) / n
+            np.testing.assert_allclose(w.averages[name].cpu().numpy()[0], avg, rtol=1e-9, atol=1e-12, err_msg=f'{p} running mean {name}')
         assert agent.faults() == 0
         agent.close(); env.close()

@@ -66,6 +66,25 @@ def _check_npusch(make_env):
     assert n_impossible > 0       # ... and the answer-without-stepping branch
 
 
+def _check_basic(make_env):
+    """BasicWrapper of the reference (wrappers.py:47-82: UE selection only, scalar action) over agent 0 of the six default agents"""
+    from nb_iot_environment_b200.wrappers import BasicWrapper
+    meta, acts, obs, rew = _load('wrappers_basic')
+    env = BasicWrapper(make_env(meta['conf'], None, 0, meta['seeds']))
+    assert list(env.action_nvec) == [4]
+    env.reset()
+    n_impossible = 0
+    for k in range(acts[0].shape[0]):
+        a = np.asarray([[acts[i][k]] for i in range(len(acts))])
+        o, r, _, _, _ = env.step(a)
+        o, r = o.cpu().numpy(), r.cpu().numpy()
+        n_impossible += int(env.last_impossible.sum())
+        for i in range(len(acts)):
+            assert np.allclose(o[i], obs[i][k + 1], rtol=REF_RTOL, atol=1e-12), (k, i)
+            assert r[i] == pytest.approx(rew[i][k], rel=1e-12), (k, i)
+    assert n_impossible > 0
+
+
 def _check_rar(make_env):
     """RAR_wrapper of the reference (wrappers.py:366-421) on its own environment, both reward criteria, against RARWrapper"""
     from nb_iot_environment_b200.wrappers import RARWrapper
@@ -111,6 +130,15 @@ def test_nprach_wrapper_on_oracle(oracle_lib):
 
 def test_scheduler_wrapper_on_oracle(oracle_lib):
     _check_npusch(_oracle_env)
+
+
+def test_basic_wrapper_on_oracle(oracle_lib):
+    _check_basic(_oracle_env)
+
+
+@pytest.mark.gpu
+def test_basic_wrapper_on_cuda():
+    _check_basic(_cuda_env)
 
 
 def test_rar_wrapper_on_oracle(oracle_lib):

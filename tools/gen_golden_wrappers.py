@@ -4,6 +4,7 @@ driven by random wrapper-level actions: tests/golden/wrappers_*.npz.  Build cont
 
   nprach : scripts/nprach set-up (evaluate_RL.py:46-131): NPRACH_wrapper over agent 3, MultiDiscrete([105,4,4,4,6,6,6])
   npusch : scripts/npusch set-up (experiments_RL.py:40-131): BasicSchedulerWrapper + DiscreteActions over agent 0
+  basic  : BasicWrapper (wrappers.py:47-82) over agent 0 of the reference's six default agents (control_agents.py:29-71: UE selection only)
   rar    : RAR_wrapper (wrappers.py:366-421) over agent 1 of the scripts/nprach agent set, reward criteria 'msg3' and 'departures'
 """
 import json, os, sys
@@ -64,6 +65,20 @@ def main():
             acts.append(a); obs.append(np.asarray(o, float)); rew.append(float(r))
         res[f'acts_{si}'] = np.asarray(acts, np.int64); res[f'obs_{si}'] = np.asarray(obs); res[f'rew_{si}'] = np.asarray(rew)
     np.savez_compressed(os.path.join(out, 'wrappers_npusch.npz'), meta=np.frombuffer(json.dumps({'conf': CFG3, 'seeds': [510, 511]}).encode(), dtype=np.uint8), **res)
+    # ---- BasicWrapper: the agent selects the UE only (scalar action); default agents of control_agents.py
+    import control_agents
+    res = {}
+    for si, seed in enumerate([530, 531]):
+        env = W.BasicWrapper(make_env(m, CFG1, control_agents.agents_conf, 0, seed))
+        rng = np.random.default_rng(seed)
+        obs0, _ = env.reset()
+        acts, obs, rew = [], [np.asarray(obs0, float)], []
+        for _ in range(500):
+            a = int(rng.integers(0, 4))
+            o, r, _, _, info = env.step(a)
+            acts.append(a); obs.append(np.asarray(o, float)); rew.append(float(r))
+        res[f'acts_{si}'] = np.asarray(acts, np.int64); res[f'obs_{si}'] = np.asarray(obs); res[f'rew_{si}'] = np.asarray(rew)
+    np.savez_compressed(os.path.join(out, 'wrappers_basic.npz'), meta=np.frombuffer(json.dumps({'conf': CFG1, 'seeds': [530, 531]}).encode(), dtype=np.uint8), **res)
     # ---- RAR wrapper (reference wrappers.py:366-421) over agent 1 (RAR_window: ce_level, rar_Imcs, Nrep), both reward criteria
     conf = dict(CFG1, ratio=0.5, ce_mcs_automatic=False)
     res = {}
