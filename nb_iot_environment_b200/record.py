@@ -129,6 +129,9 @@ def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_c
             raise NotImplementedError(f"conf['{k}']=True is outside the batched hot path (SURVEY.md section 8)")
     crit = conf['reward_criteria']
     if crit not in REWARD_IDS:
+        # 'average_total_delay' (perf_monitor.py:264-274) is the one criterion of the reference that is absent here: the reference itself
+        # fails on it -- it looks every served UE up in ue_access_times, which clear_info (:96-103) empties at each scheduling step, so the
+        # first reception of a UE that connected in an earlier step raises KeyError (step 2 of configs[0] with the default agents)
         raise NotImplementedError(f"reward_criteria '{crit}' is not supported")
     sort = conf.get('sort_criterium', 't_connection')
     if sort not in ('t_connection', 'loss'):

@@ -1,0 +1,105 @@
+"""Fuzz: random configurations (tests/fuzz_confs.py) under a random NodeB-level policy.
+ - the C oracle against the LIVE unmodified reference, decision by decision (build container only: needs /root/reference)
+ - the kernel source on the CPU (1 lane and 32 emulated lanes) against the oracle
+ - the CUDA kernels through the C ABI against the oracle (-m gpu)
+None of the cases is in a golden fixture."""
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import record_diff, REF_RTOL
+from fuzz_confs import fuzz_case, random_action
+
+REFERENCE = os.environ.get('NBIOT_REFERENCE', '/root/reference')
+CAPS = dict(grid_w=4096, hist_cap=1024)
+
+
+def _drive(make_a, make_b, k, seeds, decisions, rtol, what):
+    conf, nc, cap = fuzz_case(k)
+    a, b = make_a(conf, nc, cap, seeds), make_b(conf, nc, cap, seeds)
+    ra, rb = a.reset(), b.reset()
+    prng = np.random.default_rng(100 + k)
+    for d in range(decisions + 1):
+        for i in range(len(seeds)):
+            diff = record_diff(ra[i], rb[i], rtol=rtol)
+            assert not diff, f'{what} case {k} {conf} carriers {nc} capture {cap} seed {seeds[i]} decision {d}: {diff[:3]}'
+        assert not (np.asarray([r['fault'] for r in rb]) & 0x1F).any(), f'{what} case {k}: fault'
+        acts = np.asarray([random_action(int(ra[i]['state']), prng, nc) for i in range(len(seeds))], dtype=np.uint8)
+        ra, rb = a.step(acts), b.step(acts)
+    return a, b
+
+
+class _Oracles:
+    def __init__(self, conf, nc, cap, seeds):
+        from oracle.oracle_py import OracleCell
+        self.cells = [OracleCell(conf, s, n_carriers=nc, capture_effect=cap) for s in seeds]
+
+    def reset(self):
+        return [c.reset() for c in self.cells]
+
+    def step(self, acts):
+        return [c.step(a) for c, a in zip(self.cells, acts)]
+
+
+class _Emu:
+    def __init__(self, lanes):
+        self.lanes = lanes
+
+    def __call__(self, conf, nc, cap, seeds):
+        from hostemu_py import EmuBatch
+        self.b = EmuBatch(conf, seeds, n_carriers=nc, lanes=self.lanes, capture_effect=cap, ue_cap=conf['M'], **CAPS)
+        return self
+
+    def reset(self):
+        return self.b.reset()
+
+    def step(self, acts):
+        recs, steps = self.b.advance(acts, max_steps=1)
+        assert (steps == 1).all()
+        return recs
+
+
+class _Cuda:
+    def __call__(self, conf, nc, cap, seeds):
+        from nb_iot_environment_b200 import BatchedNBIoTEnv
+        self.env = BatchedNBIoTEnv(conf, num_envs=len(seeds), seeds=seeds, n_carriers=nc, all_states_external=True, capture_effect=cap, ue_cap=conf['M'], **CAPS)
+        return self
+
+    def reset(self):
+        self.env.reset()
+        return self.env.records()
+
+    def step(self, acts):
+        self.env.node_step(acts)
+        return self.env.records()
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason='the live reference is only present in the build container')
+@pytest.mark.parametrize('k', range(6))
+def test_oracle_against_the_live_reference(k, oracle_lib):
+    """in a process of its own: the reference fixes its carrier count at import time and puts top-level modules on sys.path"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'fuzz_ref_oracle.py'), str(k), '500'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize('k', range(6, 14))
+def test_kernel_source_on_the_cpu_against_the_oracle(k, oracle_lib):
+    _drive(_Oracles, _Emu(1), k, [7100 + k, 7200 + k], 500, 0.0, 'oracle vs core (1 lane)')
+    if k % 4 == 2:
+        _drive(_Oracles, _Emu(32), k, [7300 + k], 150, 0.0, 'oracle vs core (32 lanes)')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kernel', ['warp', 'tpcv'])
+def test_cuda_against_the_oracle(kernel, monkeypatch):
+    import __graft_entry__ as g
+    g.build_cuda()
+    monkeypatch.setenv('NBIOT_KERNEL', kernel)
+    for k in range(14, 26):
+        _, b = _drive(_Oracles, _Cuda(), k, [7400 + k, 7500 + k, 7600 + k], 400, 0.0, f'oracle vs CUDA ({kernel})')
+        assert b.env.stats()['faulted'] == 0
+        b.env.close()
