@@ -404,26 +404,37 @@ NB_DEV int nbc_res_next_start(NbResource &r, int col)
     return cand + r.t_offset;
 }
 
-NB_DEV void nbc_sclog_register(NbCtx &c, int t, int ce, int sc)   /* carrier.py:262-265 */
+/* CElevelSClog (carrier.py:254-271): the reference keeps {t: subcarriers per CE level} for every non-anchor NPRACH start it ever
+ * generated and asks for it once, when the anchor NPRACH of time t starts. Entries whose time the clock has passed are never read
+ * again, so a ring in the cell's cold block holds the live ones: up to NB_SCLOG_CAP (a long look-ahead over short periods
+ * holds hundreds), faulting loudly beyond. Only the FIRST registration of a time counts, as in the reference (:262-265). */
+NB_DEV NbSclogEntry *nbc_sclog_ring(NbCtx &c)
+{
+    const NbColdConf *cold = (const NbColdConf *)&((const NbCtaConst *)c.ctrl)->cold;
+    return cold->sclog_base + (size_t)(c.occ - cold->occ_base) * (size_t)NB_SCLOG_CAP;
+}
+
+NB_FN void nbc_sclog_register(NbCtx &c, int t, int ce, int sc)   /* carrier.py:262-265 */
 {
     NbHdr *h = nbc_hdr(c);
-    int n = h->sclog_n < NB_SCLOG ? h->sclog_n : NB_SCLOG;
+    NbSclogEntry *ring = nbc_sclog_ring(c);
     NB_NOUNROLL
-    for (int i = 0; i < n; ++i) if (h->sclog_t[i] == t) return;
-    int w = h->sclog_n % NB_SCLOG;               /* ring: entries older than the oldest pending occasion are dead */
-    h->sclog_t[w] = t;
-    h->sclog_sc[w][0] = h->sclog_sc[w][1] = h->sclog_sc[w][2] = 0;
-    h->sclog_sc[w][ce] = (uint8_t)sc;
+    while (h->sclog_lo < h->sclog_n && ring[h->sclog_lo % NB_SCLOG_CAP].t < h->time) h->sclog_lo += 1;      /* passed by the clock */
+    NB_NOUNROLL
+    for (int i = h->sclog_lo; i < h->sclog_n; ++i) if (ring[i % NB_SCLOG_CAP].t == t) return;
+    if (h->sclog_n - h->sclog_lo >= NB_SCLOG_CAP) { NB_FAULT(c, NBIOT_FAULT_LOOKAHEAD); return; }
+    NbSclogEntry e; e.t = t; e.sc[0] = e.sc[1] = e.sc[2] = e.sc[3] = 0; e.sc[ce] = (uint8_t)sc;
+    ring[h->sclog_n % NB_SCLOG_CAP] = e;
     h->sclog_n += 1;
 }
 
-NB_DEV int nbc_sclog_check(NbCtx &c, int t, int ce)               /* carrier.py:267-271, :454-459 */
+NB_FN int nbc_sclog_check(NbCtx &c, int t, int ce)               /* carrier.py:267-271, :454-459 */
 {
     NbHdr *h = nbc_hdr(c);
     if (NB_NC(c) == 1 || t == 0) return 0;
-    int n = h->sclog_n < NB_SCLOG ? h->sclog_n : NB_SCLOG;
+    const NbSclogEntry *ring = nbc_sclog_ring(c);
     NB_NOUNROLL
-    for (int i = 0; i < n; ++i) if (h->sclog_t[i] == t) return h->sclog_sc[i][ce];
+    for (int i = h->sclog_lo; i < h->sclog_n; ++i) if (ring[i % NB_SCLOG_CAP].t == t) return ring[i % NB_SCLOG_CAP].sc[ce];
     return 0;
 }
 
@@ -2081,7 +2092,7 @@ NB_FN void nbc_reset(NbCtx &c)
     });
     h->free_top = cap;
     /* carrier_set.reset (carrier.py:430-444) */
-    h->t_now = 0; h->t_ahead = 0; h->sclog_n = 0; h->max_lookahead = 0; h->max_live = 0;
+    h->t_now = 0; h->t_ahead = 0; h->sclog_n = 0; h->sclog_lo = 0; h->max_lookahead = 0; h->max_live = 0;
     NB_NOUNROLL
     for (int cc = 0; cc < 2; ++cc)
         NB_NOUNROLL

@@ -303,7 +303,7 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     CK(cudaMemcpyAsync(h->conf_dev, conf, sizeof(nbiot_conf_t), cudaMemcpyHostToDevice, st));
     static_assert(sizeof(NbCtaConst) % 4 == 0, "NbCtaConst is staged word by word");
     NbCtaConst cd; memset(&cd, 0, sizeof cd);
-    cd.ctrl = nb_make_ctrl_dev(ctrl); cd.cold = nb_make_cold(conf, h->state, L.off_occ, L.off_stat, L.off_trace);
+    cd.ctrl = nb_make_ctrl_dev(ctrl); cd.cold = nb_make_cold(conf, h->state, L.off_occ, L.off_stat, L.off_trace, L.off_sclog);
     CK(cudaMemcpyAsync(h->ctrl_dev, &cd, sizeof(NbCtaConst), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->lut2_dev, lut2, NB_LUT_CURVES * NB_LUT_SNR_PTS * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->mcs_dev, mcs, NB_MCS_LOSS_ROWS * NB_N_TBS * 3, cudaMemcpyHostToDevice, st));

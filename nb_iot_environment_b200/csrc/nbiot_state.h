@@ -31,7 +31,8 @@
 #define NB_EV_POOL 48        /* pending RAR_window_end / Msg3 / NPUSCH_end events            */
 #define NB_OCC_RING 24       /* pending NPRACH occasions per CE level (look-ahead / 80 sf)   */
 #define NB_RAR_WIN 8         /* open RAR windows per CE level (300 sf window / 80 sf period) */
-#define NB_SCLOG 16          /* non-anchor NPRACH starts remembered (2-carrier cells)        */
+#define NB_SCLOG_CAP 512     /* non-anchor NPRACH starts not yet passed by the clock (2-carrier cells; cold ring in HBM): a
+                                4096-column look-ahead holds at most 3 x 4096 / 40 of them */
 #define NB_RA_SLACK 64       /* tombstones tolerated in a random-access list                 */
 #define NB_FIXED_KEYS 10      /* fixed event slots (9 used)                                   */
 #define NB_BLK_MAX 128       /* 32-column block summaries per carrier: grid_w <= 4096        */
@@ -97,6 +98,11 @@ typedef struct {            /* 64 B: reference system/user.py:35-70 minus never-
     uint8_t where, pad[7];
 } NbUe;
 
+typedef struct {            /* 8 B: carrier.py CElevelSClog entry: subcarriers a non-anchor NPRACH start at time t gave its CE level */
+    int32_t t;
+    uint8_t sc[4];
+} NbSclogEntry;
+
 typedef struct {            /* cold per-instance block in HBM: per-occasion NPRACH histories of the current update period,
                                clustered-placement memory (population.py:57-63), statistics cursor */
     int16_t det[3][NBIOT_MAX_OCC];
@@ -151,9 +157,7 @@ typedef struct __attribute__((aligned(16))) NbHdr {
     NbResource res[2][3];
     int32_t occ_head_start[3], occ_head_end[3], occ_tail[3];   /* ring cursors (monotone counters) */
     NbOccasion occ[3][NB_OCC_RING];
-    int32_t sclog_n;
-    int32_t sclog_t[NB_SCLOG];
-    uint8_t sclog_sc[NB_SCLOG][4];
+    int32_t sclog_n, sclog_lo;        /* cursors of the cold ring of non-anchor NPRACH starts (NbSclogEntry, monotone counters) */
     /* ---- population / access procedure ---- */
     int32_t ue_count, CE_thresholds[2], preamble_trans_max, MAC_timer;
     double probability_anchor;
@@ -205,6 +209,7 @@ typedef struct {
     nbiot_trace_rec_t *trace_base;        /* [n_inst][trace_cap] */
     int32_t trace_cap, trace_mask;
     int32_t capture_effect, pad_cold;     /* Channel(capture_effect=True), channel.py:124-126 */
+    NbSclogEntry *sclog_base;             /* [n_inst][NB_SCLOG_CAP], two-carrier batches only */
 } NbColdConf;
 
 /* per-CTA constants in shared memory: NbCtx.ctrl points at the first member */
@@ -228,13 +233,13 @@ static inline NbCtrlDev nb_make_ctrl_dev(const nbiot_ctrl_t *c)
 typedef struct {
     int32_t n_inst, ue_cap, grid_w, hist_cap, n_carriers, ra_cap, stat_cap, trace_cap;
     uint64_t off_hdr, off_grid, off_ra, off_conn, off_cont, off_ue, off_free, off_occ;
-    uint64_t off_incoming, off_delays, off_service, off_rec, off_scratch, off_stat, off_trace, off_spill, total;
+    uint64_t off_incoming, off_delays, off_service, off_rec, off_scratch, off_stat, off_trace, off_spill, off_sclog, total;
 } NbLayout;
 
 static inline uint64_t nb_align256(uint64_t x) { return (x + 255u) & ~(uint64_t)255u; }
 #define nb_spill_cap(hist_cap) ((hist_cap) > NBIOT_STEP_SPILL ? (hist_cap) : NBIOT_STEP_SPILL)   /* entries per spilled info list (host and device) */
 
-static inline NbColdConf nb_make_cold(const nbiot_conf_t *c, uint8_t *state, uint64_t off_occ, uint64_t off_stat, uint64_t off_trace)
+static inline NbColdConf nb_make_cold(const nbiot_conf_t *c, uint8_t *state, uint64_t off_occ, uint64_t off_stat, uint64_t off_trace, uint64_t off_sclog)
 {
     NbColdConf k;
     double range = c->max_d > 0 ? c->max_d : NB_MAX_RANGE;      /* channel.py:128-131 */
@@ -244,6 +249,7 @@ static inline NbColdConf nb_make_cold(const nbiot_conf_t *c, uint8_t *state, uin
     k.trace_base = (nbiot_trace_rec_t *)(state + off_trace);
     k.trace_cap = c->trace_cap > 0 ? c->trace_cap : 0; k.trace_mask = k.trace_cap ? c->trace_mask : 0;
     k.capture_effect = c->capture_effect ? 1 : 0; k.pad_cold = 0;
+    k.sclog_base = (NbSclogEntry *)(state + off_sclog);
     return k;
 }
 
@@ -269,6 +275,7 @@ static inline NbLayout nb_make_layout(const nbiot_conf_t *c, int n)
     L.off_stat = o;     o = nb_align256(o + N * 4u * (uint64_t)L.stat_cap * 4u);
     L.off_trace = o;    o = nb_align256(o + N * (uint64_t)L.trace_cap * sizeof(nbiot_trace_rec_t));
     L.off_spill = o;    o = nb_align256(o + N * 6u * (uint64_t)nb_spill_cap(L.hist_cap) * 4u);
+    L.off_sclog = o;    o = nb_align256(o + (L.n_carriers == 2 ? N * (uint64_t)NB_SCLOG_CAP * sizeof(NbSclogEntry) : 0u));
     L.total = o;
     return L;
 }

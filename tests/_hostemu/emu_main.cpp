@@ -94,7 +94,7 @@ void *emu_create(const nbiot_conf_t *conf, int n_inst, const uint64_t *seeds, co
     e->conf = *conf; e->cc.ctrl = nb_make_ctrl_dev(ctrl); e->lut2 = lut2; e->mcs = mcs;
     e->L = nb_make_layout(conf, n_inst);
     e->state = (uint8_t *)calloc(1, e->L.total);
-    e->cc.cold = nb_make_cold(conf, e->state, e->L.off_occ, e->L.off_stat, e->L.off_trace);
+    e->cc.cold = nb_make_cold(conf, e->state, e->L.off_occ, e->L.off_stat, e->L.off_trace, e->L.off_sclog);
     for (int i = 0; i < n_inst; ++i) { Staged st(e, i, false); nbc_construct(*st.c, seeds[i], &e->cc.ctrl); }
     return e;
 }

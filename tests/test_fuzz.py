@@ -76,7 +76,7 @@ class _Cuda:
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason='the live reference is only present in the build container')
-@pytest.mark.parametrize('k', range(6))
+@pytest.mark.parametrize('k', range(10))
 def test_oracle_against_the_live_reference(k, oracle_lib):
     """in a process of its own: the reference fixes its carrier count at import time and puts top-level modules on sys.path"""
     import subprocess
@@ -86,7 +86,7 @@ def test_oracle_against_the_live_reference(k, oracle_lib):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize('k', range(6, 14))
+@pytest.mark.parametrize('k', range(6, 16))
 def test_kernel_source_on_the_cpu_against_the_oracle(k, oracle_lib):
     _drive(_Oracles, _Emu(1), k, [7100 + k, 7200 + k], 500, 0.0, 'oracle vs core (1 lane)')
     if k % 4 == 2:
@@ -99,7 +99,7 @@ def test_cuda_against_the_oracle(kernel, monkeypatch):
     import __graft_entry__ as g
     g.build_cuda()
     monkeypatch.setenv('NBIOT_KERNEL', kernel)
-    for k in range(14, 26):
+    for k in range(10, 26):
         _, b = _drive(_Oracles, _Cuda(), k, [7400 + k, 7500 + k, 7600 + k], 400, 0.0, f'oracle vs CUDA ({kernel})')
         assert b.env.stats()['faulted'] == 0
         b.env.close()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """One fuzz case (tests/fuzz_confs.py) on the LIVE unmodified reference and on the C oracle, decision by decision.
-usage: python tools/fuzz_ref_oracle.py <case> [decisions]      (build container only: needs /root/reference)"""
+usage: python tools/fuzz_ref_oracle.py <case> [decisions] [seed,seed...]      (build container only: needs /root/reference)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -23,5 +23,6 @@ class References:
 
 
 k = int(sys.argv[1]); D = int(sys.argv[2]) if len(sys.argv) > 2 else 500
-a, b = test_fuzz._drive(References, test_fuzz._Oracles, k, [7000 + k], D, REF_RTOL, 'reference vs oracle')
+seeds = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [7000 + k]
+a, b = test_fuzz._drive(References, test_fuzz._Oracles, k, seeds, D, REF_RTOL, 'reference vs oracle')
 print('OK case', k, fuzz_case(k))
