@@ -30,7 +30,11 @@
 #define NBIOT_FAULT_MCS_KEY 0x8u      /* loss 171.4 has no loss_tbs_to_mcs row (App. C #9)   */
 #define NBIOT_FAULT_EVENT_SLOTS 0x10u /* more pending system events than slots               */
 #define NBIOT_FAULT_LIST_TRUNC 0x20u  /* an info list was truncated (simulation unaffected)  */
-#define NBIOT_FAULT_FATAL_MASK 0x1Fu
+#define NBIOT_FAULT_STALL 0x40u       /* an external step took NBIOT_STALL_STEPS NodeB steps without reaching a state of the external
+                                         agent (e.g. a UE-selection agent over a cell whose NPRACH configuration connects nobody): the
+                                         reference's Controller.to_next_step (controller.py:262-288) loops on for ever; the cell stops */
+#define NBIOT_FAULT_FATAL_MASK 0x5Fu
+#define NBIOT_STALL_STEPS 65536       /* NodeB steps inside one external step (hundreds to ~1500 in the reference's scenarios) */
 
 typedef struct nbiot_record {
     /* ---- doubles ---- */

@@ -2191,6 +2191,7 @@ NB_FN int nbc_controller_advance(NbCtx &c, const NbCtrlDev *ctrl, const uint8_t 
         steps += 1;
         if (NB_FATAL(c)) break;
         if ((ext_mask >> h->state) & 1u) { nbc_apply_writes(c, &sw[h->state]); break; }
+        if (ext_action && until_time < 0 && steps >= NBIOT_STALL_STEPS) { NB_FAULT(c, NBIOT_FAULT_STALL); break; }   /* never hang the GPU */
     }
     if (steps > 0) nbc_node_info(c, 1, nbc_reward(c));
     else c.rec->fault = h->fault;
@@ -2295,6 +2296,7 @@ NB_FN int nbc_task_glue(NbCtx &c)
         const NbWrites *sw = c.tk_internal ? ctrl->full_writes : ctrl->state_writes;
         if (!c.tk_internal && ((ctrl->ext_state_mask >> h->state) & 1u)) { nbc_apply_writes(c, &sw[h->state]); return NB_TK_FINISH; }
         if (!(h->tk_steps < c.tk_max_steps && !(c.tk_until >= 0 && h->time >= c.tk_until))) return NB_TK_FINISH;
+        if (!c.tk_internal && c.tk_until < 0 && h->tk_steps >= NBIOT_STALL_STEPS) { NB_FAULT(c, NBIOT_FAULT_STALL); return NB_TK_FINISH; }
         nbc_node_info(c, 0, 0.0);                              /* an internal agent looks at nothing */
         nbc_apply_writes(c, &sw[h->state]);
         h->tk_phase = NB_PH_FEL;

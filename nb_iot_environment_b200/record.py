@@ -16,8 +16,8 @@ N_ACTIONS = 23
 STATE_NAMES = ['Scheduling', 'NPRACH_update', 'RAR_window', 'RAR_window_end', 'Idle']   # NB_ST_* order
 STATE_IDS = {n: i for i, n in enumerate(STATE_NAMES)}
 
-FAULT_UE_SLOTS, FAULT_LOOKAHEAD, FAULT_ACTION, FAULT_MCS_KEY, FAULT_EVENT_SLOTS, FAULT_LIST_TRUNC = 1, 2, 4, 8, 16, 32
-FAULT_FATAL_MASK = 0x1F
+FAULT_UE_SLOTS, FAULT_LOOKAHEAD, FAULT_ACTION, FAULT_MCS_KEY, FAULT_EVENT_SLOTS, FAULT_LIST_TRUNC, FAULT_STALL = 1, 2, 4, 8, 16, 32, 64
+FAULT_FATAL_MASK = 0x5F
 
 # reward_criteria names of perf_monitor.py:29-38 -> NB_RW_*
 REWARD_IDS = {'throughput': 0, 'average_delay': 1, 'accumulated_delay': 2, 'users': 3,

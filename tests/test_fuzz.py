@@ -86,6 +86,18 @@ def test_oracle_against_the_live_reference(k, oracle_lib):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason='the live reference is only present in the build container')
+@pytest.mark.parametrize('k', [0, 3, 8, 14, 21, 33])
+def test_controller_split_against_the_live_reference(k, oracle_lib):
+    """Controller level: the reference's Controller + DummyAgents (random agent set, external agent, fixed and external actions, then
+    run_until) against the kernel source on the CPU driven through the write tables of nb_iot_environment_b200/controller.py"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'fuzz_ref_controller.py'), str(k), '120', '1tg' if k % 2 else '1'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize('k', range(6, 16))
 def test_kernel_source_on_the_cpu_against_the_oracle(k, oracle_lib):
     _drive(_Oracles, _Emu(1), k, [7100 + k, 7200 + k], 500, 0.0, 'oracle vs core (1 lane)')
@@ -103,3 +115,55 @@ def test_cuda_against_the_oracle(kernel, monkeypatch):
         _, b = _drive(_Oracles, _Cuda(), k, [7400 + k, 7500 + k, 7600 + k], 400, 0.0, f'oracle vs CUDA ({kernel})')
         assert b.env.stats()['faulted'] == 0
         b.env.close()
+
+
+# A cell that never reaches the external agent's state again: UE selection (Scheduling) is external, the internal RAR agent only ever
+# serves CE level 2 and the NPRACH thresholds put nobody there, so nobody connects. The reference's Controller.to_next_step
+# (controller.py:262-288) loops for ever on it (found by tools/fuzz_ref_controller.py, case 51); the cell must stop with a loud fault.
+STALL_CONF = {'M': 2111, 'ratio': 1.0, 'buffer_range': [97, 407], 'reward_criteria': 'accumulated_delay', 'sort_criterium': 'loss', 'sc_adjustment': False, 'max_d': 1.5}
+STALL_FIXED = [{'id': 2}, {'Imcs': 1, 'Nrep': 3}, {'carrier': 0, 'delay': 1, 'sc': 3}, {'carrier': 0, 'ce_level': 2, 'rar_Imcs': 1, 'delay': 1, 'sc': 3, 'Nrep': 2}, {'backoff': 0},
+               {'rar_window': 4, 'mac_timer': 4, 'transmax': 1, 'panchor': 6, 'period_C0': 1, 'rep_C0': 2, 'sc_C0': 2, 'period_C1': 5, 'rep_C1': 1, 'sc_C1': 0,
+                'period_C2': 1, 'rep_C2': 1, 'sc_C2': 1, 'th_C1': 2, 'th_C0': 2}]
+
+
+def _stall_steps(step, records):
+    from nb_iot_environment_b200.record import FAULT_STALL
+    prng = np.random.default_rng(3)
+    for s in range(60):
+        step(np.asarray([[0, int(prng.integers(0, 4)), 3]] * 2, dtype=np.uint8))
+        rec = records()
+        if rec['fault'].any():
+            break
+    assert (rec['fault'] == FAULT_STALL).all() and s < 59
+    assert (rec['state'] != 0).all()                      # stopped somewhere else than at a decision of the external agent
+    t = rec['time'].copy()
+    step(np.asarray([[0, 0, 3]] * 2, dtype=np.uint8))      # a faulted cell stands still
+    assert np.array_equal(records()['time'], t)
+
+
+@pytest.mark.parametrize('lanes', [1, '1tg'])
+def test_stalled_external_step_faults_on_the_cpu_build(lanes, oracle_lib):
+    from hostemu_py import EmuBatch
+    from nb_iot_environment_b200.controller import ControllerTables
+    tabs = ControllerTables(None, 2)
+    for a, f in zip(tabs.agents, STALL_FIXED):
+        a.set_action(f)
+    b = EmuBatch(STALL_CONF, [9051, 9051], lanes=lanes, ctrl=tabs.build(), ue_cap=STALL_CONF['M'], **CAPS)
+    b.reset()
+    _stall_steps(lambda a: b.advance(a), b.records)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kernel', ['warp', 'tpcv'])
+def test_stalled_external_step_faults_instead_of_hanging(kernel, monkeypatch):
+    import __graft_entry__ as g
+    g.build_cuda()
+    monkeypatch.setenv('NBIOT_KERNEL', kernel)
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    env = BatchedNBIoTEnv(STALL_CONF, agents_conf=None, ext_agent=2, num_envs=2, seeds=[9051, 9051], ue_cap=STALL_CONF['M'], **CAPS)
+    for aid, f in enumerate(STALL_FIXED):
+        env.set_internal_action(aid, f)
+    env.reset()
+    _stall_steps(lambda a: env.step(a), env.records)
+    assert env.stats()['faulted'] == 2
+    env.close()
