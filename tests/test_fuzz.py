@@ -129,12 +129,12 @@ STALL_FIXED = [{'id': 2}, {'Imcs': 1, 'Nrep': 3}, {'carrier': 0, 'delay': 1, 'sc
 def _stall_steps(step, records):
     from nb_iot_environment_b200.record import FAULT_STALL
     prng = np.random.default_rng(3)
-    for s in range(60):
+    for s in range(400):
         step(np.asarray([[0, int(prng.integers(0, 4)), 3]] * 2, dtype=np.uint8))
         rec = records()
         if rec['fault'].any():
             break
-    assert (rec['fault'] == FAULT_STALL).all() and s < 59
+    assert (rec['fault'] == FAULT_STALL).all() and s < 399
     assert (rec['state'] != 0).all()                      # stopped somewhere else than at a decision of the external agent
     t = rec['time'].copy()
     step(np.asarray([[0, 0, 3]] * 2, dtype=np.uint8))      # a faulted cell stands still
@@ -161,9 +161,11 @@ def test_stalled_external_step_faults_instead_of_hanging(kernel, monkeypatch):
     monkeypatch.setenv('NBIOT_KERNEL', kernel)
     from nb_iot_environment_b200 import BatchedNBIoTEnv
     env = BatchedNBIoTEnv(STALL_CONF, agents_conf=None, ext_agent=2, num_envs=2, seeds=[9051, 9051], ue_cap=STALL_CONF['M'], **CAPS)
-    for aid, f in enumerate(STALL_FIXED):
-        env.set_internal_action(aid, f)
     env.reset()
+    for aid, f in enumerate(STALL_FIXED):
+        env.set_internal_action(aid, f)                    # DummyAgent.set_action after the Controller exists: an agent's new action reaches the shared
+    env.run_until(6500)                                    # action vector when the agent next acts (controller.py:145-154) -- the NPRACH agent at t = 3000
+    assert env.stats()['faulted'] == 0
     _stall_steps(lambda a: env.step(a), env.records)
     assert env.stats()['faulted'] == 2
     env.close()
