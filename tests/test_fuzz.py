@@ -27,6 +27,11 @@ def _drive(make_a, make_b, k, seeds, decisions, rtol, what):
         assert not (np.asarray([r['fault'] for r in rb]) & 0x1F).any(), f'{what} case {k}: fault'
         acts = np.asarray([random_action(int(ra[i]['state']), prng, nc) for i in range(len(seeds))], dtype=np.uint8)
         ra, rb = a.step(acts), b.step(acts)
+    if hasattr(a, 'extras') and hasattr(b, 'extras'):       # the sample lists (traces / statistics) and the per-departure histories since reset
+        for i, (xa, xb) in enumerate(zip(a.extras(conf), b.extras(conf))):
+            assert set(xa) == set(xb)
+            for key in xa:
+                assert np.array_equal(xa[key], xb[key]), f'{what} case {k} seed {seeds[i]}: {key} differs'
     return a, b
 
 
@@ -40,6 +45,18 @@ class _Oracles:
 
     def step(self, acts):
         return [c.step(a) for c, a in zip(self.cells, acts)]
+
+    def extras(self, conf):
+        out = []
+        for c in self.cells:
+            x = {}
+            if conf.get('traces') or conf.get('statistics'):
+                x['samples'] = c.samples()
+            if conf.get('statistics'):
+                st = c.stats()
+                x.update({'stat_' + n: st[n] for n in ('delay', 'connection', 'access', 'bits')})
+            out.append(x)
+        return out
 
 
 class _Emu:
@@ -59,6 +76,20 @@ class _Emu:
         assert (steps == 1).all()
         return recs
 
+    def extras(self, conf):
+        out = []
+        for i in range(self.b.n):
+            x = {}
+            if conf.get('traces') or conf.get('statistics'):
+                rec, n = self.b.samples(i)
+                assert n == len(rec)
+                x['samples'] = rec
+            if conf.get('statistics'):
+                st = self.b.stats(i)
+                x.update({'stat_' + n: st[n] for n in ('delay', 'connection', 'access', 'bits')})
+            out.append(x)
+        return out
+
 
 class _Cuda:
     def __call__(self, conf, nc, cap, seeds):
@@ -73,6 +104,21 @@ class _Cuda:
     def step(self, acts):
         self.env.node_step(acts)
         return self.env.records()
+
+    def extras(self, conf):
+        out = [{} for _ in range(self.env.num_envs)]
+        if conf.get('traces') or conf.get('statistics'):
+            for x, (rec, n) in zip(out, self.env.samples()):
+                assert n == len(rec)
+                x['samples'] = rec
+        if conf.get('statistics'):
+            N, cap = self.env.num_envs, self.env.stat_cap
+            cnt = self.env.stat_counts().cpu().numpy()
+            raw = self.env.state[self.env._stat_off:self.env._stat_off + N * 4 * cap * 4].cpu().numpy().view(np.int32).reshape(N, 4, cap)
+            for i, x in enumerate(out):
+                assert cnt[i] <= cap
+                x.update({'stat_' + n: raw[i, j, :cnt[i]].copy() for j, n in enumerate(('delay', 'connection', 'access', 'bits'))})
+        return out
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason='the live reference is only present in the build container')
