@@ -42,3 +42,25 @@ def random_action(state, prng, nc):
     if state == 2:             # RAR_window: index 1 = ce_level (0..2), index 2 = rar_Imcs (0..2)
         a[1] = int(prng.integers(0, 3)); a[2] = int(prng.integers(0, 3))
     return a
+
+
+def controller_case(k):
+    """-> (conf, n_carriers, capture_effect, agents_conf, ext_agent, fixed actions per agent, rng for the external actions):
+    one of the agent sets of the reference's scripts, a random external agent, random fixed actions for the others"""
+    from nb_iot_environment_b200 import parameters as par
+    from test_gpu_parity import NPRACH_AGENTS, NPUSCH_AGENTS
+    conf, nc, cap = fuzz_case(k)
+    r = np.random.default_rng(50_000 + k)
+    agents = [par.agents_conf, NPRACH_AGENTS, NPUSCH_AGENTS][int(r.integers(0, 3))]
+    ext = int(r.integers(0, len(agents)))
+
+    def draw(name):
+        v = int(r.integers(0, par.control_max_values[name][nc - 1] + 1))
+        if name == 'backoff' and v == 12:
+            v = 11                                         # control_max_values allows 12, backoff_list has 12 entries: the reference raises IndexError
+        return 3 if name == 'sc' and v == 2 else v        # sc index 2 is the value the reference raises on (parameters.py:340)
+    fixed = [{n: draw(n) for n in a['action_items']} for a in agents]
+    for f in fixed:                                        # keep th_C1 <= th_C0 half of the time (both orders are legal)
+        if 'th_C1' in f and r.integers(0, 2):
+            f['th_C1'] = min(f['th_C1'], f['th_C0'])
+    return conf, nc, cap, agents, ext, fixed, draw

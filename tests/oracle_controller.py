@@ -9,9 +9,13 @@ from nb_iot_environment_b200.record import STATE_NAMES, record_to_info
 from oracle.oracle_py import OracleCell
 
 
+class Stalled(Exception):
+    pass
+
+
 class OracleController:
-    def __init__(self, conf, seed, agents_conf=None, ext_agent=-1, n_carriers=1):
-        self.cell = OracleCell(conf, seed, n_carriers=n_carriers)
+    def __init__(self, conf, seed, agents_conf=None, ext_agent=-1, n_carriers=1, capture_effect=False):
+        self.cell = OracleCell(conf, seed, n_carriers=n_carriers, capture_effect=capture_effect)
         self.t = ControllerTables(agents_conf, ext_agent, n_carriers)
         self.action = np.zeros(par.N_actions, dtype=np.int32)
         for ag in self.t.agents:                       # _initialize_action (controller.py:63-69)
@@ -59,10 +63,14 @@ class OracleController:
             nxt = self.t.agents[nxt].next
         self._node_step()
         state = STATE_NAMES[self.rec['state']]
+        steps = 1
         while state not in ext.states:
+            if steps >= 65536:                             # NBIOT_STALL_STEPS: the reference loops on for ever, the product faults
+                raise Stalled()
             for aid in self.t.agents_ids[state]:
                 self._update_action(aid)
             self._node_step()
+            steps += 1
             state = STATE_NAMES[self.rec['state']]
         for aid in self.t.agents_ids[state]:
             if aid == ext.id:

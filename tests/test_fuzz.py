@@ -144,6 +144,18 @@ def test_controller_split_against_the_live_reference(k, oracle_lib):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason='the live reference is only present in the build container')
+@pytest.mark.parametrize('k', [1, 9, 10, 11, 13])
+def test_batched_wrappers_against_the_live_reference(k, oracle_lib):
+    """the reference's gym wrappers over its own environment against nb_iot_environment_b200/wrappers.py over the CPU test double:
+    NPRACH (discrete, default-action replay), scheduler + DiscreteActions, basic, RAR (tools/fuzz_ref_wrappers.py; kind = k % 7)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'fuzz_ref_wrappers.py'), str(k)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize('k', range(6, 16))
 def test_kernel_source_on_the_cpu_against_the_oracle(k, oracle_lib):
     _drive(_Oracles, _Emu(1), k, [7100 + k, 7200 + k], 500, 0.0, 'oracle vs core (1 lane)')
@@ -215,3 +227,60 @@ def test_stalled_external_step_faults_instead_of_hanging(kernel, monkeypatch):
     _stall_steps(lambda a: env.step(a), env.records)
     assert env.stats()['faulted'] == 2
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kernel', ['warp', 'tpcv'])
+def test_controller_split_on_cuda_against_the_oracle(kernel, monkeypatch):
+    """Controller level on the GPU: random agent set / external agent / fixed actions (set after construction, as DummyAgent.set_action is),
+    observations from the device's gather kernel, rewards and records against the test-side restatement of the reference Controller"""
+    import __graft_entry__ as g
+    g.build_cuda()
+    monkeypatch.setenv('NBIOT_KERNEL', kernel)
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from nb_iot_environment_b200.record import FAULT_STALL
+    from oracle_controller import OracleController, Stalled
+    from fuzz_confs import controller_case
+    n_stalled = 0
+    for k in range(40):
+        conf, nc, cap, agents, ext, fixed, draw = controller_case(k)
+        seeds = [9000 + k, 9500 + k]
+        env = BatchedNBIoTEnv(conf, agents_conf=agents, ext_agent=ext, num_envs=2, seeds=seeds, n_carriers=nc, capture_effect=cap, ue_cap=conf['M'], **CAPS)
+        ctrls = [OracleController(conf, s, agents_conf=agents, ext_agent=ext, n_carriers=nc, capture_effect=cap) for s in seeds]
+        for aid, f in enumerate(fixed):
+            env.set_internal_action(aid, f)
+            for c in ctrls:
+                c.t.agents[aid].set_action(f)
+        obs, _ = env.reset()
+        obs = obs.cpu().numpy()
+        for i, c in enumerate(ctrls):
+            o = c.reset()
+            assert np.array_equal(o, obs[i][:len(o)]), (k, 'reset')
+        names = agents[ext]['action_items']
+        stalled = False
+        for s in range(100):
+            a = np.asarray([[draw(n) for n in names]] * 2, dtype=np.uint8)
+            obs, rew, _, _, _ = env.step(a)
+            obs, rew, recs = obs.cpu().numpy(), rew.cpu().numpy(), env.records()
+            for i, c in enumerate(ctrls):
+                try:
+                    o_obs, o_rew = c.step(a[i])
+                except Stalled:
+                    assert recs[i]['fault'] == FAULT_STALL, (k, s, i)
+                    stalled = True
+                    continue
+                assert np.array_equal(o_obs, obs[i][:len(o_obs)]) and o_rew == rew[i], (k, s, i)
+                assert not record_diff(c.rec, recs[i], rtol=0.0), (k, s, i)
+            if stalled:
+                break
+        n_stalled += stalled
+        if not stalled:
+            T = int(recs['time'].max()) + 3000
+            env.run_until(T)
+            recs = env.records()
+            for i, c in enumerate(ctrls):
+                c.run_until(T)
+                assert not record_diff(c.rec, recs[i], rtol=0.0), (k, 'run_until', i)
+            assert env.stats()['faulted'] == 0
+        env.close()
+    assert n_stalled <= 4

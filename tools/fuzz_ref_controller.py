@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np  # noqa: E402
 import conftest  # noqa: E402,F401
-from fuzz_confs import fuzz_case  # noqa: E402
+from fuzz_confs import controller_case  # noqa: E402
 from golden_util import record_diff, REF_RTOL  # noqa: E402
 from test_gpu_parity import NPRACH_AGENTS, NPUSCH_AGENTS  # noqa: E402
 from nb_iot_environment_b200 import parameters as par  # noqa: E402
@@ -20,24 +20,8 @@ from hostemu_py import EmuBatch  # noqa: E402
 k = int(sys.argv[1]); STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 lanes = sys.argv[3] if len(sys.argv) > 3 else 1
 lanes = int(lanes) if str(lanes).isdigit() else lanes
-conf, nc, cap = fuzz_case(k)
-r = np.random.default_rng(50_000 + k)
-agents = [par.agents_conf, NPRACH_AGENTS, NPUSCH_AGENTS][int(r.integers(0, 3))]
-ext = int(r.integers(0, len(agents)))
+conf, nc, cap, agents, ext, fixed, draw = controller_case(k)
 seed = 9000 + k
-
-
-def draw(name):
-    v = int(r.integers(0, par.control_max_values[name][nc - 1] + 1))
-    if name == 'backoff' and v == 12:
-        v = 11                                             # control_max_values allows 12, backoff_list has 12 entries: the reference raises IndexError
-    return 3 if name == 'sc' and v == 2 else v            # sc index 2 is the value the reference raises on (parameters.py:340)
-
-
-fixed = [{n: draw(n) for n in a['action_items']} for a in agents]
-for f in fixed:                                          # keep th_C1 <= th_C0 half of the time (both orders are legal)
-    if 'th_C1' in f and r.integers(0, 2):
-        f['th_C1'] = min(f['th_C1'], f['th_C0'])
 
 m = load_reference(nc)
 rng = PhiloxShim(seed)
