@@ -214,11 +214,18 @@ NB_DEV uint32_t nbc_scan_chunks(NbCtx &c, int carrier, int a, int n)
  * ring at the start of a launch (nbc_blk_rebuild), maintained by every fill, never part of the state (the warp-per-cell kernel, which
  * scans 32 columns per step, does not know them). A window then costs its two ragged ends plus one summary per whole block. */
 typedef uint64_t __attribute__((may_alias)) nb_u64a;
+typedef struct __attribute__((aligned(16), may_alias)) { uint64_t lo, hi; } nb_u128a;
 NB_DEV uint32_t nbc_cols_or(const uint16_t *g, int wm, int k, int e)
 {
     uint32_t v = 0; uint64_t v8 = 0;
     NB_NOUNROLL
     while (k < e && (k & 3)) { v |= g[k & wm]; ++k; }
+#ifndef NB_SCAN_8B
+    /* eight columns per 16-byte load once the index is a multiple of 8 (the ring is 16-byte aligned, W a multiple of 8) */
+    if ((k & 4) && k + 4 <= e) { v8 = *(const nb_u64a *)&g[k & wm]; k += 4; }
+    NB_NOUNROLL
+    for (; k + 8 <= e; k += 8) { const nb_u128a q = *(const nb_u128a *)&g[k & wm]; v8 |= q.lo | q.hi; }
+#endif
     NB_NOUNROLL
     for (; k + 4 <= e; k += 4) v8 |= *(const nb_u64a *)&g[k & wm];
     NB_NOUNROLL
