@@ -143,3 +143,51 @@ def test_agent_closed_loop_on_device_matches_reference():
             np.testing.assert_allclose(w.averages[name].cpu().numpy()[0], avg, rtol=1e-9, atol=1e-12, err_msg=f'{p} running mean {name}')
         assert agent.faults() == 0
         agent.close(); env.close()
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get('NBIOT_REFERENCE', '/root/reference')), reason='the live reference is only present in the build container')
+def test_agent_oracle_against_the_live_reference_agent():
+    """random inputs (tests/fuzz_agent.py) through the reference's NPRACH_THAgent and through its restatement, in a process of its own"""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_ref_agent.py'), '0', '12'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_agent_kernel_on_random_inputs_against_the_oracle():
+    """48 cells, each fed its own seeded random sequence of NPRACH_update records (idle to far overloaded, both agent variants):
+    the CUDA agent's actions, arrival estimate, sample counter and msg3 estimate against the restatement, floats bit for bit"""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from fuzz_agent import agent_sequence
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from nb_iot_environment_b200.mb_agent import BatchedNPRACHAgent
+    from nb_iot_environment_b200.record import RECORD_DTYPE
+    from oracle.mb_agent_oracle import OracleNPRACHAgent
+    for no_th in (False, True):
+        seqs = [s for f, s in (agent_sequence(k) for k in range(100, 200)) if f == no_th][:48]
+        N = len(seqs)
+        env = BatchedNBIoTEnv({'ratio': 1.0, 'M': 1000, 'buffer_range': [100, 600], 'reward_criteria': 'throughput'}, num_envs=N, seeds=list(range(N)),
+                              ue_cap=64, grid_w=256, hist_cap=64)
+        env.reset()
+        agent = BatchedNPRACHAgent(env, no_th=no_th)
+        orcs = [OracleNPRACHAgent(no_th=no_th) for _ in range(N)]
+        for s in range(60):
+            rows = np.zeros(N, dtype=RECORD_DTYPE)
+            for i, q in enumerate(seqs):
+                info = q[s]
+                rows[i]['state'] = 1
+                for ce in range(3):
+                    d, c = info['NPRACH_detection'][ce], info['NPRACH_collision'][ce]
+                    rows[i]['n_occ'][ce] = len(d); rows[i]['det_hist'][ce][:len(d)] = d; rows[i]['col_hist'][ce][:len(c)] = c
+                rows[i]['distribution'] = info['distribution']; rows[i]['n_incoming'] = len(info['incoming'])
+            _write_records(env, rows)
+            agent.set_parameter(np.asarray([q[s]['margin'] for q in seqs]))
+            act = agent.get_action().cpu().numpy()
+            lam, k, m3 = agent.lambda_estimate.cpu().numpy(), agent.k.cpu().numpy(), agent.msg3_detection.cpu().numpy()
+            for i, q in enumerate(seqs):
+                orcs[i].set_parameter(q[s]['margin'])
+                want = orcs[i].get_action(q[s])
+                assert act[i].tolist() == want, (no_th, i, s)
+                assert lam[i] == orcs[i].lambda_estimate and k[i] == orcs[i].k and m3[i].tolist() == [float(x) for x in orcs[i].msg3_detection], (no_th, i, s)
+        assert agent.faults() == 0
+        agent.close(); env.close()
