@@ -283,6 +283,8 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     if (conf->ue_cap < 1 || conf->ue_cap > 65535) return set_err(NBIOT_E_INVALID, "nbiot_create: ue_cap must be in 1..65535");
     if (conf->grid_w < 256 || conf->grid_w > 32 * NB_BLK_MAX || (conf->grid_w & (conf->grid_w - 1))) return set_err(NBIOT_E_INVALID, "nbiot_create: grid_w must be a power of two in 256..4096");
     if (conf->hist_cap < 1 || conf->n_carriers < 1 || conf->n_carriers > 2) return set_err(NBIOT_E_INVALID, "nbiot_create: bad hist_cap / n_carriers");
+    if (conf->M < 1 || !(conf->ratio >= 0.0)) return set_err(NBIOT_E_INVALID, "nbiot_create: M must be >= 1 and ratio >= 0");
+    if (conf->buffer_lo < 1 || conf->buffer_lo > 65535 || conf->buffer_hi > 65535) return set_err(NBIOT_E_INVALID, "nbiot_create: buffer range must lie in 1..65535 (a UE's buffer is held in 16 bits)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_err(NBIOT_E_NOGPU, "no CUDA device: this library has no CPU path");
     if (device < 0 || device >= ndev) return set_err(NBIOT_E_INVALID, "nbiot_create: bad device index");

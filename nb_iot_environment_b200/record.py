@@ -141,6 +141,13 @@ def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_c
     if grid_w & (grid_w - 1) or grid_w < 256 or grid_w > 4096:
         raise ValueError('grid_w must be a power of two in 256..4096')
     M = int(conf['M'])
+    lo_b, hi_b = int(conf['buffer_range'][0]), int(conf['buffer_range'][1])
+    if M < 1:
+        raise ValueError("conf['M'] must be >= 1")
+    if not 0 <= float(conf['ratio']):
+        raise ValueError("conf['ratio'] must be >= 0 (values above 1 act as 1, ue_generator.py:39)")
+    if not (0 < lo_b <= 65535 and hi_b <= 65535):        # hi <= lo is legal in the reference: every buffer is lo (ue_generator.py:98-104)
+        raise ValueError("conf['buffer_range'] must lie in 1..65535 (a UE's buffer is held in 16 bits)")
     c = NbiotConf()
     c.ratio = float(conf['ratio'])
     c.max_d = float(conf.get('max_d') or 0.0)

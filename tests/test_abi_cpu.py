@@ -105,6 +105,10 @@ def test_conf_validation():
         make_conf(dict(base, bogus=1))
     with pytest.raises(ValueError):
         make_conf(base, grid_w=1000)
+    for bad in (dict(buffer_range=[100, 70000]), dict(buffer_range=[0, 10]), dict(M=0), dict(ratio=-0.1)):
+        with pytest.raises(ValueError):
+            make_conf(dict(base, **bad))
+    assert make_conf(dict(base, buffer_range=[300, 200])).buffer_lo == 300          # legal in the reference: every buffer is 300 (ue_generator.py:98-104)
 
 
 def test_controller_tables_follow_reference_split():
