@@ -300,7 +300,8 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     CK(cudaMalloc(&h->lut2_dev, NB_LUT_CURVES * NB_LUT_SNR_PTS * sizeof(uint16_t)));
     CK(cudaMalloc(&h->mcs_dev, NB_MCS_LOSS_ROWS * NB_N_TBS * 3));
     CK(cudaMalloc(&h->seeds_dev, sizeof(uint64_t) * (size_t)n_inst));
-    CK(cudaMalloc(&h->counter_dev, sizeof(unsigned int)));
+    CK(cudaMalloc(&h->counter_dev, sizeof(unsigned int) * (1 + NB_SM_HINTS)));     /* [0]: claim counter of a launch; [1 + sm]: class hint of the voted kernel (measurement builds) */
+    CK(cudaMemsetAsync(h->counter_dev, 0, sizeof(unsigned int) * (1 + NB_SM_HINTS), st));
     if (getenv("NBIOT_PROF_INST") && atoi(getenv("NBIOT_PROF_INST"))) CK(cudaMalloc(&h->prof_dev, sizeof(unsigned long long) * 4 * (size_t)n_inst));
     CK(cudaMemcpyAsync(h->conf_dev, conf, sizeof(nbiot_conf_t), cudaMemcpyHostToDevice, st));
     static_assert(sizeof(NbCtaConst) % 4 == 0, "NbCtaConst is staged word by word");

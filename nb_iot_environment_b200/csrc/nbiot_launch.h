@@ -16,7 +16,7 @@ struct NbKernelArgs {
     const NbCtaConst *ctrl;      /* controller tables + cold configuration */
     const uint16_t *lut2;
     const uint8_t *mcs;
-    unsigned int *counter;
+    unsigned int *counter;          /* [0] claim counter, [1 .. NB_SM_HINTS] per-SM class hints (-DNB_TPC_AFFINITY_SM builds of the voted kernel) */
     unsigned long long *prof;    /* optional (NBIOT_PROF_INST=1): per instance { start ns, end ns, SM id, 0 } of the last launch (measurement aid) */
     int32_t *evlog; int evlog_cap;
     int smem_per_warp, hdr_bytes16, grid_bytes16;
@@ -82,6 +82,7 @@ void nb_sim_variant_c1s(NbSimVariant *out);
 void nb_sim_variant_tpc_gen(NbSimVariant *out);
 void nb_sim_variant_tpc_c1(NbSimVariant *out);
 #ifndef NB_TPC_MIN_CELLS
+#define NB_SM_HINTS 256
 #define NB_TPC_MIN_CELLS 32768      /* batches from this size on advance on the thread-per-cell kernel */
 #endif
 
