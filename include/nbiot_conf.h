@@ -50,8 +50,13 @@ typedef struct nbiot_conf {
     int32_t capture_effect;   /* Channel(capture_effect=True) (channel.py:124-126, :158-159, :200-219): a preamble chosen by several UEs
                                  can still be detected (states CAPTURE / COLLIDED), msg3 grants then carry several contenders.
                                  Not reachable through create_system (system_creator.py:51); a constructor argument here.     */
-    int32_t pad_conf;
+    int32_t kernel;           /* which kernel runs the LONG advances (many NodeB steps per launch; launches of one or two steps always run on the
+                                 warp-per-cell kernel): NBIOT_KERNEL_AUTO by batch size (thread-per-cell from 32 768 cells on), or forced.
+                                 Results are bit-identical; lightly loaded cells favour the thread-per-cell kernel (2.9e9 against 1.4e9
+                                 subframe-instances/s at 131 072 cells of configs[0] traffic), cells with hundreds of live UEs the
+                                 warp-per-cell one (1.01e9 against 0.87e9 at 65 536 cells of the configs[1] scenario)                 */
 } nbiot_conf_t;
+enum { NBIOT_KERNEL_AUTO = 0, NBIOT_KERNEL_WARP = 1, NBIOT_KERNEL_THREAD = 2, NBIOT_KERNEL_THREAD_VOTED = 3 };
 
 /* one sample of the ring (16 bytes), in the order the reference appends to its lists */
 enum { NBIOT_TR_NPRACH = 1, NBIOT_TR_MSG3 = 2, NBIOT_TR_RARWIN = 4, NBIOT_TR_RES_MSG3 = 8, NBIOT_TR_RES_NPUSCH = 16, NBIOT_TR_RES_NPRACH = 32,

@@ -347,7 +347,11 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
      * SLOWER on the sweep configuration (the kernel waits on memory, and the summaries are one more scattered region per cell):
      * off unless NBIOT_TPC_BLK=1 (profiles/r02_tpc_variants.txt) */
     if (getenv("NBIOT_TPC_BLK") && atoi(getenv("NBIOT_TPC_BLK"))) CK(cudaMalloc(&h->blk_dev, sizeof(uint16_t) * (size_t)n_inst * L.n_carriers * (L.grid_w >> 5)));
-    if (const char *e = getenv("NBIOT_KERNEL")) {
+    if (conf->kernel < NBIOT_KERNEL_AUTO || conf->kernel > NBIOT_KERNEL_THREAD_VOTED) return set_err(NBIOT_E_INVALID, "nbiot_create: conf.kernel must be one of NBIOT_KERNEL_*");
+    if (conf->kernel == NBIOT_KERNEL_WARP) h->use_tpc = 0;
+    else if (conf->kernel == NBIOT_KERNEL_THREAD) h->use_tpc = 1;
+    else if (conf->kernel == NBIOT_KERNEL_THREAD_VOTED) h->use_tpc = 2;
+    if (const char *e = getenv("NBIOT_KERNEL")) {              /* measurement override: tpc / tpcv also take the short launches */
         if (!strcmp(e, "tpc")) { h->use_tpc = 1; h->tpc_forced = 1; }
         else if (!strcmp(e, "tpcv")) { h->use_tpc = 2; h->tpc_forced = 1; }
         else if (!strcmp(e, "warp")) h->use_tpc = 0;

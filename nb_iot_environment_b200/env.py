@@ -115,11 +115,12 @@ class LazyInfos:
 class BatchedNBIoTEnv:
     """conf: the reference's conf dict (system/system_creator.py:24-44); agents_conf: list of agent dicts
     (control_agents.py:29-71; None = the reference's default six agents); ext_agent: index of the agent
-    that is driven from outside (-1: none, the cells run on their internal agents). capture_effect: Channel(capture_effect=True) of the
+    that is driven from outside (-1: none, the cells run on their internal agents). kernel: which kernel runs the long advances -- None / 'auto' (by batch size), 'warp', 'thread', 'thread_voted'
+    (results are bit-identical; include/nbiot_conf.h says which load favours which). capture_effect: Channel(capture_effect=True) of the
     reference (channel.py:124-126; create_system never sets it, so it is a constructor argument here too)."""
 
     def __init__(self, conf, agents_conf=None, ext_agent=-1, num_envs=1, seeds=None, n_carriers=1, device=0,
-                 ue_cap=None, grid_w=1024, hist_cap=256, all_states_external=False, stat_cap=None, trace_cap=None, capture_effect=False):
+                 ue_cap=None, grid_w=1024, hist_cap=256, all_states_external=False, stat_cap=None, trace_cap=None, capture_effect=False, kernel=None):
         if not torch.cuda.is_available():
             raise _cabi.NbiotError('BatchedNBIoTEnv needs a CUDA device: there is no CPU fallback')
         self.L = _cabi.load()
@@ -127,7 +128,7 @@ class BatchedNBIoTEnv:
         self.device = torch.device('cuda', device)
         self.conf = dict(conf)
         self.n_carriers = n_carriers
-        self.cconf = make_conf(conf, n_carriers=n_carriers, ue_cap=ue_cap, grid_w=grid_w, hist_cap=hist_cap, stat_cap=stat_cap, trace_cap=trace_cap, capture_effect=capture_effect)
+        self.cconf = make_conf(conf, n_carriers=n_carriers, ue_cap=ue_cap, grid_w=grid_w, hist_cap=hist_cap, stat_cap=stat_cap, trace_cap=trace_cap, capture_effect=capture_effect, kernel=kernel)
         self.tables = ControllerTables(agents_conf, ext_agent, n_carriers)
         self.all_states_external = bool(all_states_external)
         self.ctrl = self.tables.build(all_states_external=self.all_states_external)

@@ -64,7 +64,7 @@ class NbiotConf(ctypes.Structure):
                 ('ue_cap', ctypes.c_int32), ('grid_w', ctypes.c_int32), ('hist_cap', ctypes.c_int32),
                 ('stat_cap', ctypes.c_int32), ('clustered', ctypes.c_int32), ('cluster_lo', ctypes.c_int32), ('cluster_hi', ctypes.c_int32),
                 ('cluster_prob', ctypes.c_double), ('cluster_range', ctypes.c_double),
-                ('trace_cap', ctypes.c_int32), ('trace_mask', ctypes.c_int32), ('capture_effect', ctypes.c_int32), ('pad_conf', ctypes.c_int32)]
+                ('trace_cap', ctypes.c_int32), ('trace_mask', ctypes.c_int32), ('capture_effect', ctypes.c_int32), ('kernel', ctypes.c_int32)]
 
 
 # nbiot_trace_rec_t (include/nbiot_conf.h): one sample of PerfMonitor's lists
@@ -119,7 +119,10 @@ _KNOWN = {'ratio', 'M', 'buffer_range', 'reward_criteria', 'sort_criterium', 'le
 DEFAULT_STAT_CAP = 2048
 
 
-def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_cap=None, trace_cap=None, capture_effect=False):
+KERNEL_IDS = {None: 0, 'auto': 0, 'warp': 1, 'thread': 2, 'thread_voted': 3}      # NBIOT_KERNEL_* (include/nbiot_conf.h)
+
+
+def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_cap=None, trace_cap=None, capture_effect=False, kernel=None):
     """conf dict with the reference's keys and defaults (system_creator.py:24-44) -> NbiotConf."""
     unknown = set(conf) - _KNOWN
     if unknown:
@@ -176,6 +179,9 @@ def make_conf(conf, n_carriers=1, ue_cap=None, grid_w=1024, hist_cap=256, stat_c
     if not c.trace_cap:
         c.trace_mask = 0
     c.capture_effect = int(bool(capture_effect))        # Channel(capture_effect=True), channel.py:124-126
+    if kernel not in KERNEL_IDS:
+        raise ValueError(f'kernel must be one of {sorted(k for k in KERNEL_IDS if k)} or None')
+    c.kernel = KERNEL_IDS[kernel]
     # clustered placement (system_creator.py:41-44, population.py:57-63)
     c.clustered = int(bool(conf.get('clustered', False)))
     lo, hi = conf.get('cluster_ues', [10, 30])

@@ -108,6 +108,9 @@ def test_conf_validation():
     for bad in (dict(buffer_range=[100, 70000]), dict(buffer_range=[0, 10]), dict(M=0), dict(ratio=-0.1)):
         with pytest.raises(ValueError):
             make_conf(dict(base, **bad))
+    assert (make_conf(base).kernel, make_conf(base, kernel='warp').kernel, make_conf(base, kernel='thread_voted').kernel) == (0, 1, 3)      # NBIOT_KERNEL_*
+    with pytest.raises(ValueError):
+        make_conf(base, kernel='fastest')
     assert make_conf(dict(base, buffer_range=[300, 200])).buffer_lo == 300          # legal in the reference: every buffer is 300 (ue_generator.py:98-104)
 
 

@@ -671,3 +671,25 @@ def test_dealing_cells_to_sms_changes_nothing(monkeypatch):
         assert (env.records()['time'] >= 15000).all()
         env.close()
     assert np.array_equal(states[0], states[1])
+
+
+def test_kernel_selector_of_the_constructor(monkeypatch):
+    """BatchedNBIoTEnv(kernel=...) / nbiot_conf_t.kernel: which kernel runs the long advances; the state buffers do not depend on it"""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    monkeypatch.delenv('NBIOT_KERNEL', raising=False)
+    states, names = [], []
+    for kernel in (None, 'warp', 'thread', 'thread_voted'):
+        env = BatchedNBIoTEnv(CFG1, num_envs=70, seeds=list(range(70)), ue_cap=512, grid_w=2048, kernel=kernel)
+        env.reset()
+        env.run_until(12000)
+        torch.cuda.synchronize()
+        names.append(env.kernel_name())
+        hdr = env.L.nbiot_hdr_bytes(); tail = env.L.nbiot_hdr_task_bytes()
+        s = env.state.cpu().numpy().copy()
+        h = s[:70 * hdr].reshape(70, hdr); h[:, hdr - tail:] = 0      # the trailing task words only the task-chain kernels write
+        states.append(s); assert env.stats()['faulted'] == 0
+        env.close()
+    assert 'warp' in names[0] and 'warp' in names[1] and 'thread' in names[2] and 'voted' in names[3], names
+    for s in states[1:]:
+        assert np.array_equal(states[0], s)
