@@ -51,6 +51,15 @@ struct nbiot_handle {
     NbSimVariant k_tpc_gen, k_tpc_c1;        /* builds of the thread-per-cell kernel (nbiot_simt.cuh) */
     int use_tpc;                 /* long advances run on the thread-per-cell kernel: 1 plain, 2 voted dispatch (large batches) */
     int tpc_forced;              /* NBIOT_KERNEL=tpc|tpcv: every advance, short launches included (tests, measurements) */
+    /* NBIOT_KERNEL_AUTO on a batch large enough for the thread-per-cell kernel: a tiny kernel sums the live UEs of the batch in front of every
+     * long launch, BOTH simulation kernels are launched, and each looks at the sum: the thread-per-cell one runs while the mean is at most
+     * max_load live UEs per cell, the warp-per-cell one above it, the other returns at once (cells with long lists are warp-per-cell work at
+     * any batch size: profiles/r02_tpc_variants.txt section 16). Decided on the device, so a host that enqueues many steps ahead cannot make
+     * it stale; the sum is also copied back asynchronously, for nbiot_kernel_name only. */
+    int auto_kernel, load_pending, last_long_tpc;
+    double max_load;
+    unsigned long long *load_dev, *load_pin;
+    cudaEvent_t load_ev;
     int use_staged_builds;       /* measurement knob NBIOT_SIM_STAGED_BUILDS=0: staged launches on the ring-anywhere builds */
     int use_c1;                  /* single-carrier batch: the c1 build (the generic one while an event log is attached) */
     long long launches;
@@ -198,11 +207,25 @@ nbiot_deal_kernel(const NbHdr *hdr, const uint32_t *dur, const uint8_t *active, 
     }
 }
 
+/* live UEs of the batch (the load proxy of the automatic kernel choice) */
+__global__ void nbiot_load_kernel(const NbHdr *hdr, int n_inst, unsigned long long *out)
+{
+    unsigned long long acc = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_inst; i += gridDim.x * blockDim.x) {
+        const NbHdr *h = hdr + i;
+        int live = h->ue_count - (h->ue_departures[0] + h->ue_departures[1] + h->ue_departures[2]);
+        acc += (unsigned long long)(live > 0 ? live : 0);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 /* ------------------------------------------------------------------ host side */
 static NbKernelArgs make_args(nbiot_handle_t *h, int stage_grid = 1)
 {
     NbKernelArgs A;
     A.state = h->state; A.L = h->L; A.conf = h->conf_dev; A.ctrl = h->ctrl_dev; A.lut2 = h->lut2_dev; A.mcs = h->mcs_dev;
+    A.load_sum = nullptr; A.load_max = 0ull; A.load_side = 0;
     A.counter = h->counter_dev; A.prof = h->prof_dev; A.evlog = h->evlog; A.evlog_cap = h->evlog_cap;
     A.hdr_bytes16 = (int)(sizeof(NbHdr) / 16);
     A.grid_bytes16 = (int)((size_t)h->L.n_carriers * h->L.grid_w * 2 / 16);
@@ -230,15 +253,36 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
     int stage = h->stage_policy >= 0 ? h->stage_policy : !(mode == 2 && ext_actions && (h->ctrl.ext_state_mask & frequent));
     NbKernelArgs A = make_args(h, stage);
     int blocks = stage ? h->blocks : h->blocks_short, smem = stage ? h->smem_bytes : h->smem_short, hi = stage ? h->sim_hi : h->sim_hi_short;
-    if (mode == 2 && h->use_tpc && !h->evlog && (stage || h->tpc_forced)) {
+    int use_tpc = h->use_tpc;
+    const int both = mode == 2 && h->auto_kernel && stage && !h->evlog;      /* automatic choice: both kernels are launched, the load decides on the device */
+    if (both) {
+        if (h->load_pending && cudaEventQuery(h->load_ev) == cudaSuccess) {   /* for nbiot_kernel_name only: what an earlier long launch saw */
+            h->last_long_tpc = (double)*h->load_pin > h->max_load * (double)h->n_inst ? 0 : h->use_tpc;
+            h->load_pending = 0;
+        }
+        (void)cudaGetLastError();
+        CK(cudaMemsetAsync(h->load_dev, 0, sizeof(unsigned long long), st));
+        nbiot_load_kernel<<<296, 256, 0, st>>>((const NbHdr *)(h->state + h->L.off_hdr), h->n_inst, h->load_dev);
+        CK(cudaGetLastError());
+        h->launches += 1;
+        if (!h->load_pending) {
+            CK(cudaMemcpyAsync(h->load_pin, h->load_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(h->load_ev, st));
+            h->load_pending = 1;
+        }
+    }
+    if (mode == 2 && use_tpc && !h->evlog && (stage || h->tpc_forced)) {
         /* one thread per cell: header in local memory, ring / lists / UE records in place in HBM */
         NbKernelArgs T = make_args(h, 0);
+        if (both) { T.load_sum = h->load_dev; T.load_max = (unsigned long long)(h->max_load * (double)h->n_inst); T.load_side = 0; }
         const NbSimVariant *v = h->use_c1 ? &h->k_tpc_c1 : &h->k_tpc_gen;
         int threads = v->warps_per_block * 32;
         void *args[] = { (void *)&T, (void *)&ext_actions, (void *)&active, (void *)&until_time, (void *)&max_steps };
-        CK(cudaLaunchKernel(h->use_tpc == 2 ? v->sim_hi : v->sim_lo, dim3((h->n_inst + threads - 1) / threads), dim3(threads), args, 0, st));
+        CK(cudaLaunchKernel(use_tpc == 2 ? v->sim_hi : v->sim_lo, dim3((h->n_inst + threads - 1) / threads), dim3(threads), args, 0, st));
     }
-    else if (mode == 2) {
+    if (mode == 2 && both) { CK(cudaGetLastError()); h->launches += 1; }
+    if (mode == 2 && (both || !(use_tpc && !h->evlog && (stage || h->tpc_forced)))) {
+        if (both) { A.load_sum = h->load_dev; A.load_max = (unsigned long long)(h->max_load * (double)h->n_inst); A.load_side = 1; }
         const NbSimVariant *v = sim_variant(h, stage);
         if (stage && h->deal && blocks * NB_WPB >= h->n_inst) {     /* a long launch in one wave: deal the cells to the SMs by predicted cost */
             nbiot_deal_kernel<<<1, 1024, (size_t)h->deal_pad * sizeof(unsigned long long), st>>>((const NbHdr *)(h->state + h->L.off_hdr), h->dur_dev, active, h->n_inst,
@@ -250,7 +294,7 @@ static int launch_sim(nbiot_handle_t *h, int mode, const uint8_t *ext_actions, i
         if (stage) A.dur = h->dur_dev;
         void *args[] = { (void *)&A, (void *)&ext_actions, (void *)&active, (void *)&until_time, (void *)&max_steps };
         CK(cudaLaunchKernel(hi ? v->sim_hi : v->sim_lo, dim3(blocks), dim3(NB_WPB * 32), args, (size_t)smem, st));
-    } else {
+    } else if (mode != 2) {
         int construct = mode == 0 ? 1 : 0;
         const uint64_t *seeds = h->seeds_dev;
         void *args[] = { (void *)&A, (void *)&construct, (void *)&seeds };
@@ -351,6 +395,14 @@ int nbiot_create(const nbiot_conf_t *conf, int n_inst, int device, void *state_d
     if (conf->kernel == NBIOT_KERNEL_WARP) h->use_tpc = 0;
     else if (conf->kernel == NBIOT_KERNEL_THREAD) h->use_tpc = 1;
     else if (conf->kernel == NBIOT_KERNEL_THREAD_VOTED) h->use_tpc = 2;
+    h->auto_kernel = conf->kernel == NBIOT_KERNEL_AUTO && h->use_tpc && !getenv("NBIOT_KERNEL");
+    h->last_long_tpc = h->use_tpc;
+    h->max_load = getenv("NBIOT_TPC_MAX_LOAD") ? atof(getenv("NBIOT_TPC_MAX_LOAD")) : NB_TPC_MAX_LOAD;      /* measurement knob */
+    if (h->auto_kernel) {
+        CK(cudaMalloc(&h->load_dev, sizeof(unsigned long long)));
+        CK(cudaMallocHost(&h->load_pin, sizeof(unsigned long long)));
+        CK(cudaEventCreateWithFlags(&h->load_ev, cudaEventDisableTiming));
+    }
     if (const char *e = getenv("NBIOT_KERNEL")) {              /* measurement override: tpc / tpcv also take the short launches */
         if (!strcmp(e, "tpc")) { h->use_tpc = 1; h->tpc_forced = 1; }
         else if (!strcmp(e, "tpcv")) { h->use_tpc = 2; h->tpc_forced = 1; }
@@ -406,6 +458,8 @@ int nbiot_destroy(nbiot_handle_t *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    if (h->load_ev) cudaEventDestroy(h->load_ev);
+    cudaFree(h->load_dev); if (h->load_pin) cudaFreeHost(h->load_pin);
     cudaFree(h->conf_dev); cudaFree(h->ctrl_dev); cudaFree(h->lut2_dev); cudaFree(h->mcs_dev); cudaFree(h->seeds_dev); cudaFree(h->counter_dev); cudaFree(h->prof_dev); cudaFree(h->blk_dev); cudaFree(h->dur_dev); cudaFree(h->deal_order); cudaFree(h->deal_len); cudaFree(h->deal_cnt);
     cudaFree(h->act_dev); cudaFree(h->obs_dev); cudaFree(h->rew_dev); cudaFree(h->items_dev);
     cudaFreeHost(h->act_pin); cudaFreeHost(h->obs_pin); cudaFreeHost(h->rew_pin);
@@ -642,7 +696,8 @@ int nbiot_launch_geometry(nbiot_handle_t *h, int *blocks, int *warps_per_block, 
 const char *nbiot_kernel_name(nbiot_handle_t *h)
 {
     if (!h) return "";
-    return h->use_tpc == 2 ? "thread-per-cell, voted dispatch (long launches)" : h->use_tpc ? "thread-per-cell (long launches)" : "warp-per-cell";
+    int t = h->auto_kernel ? h->last_long_tpc : h->use_tpc;      /* automatic choice: what the last long launch ran on */
+    return t == 2 ? "thread-per-cell, voted dispatch (long launches)" : t ? "thread-per-cell (long launches)" : "warp-per-cell";
 }
 
 double nbiot_rng_u01(uint64_t seed, uint64_t ctr, uint32_t stream) { return nb_rng_u01(seed, ctr, stream); }

@@ -16,6 +16,10 @@ struct NbKernelArgs {
     const NbCtaConst *ctrl;      /* controller tables + cold configuration */
     const uint16_t *lut2;
     const uint8_t *mcs;
+    /* automatic kernel choice, decided on the device so that it is never stale: load_sum = live UEs of the batch (nbiot_load_kernel, launched
+     * just before); a kernel launched with load_side 0 runs only while load_sum <= load_max (light cells: thread-per-cell), with load_side 1
+     * only above it (warp-per-cell); the other one returns at once. NULL: unconditional. */
+    const unsigned long long *load_sum; unsigned long long load_max; int load_side;
     unsigned int *counter;          /* [0] claim counter, [1 .. NB_SM_HINTS] per-SM class hints (-DNB_TPC_AFFINITY_SM builds of the voted kernel) */
     unsigned long long *prof;    /* optional (NBIOT_PROF_INST=1): per instance { start ns, end ns, SM id, 0 } of the last launch (measurement aid) */
     int32_t *evlog; int evlog_cap;
@@ -83,6 +87,11 @@ void nb_sim_variant_tpc_gen(NbSimVariant *out);
 void nb_sim_variant_tpc_c1(NbSimVariant *out);
 #ifndef NB_TPC_MIN_CELLS
 #define NB_SM_HINTS 256
+#define NB_NOT_MY_LOAD(A) ((A).load_sum && ((*(A).load_sum > (A).load_max) != ((A).load_side == 1)))
+#ifndef NB_TPC_MAX_LOAD
+#define NB_TPC_MAX_LOAD 140.0     /* mean live UEs per cell above which a long launch runs on the warp-per-cell kernel (27: 2.9e9 against 1.4e9; 166: 0.87e9
+                                     against 1.01e9; thresholds 40 / 70 / 100 / 140 / 200 on the bursty scenario at 65 536 cells: 1.23 / 1.28 / 1.30 / 1.36 / 1.35e9) */
+#endif
 #define NB_TPC_MIN_CELLS 32768      /* batches from this size on advance on the thread-per-cell kernel */
 #endif
 

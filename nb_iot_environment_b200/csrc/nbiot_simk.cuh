@@ -119,6 +119,7 @@ template <int MINB>
 __global__ void __launch_bounds__(NB_WPB * 32, MINB)
 nbiot_sim_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps)
 {
+    if (NB_NOT_MY_LOAD(A)) return;                     /* automatic kernel choice: this launch belongs to the other kernel */
     nb_for_each_instance<true>(A, active, [&](NbCtx &c, int i) {
         nbc_controller_advance(c, c.ctrl, ext_actions ? ext_actions + (size_t)i * c.ctrl->ext_k : nullptr, until_time, max_steps);
     });

@@ -55,6 +55,7 @@ struct __align__(16) NbLocal { NbCtx c; NbHdr h; };      /* nbc_hdr(c) = the byt
 __global__ void __launch_bounds__(NB_TPC_THREADS, NB_TPC_MIN_CTAS)
 nbiot_simt_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps)
 {
+    if (NB_NOT_MY_LOAD(A)) return;
     __shared__ NbCtaConst s_ctrl;                      /* the controller tables + cold configuration, once per CTA */
     for (int k = threadIdx.x; k < (int)(sizeof(NbCtaConst) / 4); k += blockDim.x) ((uint32_t *)&s_ctrl)[k] = ((const uint32_t *)A.ctrl)[k];
     __syncthreads();
@@ -97,6 +98,7 @@ nbiot_simt_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *act
 __global__ void __launch_bounds__(NB_TPC_THREADS, NB_TPC_MIN_CTAS)
 nbiot_simtv_kernel(NbKernelArgs A, const uint8_t *ext_actions, const uint8_t *active, int until_time, int max_steps)
 {
+    if (NB_NOT_MY_LOAD(A)) return;                     /* automatic kernel choice: this launch belongs to the other kernel */
     __shared__ NbCtaConst s_ctrl;
 #if NB_TPC_AFFINITY > 0
     /* Class affinity. Both kernels of this library are short of instruction FETCH, and the two SMs of a TPC share the instruction cache behind

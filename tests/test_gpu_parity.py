@@ -693,3 +693,46 @@ def test_kernel_selector_of_the_constructor(monkeypatch):
     assert 'warp' in names[0] and 'warp' in names[1] and 'thread' in names[2] and 'voted' in names[3], names
     for s in states[1:]:
         assert np.array_equal(states[0], s)
+
+
+def test_automatic_kernel_choice_follows_the_load(monkeypatch):
+    """kernel=None on a batch large enough for the thread-per-cell kernel: the mean number of live UEs per cell, read back behind every long
+    launch on the device, decides which of the two kernels runs it -- lightly loaded cells stay on the voted thread-per-cell kernel, cells with long lists go to
+    the warp-per-cell kernel (profiles/r02_tpc_variants.txt section 16). The choice never changes a result (sampled cells against the oracle)."""
+    import torch
+    from nb_iot_environment_b200 import BatchedNBIoTEnv
+    from oracle_controller import OracleController
+    monkeypatch.delenv('NBIOT_KERNEL', raising=False)
+    N = 32768
+    # light: configs[0] traffic on the default agents
+    env = BatchedNBIoTEnv(CFG1, num_envs=N, seeds=list(range(N)), ue_cap=256, grid_w=1024, hist_cap=64)
+    env.reset()
+    for T in (3000, 6000, 9000):
+        env.run_until(T)
+        torch.cuda.synchronize()
+    assert 'voted' in env.kernel_name() and env.stats()['faulted'] == 0
+    env.close()
+    # loaded: the NPRACH scenario of bench.py (bursty traffic, 100+ live UEs per cell after the first bursts)
+    conf = dict(CFG1, ratio=0.5)
+    env = BatchedNBIoTEnv(conf, agents_conf=NPRACH_AGENTS, ext_agent=3, num_envs=N, seeds=list(range(N)), ue_cap=1000, grid_w=2048, hist_cap=512)
+    env.reset()
+    r = np.random.default_rng(11)
+    a = _random_ext_actions(r, env.action_nvec, 1)
+    a[:, 0] = np.minimum(a[:, 0], a[:, 1])
+    acts = np.repeat(a, N, axis=0)
+    names = []
+    for k in range(6):
+        env.step(acts)
+        torch.cuda.synchronize()
+        names.append(env.kernel_name())
+    st = env.stats()
+    assert st['faulted'] == 0 and st['live_ues'] / N > 140, st        # NB_TPC_MAX_LOAD
+    assert 'voted' in names[0] and any('warp' in n for n in names[1:]), names
+    recs = env.records()
+    for i in (0, 1, N // 2, N - 1):
+        c = OracleController(conf, i, agents_conf=NPRACH_AGENTS, ext_agent=3)
+        c.reset()
+        for k in range(6):
+            c.step(acts[i])
+        assert not record_diff(c.rec, recs[i], rtol=0.0), i
+    env.close()
