@@ -1396,6 +1396,19 @@ NB_FN1S void nbc_conn_remove(NbCtx &c, int slot)
             if (m) { idx = base + nbw_ffs(m) - 1; break; }
         }
         if (idx < 0) return -1;
+#if NB_LANES == 1 && !defined(NB_CONN_SHIFT_1)
+        /* one lane owns the cell and shifts a sorted queue of up to hundreds of 16-byte entries: two loads in flight per step. +19 % on cells
+         * with 150-300 live UEs, -0.4 % on lightly loaded ones; four in flight, or the same in nbc_conn_insert, cost the lightly loaded cells
+         * 1.3-3.5 % in code size for no more (profiles/r02_tpc_variants.txt section 18) */
+        int lo = idx;
+        NB_NOUNROLL
+        for (; lo + 2 <= n - 1; lo += 2) {
+            NbConnEntry a = Q[lo + 1], b = Q[lo + 2];
+            Q[lo] = a; Q[lo + 1] = b;
+        }
+        NB_NOUNROLL
+        for (; lo < n - 1; ++lo) Q[lo] = Q[lo + 1];
+#else
         NB_NOUNROLL
         for (int base = idx; base < n - 1; base += NB_LANES) {
             int i = base + nbw_lane();
@@ -1405,6 +1418,7 @@ NB_FN1S void nbc_conn_remove(NbCtx &c, int slot)
             if (i < n - 1) Q[i] = m;
             nbw_sync();
         }
+#endif
         return idx;
     });
     if (found >= 0) h->conn_n = n - 1;
